@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""Headline benchmark: GAT layer fwd+bwd edges/sec (BASELINE.json metric) + achieved HBM GB/s vs peak.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload powerlaw_200m|elliptic|skew] [--impl reference]
+
+A "step" is one GATConv layer (H=8, C=64, concat=False, bias, dropout off) forward + backward over the
+whole synthetic graph, CSR cached (its build is reported separately).  Default workload at N=1 is the
+configuration the metric's target is quoted on: the 200M-edge / 20M-node power-law graph, K=166
+(BASELINE.json configs[3], "powerlaw_200m"); it fits one B200 (~125 GB).  One JSON line on stdout (rank 0).
+
+`--impl reference` times the reference formulation (PyG GATConv semantics: the CPU oracle port, since
+torch_geometric is not installable in this image) on the host cores, on a bounded sample of the same
+workload family.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "gat_layer_fwd_bwd_edges_per_sec"
+UNIT = "edges/s"
+H, C = 8, 64
+
+WORKLOADS = {
+    # name: (N, E, K)
+    "powerlaw_200m": (20_000_000, 200_000_000, 166),
+    "powerlaw_20m": (2_000_000, 20_000_000, 166),
+    "elliptic": (203_769, 234_355, 166),
+    "skew": (1_000_000, 5_000_000 + 16 * 131_072 + 64_000, 166),
+}
+CPU_SAMPLE = (50_000, 500_000, 166)   # 1/400-scale power-law graph for the CPU arm (bounded sample)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def make_edges(workload: str, N: int, E: int, device):
+    from gnn_fraud_detection_b200 import synth
+    if workload.startswith("powerlaw"):
+        return synth.powerlaw_graph(N, E, seed=1234, device=device)
+    if workload == "elliptic":
+        return synth.elliptic_synth(N, E, 1, seed=0, device=device)[1]
+    if workload == "skew":
+        return synth.fraud_ring_skew(num_nodes=N, seed=7, device=device)
+    raise ValueError(workload)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (pynvml; nvidia-smi fallback)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _loop(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self._h is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (reference formulation = oracle port)
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(N, E, K, threads):
+    """Returns (step_fn, description).  Only bench.py's cpu_baseline / --impl reference legs use the oracle."""
+    from gnn_fraud_detection_b200 import synth
+    from oracle import pyg_gatconv as O
+    torch.set_num_threads(threads)
+    kind = "port"
+    ei = synth.powerlaw_graph(N, E, seed=1234, device="cpu")
+    x = torch.randn(N, K, generator=torch.Generator().manual_seed(0))
+    torch.manual_seed(1)
+    conv = O.OracleGATConv(K, C, heads=H, concat=False, dropout=0.0)
+    if O.real_pyg_available():      # never true in this image; kept so the arm uses the real thing if it appears
+        from torch_geometric.nn import GATConv as PygGATConv
+        conv = PygGATConv(K, C, heads=H, concat=False, dropout=0.0)
+        kind = "reference"
+    d_out = torch.ones(N, C) / N
+
+    def step():
+        for p in conv.parameters():
+            p.grad = None
+        out = conv(x, ei)
+        out.backward(d_out)
+        return float(out[0, 0].detach())
+
+    return step, kind, f"power-law graph N={N} E={E} K={K} (1/{200_000_000 // E}-scale powerlaw_200m), one GATConv fwd+bwd"
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    N, E, K = CPU_SAMPLE
+    step, kind, sample = cpu_reference_step_fn(N, E, K, threads)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = E / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "reference_sample": sample, "H": H, "C": C, "K": K,
+                   "note": "reference = PyG GATConv formulation on host cores; torch_geometric is absent from "
+                           "this image so the CPU oracle port (oracle/pyg_gatconv.py) is what runs"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    from gnn_fraud_detection_b200 import GATConv, _abi, build_csr, functional as Fn, roofline, synth
+    from gnn_fraud_detection_b200.graph import GLOBAL_CSR_CACHE
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product path has no CPU fallback); use --impl reference "
+                         "for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from gnn_fraud_detection_b200 import partition
+    L = _abi.lib()
+
+    workload = args.workload
+    N, E, K = WORKLOADS[workload]
+    free_b, total_b = torch.cuda.mem_get_info()
+    note = None
+    if workload == "powerlaw_200m" and world == 1 and free_b < 140e9:
+        workload, note = "powerlaw_20m", f"only {free_b / 1e9:.0f} GB free: fell back from powerlaw_200m"
+        N, E, K = WORKLOADS[workload]
+
+    # ---- inputs, resident in HBM before the timed region ------------------------------------------
+    t_gen = time.perf_counter()
+    ei = make_edges(workload, N, E, dev)
+    E = ei.size(1)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    torch.manual_seed(1)
+    conv = GATConv(K, C, heads=H, concat=False, dropout=0.0, gemm_algo=args.algo,
+                   feature_dtype=torch.bfloat16 if args.bf16 else torch.float32).to(dev)
+    W = conv.lin_src.weight.detach()
+    a_s, a_d = conv.att_src.detach().view(-1).contiguous(), conv.att_dst.detach().view(-1).contiguous()
+    bias = conv.bias.detach()
+    xw_dtype = conv.feature_dtype
+
+    if world == 1:
+        x = torch.randn(N, K, device=dev, generator=gen)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        g = build_csr(ei, N)
+        torch.cuda.synchronize()
+        csr_ms = (time.perf_counter() - t0) * 1e3
+        Ep = g.n_edges
+        d_out = torch.full((N, C), 1.0 / N, device=dev)      # timing only; parity runs use randn/N
+        n_local, part = N, None
+    else:
+        part = partition.DstRangePartition.build(ei, N, rank, world, dev)
+        del ei
+        g, Ep, n_local = part.graph, part.graph.n_edges, part.n_local
+        csr_ms = part.build_ms
+        x = torch.randn(part.rows_padded, K, device=dev, generator=gen)   # this rank's rows of x
+        d_out = torch.full((n_local, C), 1.0 / N, device=dev)
+    gen_s = time.perf_counter() - t_gen
+
+    stages = ["project_fwd", "gat_fwd", "gat_bwd_dst_src", "project_bwd"]
+    ev = {}
+
+    def step(timed: bool):
+        """One layer fwd+bwd through the C ABI stage calls (exactly what GATConvFunction issues)."""
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] if timed else None
+        if timed:
+            marks[0].record()
+        if part is None:
+            xw, a_src, a_dst = Fn.project_fwd(x, W, a_s, a_d, H, C, xw_dtype, args.algo)
+            if timed: marks[1].record()
+            out, rowmax, rowsum = Fn.gat_fwd(g, xw, a_src, a_dst, bias, H, C, 0.2, False)
+            if timed: marks[2].record()
+            dxw, da_src, da_dst = Fn.gat_bwd(g, xw, a_src, a_dst, rowmax, rowsum, d_out, a_s, a_d, H, C, 0.2, False)
+            if timed: marks[3].record()
+            grads = Fn.project_bwd(x, W, dxw, xw, da_src, da_dst, d_out, H, C, C, False, args.algo)
+            if timed: marks[4].record()
+        else:
+            out, grads = part.layer_fwd_bwd(x, W, a_s, a_d, bias, d_out, H, C, xw_dtype, args.algo, marks)
+        return out, grads, marks
+
+    for _ in range(max(args.warmup, 3)):
+        step(False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    L.gnnfd_launch_count_reset()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    all_marks = []
+    e_start.record()
+    for _ in range(args.steps):
+        _, _, marks = step(True)
+        all_marks.append(marks)
+    e_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    launches = int(L.gnnfd_launch_count())
+    total_ms = e_start.elapsed_time(e_end)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    stage_ms = {s: statistics.mean(m[i].elapsed_time(m[i + 1]) for m in all_marks) for i, s in enumerate(stages)}
+
+    # ---- roofline ------------------------------------------------------------------------------------
+    peak, peak_src = load_peaks()
+    s_bytes = 2 if args.bf16 else 4
+    E_total = E
+    if world > 1:
+        te = torch.tensor([float(Ep)], device=dev)
+        dist.all_reduce(te)
+        Ep_total = int(te.item())
+    else:
+        Ep_total = Ep
+    bmodel = roofline.stage_bytes(N, Ep_total, K, H, C, False, s_bytes, need_dx=False)
+    local = roofline.stage_bytes(n_local, Ep, K, H, C, False, s_bytes, need_dx=False, n_src=(N if world > 1 else None))
+    # dominant kernel = the forward fused softmax/aggregation kernel (one launch per step on this rank)
+    dom_bytes = local["gat_fwd"]
+    dom_ms = stage_ms["gat_fwd"]
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "gat_fwd_rows (+hub chunks/merge)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+            "layer": {"algorithmic_bytes": bmodel["total"], "achieved": bmodel["total"] / (ms_per_step * 1e-3) / 1e9 / world,
+                      "frac": bmodel["total"] / (ms_per_step * 1e-3) / 1e9 / world / peak},
+            "stages_ms": stage_ms,
+            "stages_gbs": {"project_fwd": local["project_fwd"] / stage_ms["project_fwd"] / 1e6,
+                           "gat_fwd": local["gat_fwd"] / stage_ms["gat_fwd"] / 1e6,
+                           "gat_bwd_dst_src": (local["gat_bwd_dst"] + local["gat_bwd_src"]) / stage_ms["gat_bwd_dst_src"] / 1e6,
+                           "project_bwd": local["project_bwd"] / stage_ms["project_bwd"] / 1e6}}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            roof["traffic"] = json.load(open(traffic_file)).get(workload, {}).get("gat_fwd_rows")
+        except Exception:
+            pass
+
+    value = E_total / (ms_per_step * 1e-3)
+
+    # ---- e2e: public API (GATConv module) with HOST buffers, copies inside the timed region ----------
+    e2e = None
+    if not args.no_e2e:
+        if world == 1:
+            # stage the inputs in pinned host memory, then release the device-resident copies
+            x_host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x)
+            ei_host = torch.empty(ei.shape, dtype=ei.dtype, pin_memory=True).copy_(ei)
+            torch.cuda.synchronize()
+            del x, ei, g, d_out, all_marks
+            GLOBAL_CSR_CACHE.clear()
+            torch.cuda.empty_cache()
+            e2e = run_e2e(args, conv, x_host, ei_host, N, E_total, dev)
+        else:
+            e2e = part.e2e(args, conv, x, N, E_total, K, dev)
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only) -------------------------------------------
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        cn, ce, ck = CPU_SAMPLE
+        cstep, kind, sample = cpu_reference_step_fn(cn, ce, ck, threads)
+        cstep()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            cstep()
+        cdt = (time.perf_counter() - t0) / reps
+        cpu = {"value": ce / cdt, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+               "ms_per_step": cdt * 1e3}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16-storage/f32-accum" if args.bf16 else "f32", "data": "synthetic",
+            "config": {"workload": workload, "nodes": N, "edges": E_total, "edges_after_self_loop_rewrite": Ep_total,
+                       "in_features": K, "heads": H, "out_channels": C, "concat": False,
+                       "l2": "inputs larger than L2 (xw %.1f GB per pass)" % (N * H * C * s_bytes / 1e9),
+                       "parallelism": "1 GPU" if world == 1 else f"dst-range x{world}, NCCL all-gather of projected features",
+                       "csr_build_ms": csr_ms, "setup_s": gen_s, "gemm_algo": args.algo, "note": note},
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, conv, x_host, ei_host, N, E_total, dev):
+    """Same metric through the drop-in module with pinned HOST inputs: every step copies x and edge_index to
+    the device (src/train.py:105 `batch.to(device)`), rebuilds the CSR (a fresh edge_index tensor, exactly as
+    the reference's per-call self-loop rewrite), runs forward + backward, and reads the loss and the
+    parameter gradients back (src/train.py:146-149)."""
+    from gnn_fraud_detection_b200.graph import GLOBAL_CSR_CACHE
+    steps = max(1, min(args.steps, args.e2e_steps))
+    w_scale = 1.0 / N
+
+    def one():
+        GLOBAL_CSR_CACHE.clear()
+        xd = x_host.to(dev, non_blocking=True)
+        ed = ei_host.to(dev, non_blocking=True)
+        for p in conv.parameters():
+            p.grad = None
+        out = conv(xd, ed)
+        loss = out.sum() * w_scale
+        loss.backward()
+        res = [loss.detach().cpu()] + [p.grad.cpu() for p in conv.parameters()]
+        return res
+
+    one()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        res = one()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    GLOBAL_CSR_CACHE.clear()
+    h2d = x_host.numel() * x_host.element_size() + ei_host.numel() * ei_host.element_size()
+    d2h = sum(t.numel() * t.element_size() for t in res)
+    return {"value": E_total / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+            "ms_per_step": dt * 1e3, "includes": "H2D of x+edge_index, CSR/CSC rebuild, fwd+bwd, D2H of loss+grads"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="powerlaw_200m", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", type=int, default=0, help="projection GEMM: 0 auto, 1 fp32 SIMT, 2 tensor core")
+    ap.add_argument("--bf16", action="store_true", help="bf16 storage of projected features")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

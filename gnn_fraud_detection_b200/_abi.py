@@ -1,0 +1,105 @@
+"""ctypes binding of ``libgnnfd_b200.so`` (the C ABI declared in ``include/gnnfd_b200.h``).
+
+There is no fallback: if the shared library is missing or fails to load, importing the product path
+raises.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` (or ``make -C
+gnn_fraud_detection_b200/csrc``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgnnfd_b200.so")
+
+# enums (mirror include/gnnfd_b200.h)
+ADD_SELF_LOOPS, BUILD_CSC = 1, 2
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
+HUB_THRESHOLD, HUB_CHUNK = 512, 512
+ABI_VERSION = 1
+
+_i32p = C.POINTER(C.c_int32)
+
+
+class HubPlan(C.Structure):
+    _fields_ = [("n_hub", C.c_int32), ("n_chunk", C.c_int32), ("threshold", C.c_int32), ("chunk", C.c_int32),
+                ("hub_row", C.c_void_p), ("hub_chunk_ptr", C.c_void_p), ("chunk_hub", C.c_void_p)]
+
+
+class Graph(C.Structure):
+    _fields_ = [("n_dst", C.c_int64), ("n_src", C.c_int64), ("n_edges", C.c_int64),
+                ("rowptr", C.c_void_p), ("col", C.c_void_p), ("perm", C.c_void_p),
+                ("colptr", C.c_void_p), ("csc_row", C.c_void_p), ("csc_eid", C.c_void_p),
+                ("hub_dst", HubPlan), ("hub_src", HubPlan)]
+
+
+# name -> (restype, argtypes); every symbol include/gnnfd_b200.h declares
+_vp, _sz, _i64, _i, _f = C.c_void_p, C.c_size_t, C.c_int64, C.c_int, C.c_float
+_szp, _i64p, _gp = C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(Graph)
+SIGNATURES = {
+    "gnnfd_last_error": (C.c_char_p, []),
+    "gnnfd_abi_version": (_i, []),
+    "gnnfd_sizeof_graph": (_sz, []),
+    "gnnfd_sizeof_hub_plan": (_sz, []),
+    "gnnfd_launch_count": (_i64, []),
+    "gnnfd_launch_count_reset": (None, []),
+    "gnnfd_csr_workspace_bytes": (_i, [_i64, _i64, _i, _szp]),
+    "gnnfd_csr_build": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64p, _vp, _sz, _vp]),
+    "gnnfd_hub_plan_workspace_bytes": (_i, [_i64, _szp]),
+    "gnnfd_hub_plan": (_i, [_vp, _i64, C.c_int32, C.c_int32, _vp, _vp, _vp, _i64, _i64, _i64p, _vp, _sz, _vp]),
+    "gnnfd_project_workspace_bytes": (_i, [_i64, _i64, _i, _i, _i, _szp]),
+    "gnnfd_project_fwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gnnfd_gat_fwd_workspace_bytes": (_i, [_gp, _i, _i, _szp]),
+    "gnnfd_gat_fwd": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gnnfd_gat_alpha": (_i, [_gp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
+    "gnnfd_gat_bwd_workspace_bytes": (_i, [_gp, _i, _i, _szp]),
+    "gnnfd_gat_bwd_dst": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _f, _vp, _vp, _vp, _vp,
+                               _sz, _vp]),
+    "gnnfd_gat_bwd_src": (_i, [_gp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "gnnfd_project_bwd_workspace_bytes": (_i, [_i64, _i64, _i, _i, _i, _szp]),
+    "gnnfd_project_bwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp,
+                               _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+}
+
+
+class GnnfdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libgnnfd_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and type the shared library.  Raises if it is missing -- there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is required (no CPU/PyTorch fallback). "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'`.")
+    l = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(l, name)  # AttributeError => a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if l.gnnfd_abi_version() != ABI_VERSION:
+        raise ImportError(f"libgnnfd_b200 ABI {l.gnnfd_abi_version()} != binding {ABI_VERSION}; rebuild")
+    if l.gnnfd_sizeof_graph() != C.sizeof(Graph) or l.gnnfd_sizeof_hub_plan() != C.sizeof(HubPlan):
+        raise ImportError("gnnfd_graph_t layout mismatch between header and ctypes binding")
+    _lib = l
+    return l
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise GnnfdError(rc, lib().gnnfd_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t) -> int:
+    """data_ptr of a tensor or 0 for None."""
+    return 0 if t is None else t.data_ptr()

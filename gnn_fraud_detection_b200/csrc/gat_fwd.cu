@@ -1,0 +1,431 @@
+// (3) fused LeakyReLU + online segment softmax + alpha-weighted neighbour gather-sum (forward).
+//
+// Replaces edge_update + message + aggregate + head mean/concat + bias of PyG's GATConv.forward at the
+// reference call sites src/models/gat.py:80 / src/models/tgn.py:94.
+// One warp per destination row.  Per chunk of 32 edges:
+//   phase A  lane = edge: gather the source logits (32 B), LeakyReLU, chunk max / sum by warp shuffles,
+//            online-softmax rescale of the running (m, s, acc); exp() is evaluated once per (edge, head)
+//            and the weights are staged in shared memory;
+//   phase B  lane = feature slot: every edge's 2 KB (fp32) / 1 KB (bf16) source row is read with
+//            fully coalesced 128-bit loads, four edges in flight per warp, FMA into 16 accumulators.
+// Rows longer than the hub threshold are split edge-balanced into chunks (one warp each) whose partial
+// (m, s, acc) are merged in chunk order by the online-softmax combine rule -- deterministic.
+#include "gat_common.cuh"
+
+#include <atomic>
+#include <climits>
+
+namespace gnnfd {
+extern std::atomic<long long> g_launches;
+
+constexpr int FWD_U = 4;  // edges in flight per warp in phase B
+
+template <class GE, bool DROPOUT>
+__device__ __forceinline__ void fwd_range(int beg, int end, const int32_t* __restrict__ col,
+                                          const int32_t* __restrict__ perm,
+                                          const typename GE::XT* __restrict__ xw,
+                                          const float* __restrict__ a_src, const float (&adst)[GE::H], float slope,
+                                          const uint8_t* __restrict__ keep, float keep_scale, float (&m)[GE::H],
+                                          float (&s)[GE::H], float (&acc)[GE::NS][GE::VW], float* p_s, int* j_s,
+                                          int lane)
+{
+    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP, D = GE::D;
+    const int sub = lane / GE::G;
+    for (int base = beg; base < end; base += 32) {
+        const int n = min(32, end - base);
+        float e[H], kp[H];
+        int j = 0;
+        if (lane < n) {
+            j = col[base + lane];
+            float as[H];
+            load_vecH<H>(a_src + int64_t(j) * H, as);
+#pragma unroll
+            for (int h = 0; h < H; ++h) e[h] = leaky(as[h] + adst[h], slope);
+            if (DROPOUT) {
+                const uint8_t* kb = keep + int64_t(perm[base + lane]) * H;
+#pragma unroll
+                for (int h = 0; h < H; ++h) kp[h] = kb[h] ? keep_scale : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int h = 0; h < H; ++h) { e[h] = -INFINITY; kp[h] = 0.f; }
+        }
+        float sc[H], w[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float mn = fmaxf(m[h], warp_max(e[h]));
+            sc[h] = expf(m[h] - mn);
+            const float p = (lane < n) ? expf(e[h] - mn) : 0.f;
+            s[h] = s[h] * sc[h] + warp_sum(p);
+            m[h] = mn;
+            w[h] = DROPOUT ? p * kp[h] : p;
+        }
+        store_vecH<H>(p_s + lane * H, w);
+        j_s[lane] = j;
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const float f = pick<HP>(sc, q, sub);
+#pragma unroll
+            for (int k = 0; k < VW; ++k) acc[q][k] *= f;
+        }
+        __syncwarp();
+        for (int t = 0; t < n; t += FWD_U) {
+            float v[FWD_U][NS][VW], wq[FWD_U][NS];
+#pragma unroll
+            for (int u = 0; u < FWD_U; ++u) {
+                const bool ok = t + u < n;
+                const int tt = ok ? t + u : t;
+                const typename GE::XT* row = xw + int64_t(j_s[tt]) * D;
+#pragma unroll
+                for (int q = 0; q < NS; ++q) {
+                    if (ok) load_slot(row, q, lane, v[u][q]);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < VW; ++k) v[u][q][k] = 0.f;
+                    }
+                    wq[u][q] = ok ? p_s[tt * H + q * HP + sub] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < FWD_U; ++u)
+#pragma unroll
+                for (int q = 0; q < NS; ++q)
+#pragma unroll
+                    for (int k = 0; k < VW; ++k) acc[q][k] = fmaf(wq[u][q], v[u][q][k], acc[q][k]);
+        }
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ float apply_act(float v, int act)
+{
+    if (act == GNNFD_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == GNNFD_ACT_ELU) return v > 0.f ? v : expm1f(v);
+    return v;
+}
+
+// normalise by the softmax denominator, save the row statistics, head mean/concat + bias + activation
+template <class GE, bool CONCAT>
+__device__ __forceinline__ void fwd_epilogue(int64_t i, const float (&m)[GE::H], const float (&s)[GE::H],
+                                             float (&acc)[GE::NS][GE::VW], const float* __restrict__ bias, int act,
+                                             float* __restrict__ out, float* __restrict__ rowmax,
+                                             float* __restrict__ rowsum, int lane)
+{
+    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP, D = GE::D, C = GE::C, G = GE::G;
+    const int sub = lane / G;
+    float st[H], inv[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        st[h] = s[h] + 1e-16f;   // PyG softmax: out / (sum + 1e-16)
+        inv[h] = 1.f / st[h];
+    }
+    if (lane == 0) {
+        store_vecH<H>(rowmax + i * H, m);
+        store_vecH<H>(rowsum + i * H, st);
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        const float f = pick<HP>(inv, q, sub);
+#pragma unroll
+        for (int k = 0; k < VW; ++k) acc[q][k] *= f;
+    }
+    if (CONCAT) {
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const int c0 = VW * (lane + 32 * q);
+            float r[VW];
+#pragma unroll
+            for (int k = 0; k < VW; ++k) r[k] = apply_act(acc[q][k] + (bias ? bias[c0 + k] : 0.f), act);
+#pragma unroll
+            for (int k = 0; k < VW; k += 4)
+                stg_stream(reinterpret_cast<float4*>(out + i * D + c0 + k), make_float4(r[k], r[k + 1], r[k + 2], r[k + 3]));
+        }
+    } else {
+        float r[VW];
+#pragma unroll
+        for (int k = 0; k < VW; ++k) {
+            r[k] = 0.f;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) r[k] += acc[q][k];
+#pragma unroll
+            for (int o = G; o < 32; o <<= 1) r[k] += __shfl_xor_sync(FULL, r[k], o);
+        }
+        if (sub == 0) {
+            const int c0 = VW * lane;  // lane < G here
+#pragma unroll
+            for (int k = 0; k < VW; ++k) r[k] = apply_act(r[k] * (1.f / H) + (bias ? bias[c0 + k] : 0.f), act);
+#pragma unroll
+            for (int k = 0; k < VW; k += 4)
+                stg_stream(reinterpret_cast<float4*>(out + i * C + c0 + k), make_float4(r[k], r[k + 1], r[k + 2], r[k + 3]));
+        }
+    }
+}
+
+template <class GE, bool CONCAT, bool DROPOUT>
+__global__ void __launch_bounds__(ROW_THREADS)
+gat_fwd_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+             const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+             const float* __restrict__ a_dst, const float* __restrict__ bias, int64_t n_dst, int hub_threshold,
+             float slope, int act, const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ out,
+             float* __restrict__ rowmax, float* __restrict__ rowsum)
+{
+    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW;
+    __shared__ __align__(16) float p_sh[ROW_WARPS][32 * H];
+    __shared__ int j_sh[ROW_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = int64_t(blockIdx.x) * ROW_WARPS + warp;
+    if (i >= n_dst) return;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    if (end - beg > hub_threshold) return;  // split rows are produced by the hub kernels
+    float adst[H], m[H], s[H], acc[NS][VW];
+    load_vecH<H>(a_dst + i * H, adst);
+#pragma unroll
+    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; }
+#pragma unroll
+    for (int q = 0; q < NS; ++q)
+#pragma unroll
+        for (int k = 0; k < VW; ++k) acc[q][k] = 0.f;
+    fwd_range<GE, DROPOUT>(beg, end, col, perm, xw, a_src, adst, slope, keep, keep_scale, m, s, acc, p_sh[warp],
+                           j_sh[warp], lane);
+    fwd_epilogue<GE, CONCAT>(i, m, s, acc, bias, act, out, rowmax, rowsum, lane);
+}
+
+// one warp per (hub row, chunk): partial (m, s, unnormalised acc)
+template <class GE, bool DROPOUT>
+__global__ void __launch_bounds__(ROW_THREADS)
+gat_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                   const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+                   const float* __restrict__ a_dst, gnnfd_hub_plan_t plan, float slope,
+                   const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ part_ms,
+                   float* __restrict__ part_acc)
+{
+    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, D = GE::D;
+    __shared__ __align__(16) float p_sh[ROW_WARPS][32 * H];
+    __shared__ int j_sh[ROW_WARPS][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * ROW_WARPS + warp;
+    if (c >= plan.n_chunk) return;
+    const int slot = plan.chunk_hub[c];
+    const int64_t i = plan.hub_row[slot];
+    const int k = c - plan.hub_chunk_ptr[slot];
+    const int beg = rowptr[i] + k * plan.chunk;
+    const int end = min(rowptr[i + 1], beg + plan.chunk);
+    float adst[H], m[H], s[H], acc[NS][VW];
+    load_vecH<H>(a_dst + i * H, adst);
+#pragma unroll
+    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; }
+#pragma unroll
+    for (int q = 0; q < NS; ++q)
+#pragma unroll
+        for (int kk = 0; kk < VW; ++kk) acc[q][kk] = 0.f;
+    fwd_range<GE, DROPOUT>(beg, end, col, perm, xw, a_src, adst, slope, keep, keep_scale, m, s, acc, p_sh[warp],
+                           j_sh[warp], lane);
+    if (lane == 0) {
+        store_vecH<H>(part_ms + int64_t(c) * 2 * H, m);
+        store_vecH<H>(part_ms + int64_t(c) * 2 * H + H, s);
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q)
+#pragma unroll
+        for (int kk = 0; kk < VW; kk += 4)
+            *reinterpret_cast<float4*>(part_acc + int64_t(c) * D + VW * (lane + 32 * q) + kk) =
+                make_float4(acc[q][kk], acc[q][kk + 1], acc[q][kk + 2], acc[q][kk + 3]);
+}
+
+// one warp per hub row: merge the chunk partials in chunk order
+template <class GE, bool CONCAT>
+__global__ void __launch_bounds__(ROW_THREADS)
+gat_fwd_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_ms, const float* __restrict__ part_acc,
+                  const float* __restrict__ bias, int act, float* __restrict__ out, float* __restrict__ rowmax,
+                  float* __restrict__ rowsum)
+{
+    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP, D = GE::D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * ROW_WARPS + warp;
+    if (slot >= plan.n_hub) return;
+    const int sub = lane / GE::G;
+    const int64_t i = plan.hub_row[slot];
+    const int c0 = plan.hub_chunk_ptr[slot], c1 = plan.hub_chunk_ptr[slot + 1];
+    float M[H], s[H], acc[NS][VW];
+#pragma unroll
+    for (int h = 0; h < H; ++h) { M[h] = -INFINITY; s[h] = 0.f; }
+    for (int c = c0; c < c1; ++c) {
+        float mc[H];
+        load_vecH<H>(part_ms + int64_t(c) * 2 * H, mc);
+#pragma unroll
+        for (int h = 0; h < H; ++h) M[h] = fmaxf(M[h], mc[h]);
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q)
+#pragma unroll
+        for (int k = 0; k < VW; ++k) acc[q][k] = 0.f;
+    for (int c = c0; c < c1; ++c) {
+        float mc[H], sc[H], f[H];
+        load_vecH<H>(part_ms + int64_t(c) * 2 * H, mc);
+        load_vecH<H>(part_ms + int64_t(c) * 2 * H + H, sc);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            f[h] = expf(mc[h] - M[h]);
+            s[h] = fmaf(sc[h], f[h], s[h]);
+        }
+#pragma unroll
+        for (int q = 0; q < NS; ++q) {
+            const float fq = pick<HP>(f, q, sub);
+#pragma unroll
+            for (int k = 0; k < VW; k += 4) {
+                const float4 v = *reinterpret_cast<const float4*>(part_acc + int64_t(c) * D + VW * (lane + 32 * q) + k);
+                acc[q][k] = fmaf(v.x, fq, acc[q][k]);
+                acc[q][k + 1] = fmaf(v.y, fq, acc[q][k + 1]);
+                acc[q][k + 2] = fmaf(v.z, fq, acc[q][k + 2]);
+                acc[q][k + 3] = fmaf(v.w, fq, acc[q][k + 3]);
+            }
+        }
+    }
+    fwd_epilogue<GE, CONCAT>(i, M, s, acc, bias, act, out, rowmax, rowsum, lane);
+}
+
+// alpha[e,h] in CSR order from the saved row statistics; warp per row, lane = edge
+template <int H>
+__global__ void __launch_bounds__(ROW_THREADS)
+gat_alpha_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ a_src,
+               const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+               int64_t n_dst, float slope, float* __restrict__ alpha)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = int64_t(blockIdx.x) * ROW_WARPS + warp;
+    if (i >= n_dst) return;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    float adst[H], m[H], st[H];
+    load_vecH<H>(a_dst + i * H, adst);
+    load_vecH<H>(rowmax + i * H, m);
+    load_vecH<H>(rowsum + i * H, st);
+    for (int e = beg + lane; e < end; e += 32) {
+        float as[H], al[H];
+        load_vecH<H>(a_src + int64_t(col[e]) * H, as);
+#pragma unroll
+        for (int h = 0; h < H; ++h) al[h] = expf(leaky(as[h] + adst[h], slope) - m[h]) / st[h];
+        store_vecH<H>(alpha + int64_t(e) * H, al);
+    }
+}
+
+template <class GE>
+static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_src, const float* a_dst,
+                      const float* bias, float slope, int concat, int act, const uint8_t* keep, float p_drop,
+                      float* out, float* rowmax, float* rowsum, void* ws, size_t ws_bytes, cudaStream_t st)
+{
+    using XT = typename GE::XT;
+    const XT* xw = reinterpret_cast<const XT*>(xw_);
+    const int64_t n = g->n_dst;
+    if (n == 0) return GNNFD_OK;
+    const bool drop = keep != nullptr && p_drop > 0.f;
+    const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
+    const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
+    const unsigned grid = (unsigned)((n + ROW_WARPS - 1) / ROW_WARPS);
+#define GNNFD_FWD_ROWS(CC, DD)                                                                                      \
+    gat_fwd_rows<GE, CC, DD><<<grid, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, bias, n,    \
+                                                           thr, slope, act, keep, ks, out, rowmax, rowsum)
+    if (concat) { if (drop) GNNFD_FWD_ROWS(true, true); else GNNFD_FWD_ROWS(true, false); }
+    else        { if (drop) GNNFD_FWD_ROWS(false, true); else GNNFD_FWD_ROWS(false, false); }
+#undef GNNFD_FWD_ROWS
+    g_launches += 1;
+    if (g->hub_dst.n_hub > 0) {
+        const gnnfd_hub_plan_t& pl = g->hub_dst;
+        const size_t need = carve_bytes(size_t(pl.n_chunk) * 2 * GE::H, 4) + carve_bytes(size_t(pl.n_chunk) * GE::D, 4);
+        GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "gat_fwd: workspace %zu < %zu", ws_bytes, need);
+        char* p = reinterpret_cast<char*>(ws);
+        float* part_ms = carve<float>(p, size_t(pl.n_chunk) * 2 * GE::H);
+        float* part_acc = carve<float>(p, size_t(pl.n_chunk) * GE::D);
+        const unsigned gc = (unsigned)((pl.n_chunk + ROW_WARPS - 1) / ROW_WARPS);
+        const unsigned gh = (unsigned)((pl.n_hub + ROW_WARPS - 1) / ROW_WARPS);
+        if (drop)
+            gat_fwd_hub_chunks<GE, true><<<gc, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, pl,
+                                                                     slope, keep, ks, part_ms, part_acc);
+        else
+            gat_fwd_hub_chunks<GE, false><<<gc, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, pl,
+                                                                      slope, keep, ks, part_ms, part_acc);
+        if (concat)
+            gat_fwd_hub_merge<GE, true><<<gh, ROW_THREADS, 0, st>>>(pl, part_ms, part_acc, bias, act, out, rowmax, rowsum);
+        else
+            gat_fwd_hub_merge<GE, false><<<gh, ROW_THREADS, 0, st>>>(pl, part_ms, part_acc, bias, act, out, rowmax, rowsum);
+        g_launches += 2;
+    }
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+
+int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who)
+{
+    GNNFD_REQUIRE(g != nullptr, GNNFD_ERR_ARG, "%s: graph is NULL", who);
+    GNNFD_REQUIRE(g->n_dst >= 0 && g->n_src >= 0 && g->n_edges >= 0, GNNFD_ERR_ARG, "%s: negative graph size", who);
+    GNNFD_REQUIRE(g->n_dst == 0 || g->rowptr, GNNFD_ERR_ARG, "%s: rowptr is NULL", who);
+    GNNFD_REQUIRE(g->n_edges == 0 || (g->col && g->perm), GNNFD_ERR_ARG, "%s: col/perm is NULL", who);
+    if (need_csc)
+        GNNFD_REQUIRE(g->n_src == 0 || (g->colptr && (g->n_edges == 0 || (g->csc_row && g->csc_eid))), GNNFD_ERR_ARG,
+                      "%s: the CSC twin (colptr/csc_row/csc_eid) is required", who);
+    return GNNFD_OK;
+}
+
+}  // namespace gnnfd
+
+using namespace gnnfd;
+
+extern "C" {
+
+int gnnfd_gat_fwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* bytes)
+{
+    GNNFD_REQUIRE(g && bytes, GNNFD_ERR_ARG, "gat_fwd_workspace_bytes: NULL argument");
+    const size_t nc = (size_t)g->hub_dst.n_chunk;
+    *bytes = carve_bytes(nc * 2 * H, 4) + carve_bytes(nc * size_t(H) * C, 4) + 256;
+    return GNNFD_OK;
+}
+
+int gnnfd_gat_fwd(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src, const float* a_dst,
+                  const float* bias, int H, int C, float negative_slope, int concat, int act,
+                  const uint8_t* keep_mask, float p_drop, float* out, float* rowmax, float* rowsum, void* ws,
+                  size_t ws_bytes, gnnfd_stream_t stream)
+{
+    int rc = check_graph(g, false, "gat_fwd");
+    if (rc) return rc;
+    GNNFD_REQUIRE(g->n_dst == 0 || (xw && a_src && a_dst && out && rowmax && rowsum), GNNFD_ERR_ARG,
+                  "gat_fwd: NULL tensor");
+    GNNFD_REQUIRE(p_drop >= 0.f && p_drop < 1.f, GNNFD_ERR_ARG, "gat_fwd: dropout p must be in [0,1)");
+    GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(xw) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                  GNNFD_ERR_ARG, "gat_fwd: xw/out must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H == 8 && C == 64 && xw_dtype == GNNFD_F32)
+        return launch_fwd<Geo<8, 64, float>>(g, xw, a_src, a_dst, bias, negative_slope, concat, act, keep_mask, p_drop,
+                                             out, rowmax, rowsum, ws, ws_bytes, st);
+    if (H == 8 && C == 64 && xw_dtype == GNNFD_BF16)
+        return launch_fwd<Geo<8, 64, __nv_bfloat16>>(g, xw, a_src, a_dst, bias, negative_slope, concat, act, keep_mask,
+                                                     p_drop, out, rowmax, rowsum, ws, ws_bytes, st);
+    if (H == 4 && C == 32 && xw_dtype == GNNFD_F32)
+        return launch_fwd<Geo<4, 32, float>>(g, xw, a_src, a_dst, bias, negative_slope, concat, act, keep_mask, p_drop,
+                                             out, rowmax, rowsum, ws, ws_bytes, st);
+    GNNFD_REQUIRE(false, GNNFD_ERR_UNSUPPORTED, "gat_fwd: (heads=%d, out_channels=%d, dtype=%d) is not built; "
+                  "available: (8,64,f32), (8,64,bf16), (4,32,f32)", H, C, xw_dtype);
+    return GNNFD_ERR_UNSUPPORTED;
+}
+
+int gnnfd_gat_alpha(const gnnfd_graph_t* g, const float* a_src, const float* a_dst, const float* rowmax,
+                    const float* rowsum, int H, float negative_slope, float* alpha, gnnfd_stream_t stream)
+{
+    int rc = check_graph(g, false, "gat_alpha");
+    if (rc) return rc;
+    if (g->n_dst == 0 || g->n_edges == 0) return GNNFD_OK;
+    GNNFD_REQUIRE(a_src && a_dst && rowmax && rowsum && alpha, GNNFD_ERR_ARG, "gat_alpha: NULL tensor");
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((g->n_dst + ROW_WARPS - 1) / ROW_WARPS);
+    if (H == 8)
+        gat_alpha_rows<8><<<grid, ROW_THREADS, 0, st>>>(g->rowptr, g->col, a_src, a_dst, rowmax, rowsum, g->n_dst,
+                                                        negative_slope, alpha);
+    else if (H == 4)
+        gat_alpha_rows<4><<<grid, ROW_THREADS, 0, st>>>(g->rowptr, g->col, a_src, a_dst, rowmax, rowsum, g->n_dst,
+                                                        negative_slope, alpha);
+    else
+        GNNFD_REQUIRE(false, GNNFD_ERR_UNSUPPORTED, "gat_alpha: heads=%d is not built", H);
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+
+}  // extern "C"

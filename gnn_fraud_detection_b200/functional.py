@@ -1,0 +1,169 @@
+"""``torch.autograd.Function`` over the C ABI: one GATConv layer, forward and backward.
+
+PyTorch is used here for device memory, streams and autograd bookkeeping only; every arithmetic step
+of the layer runs in ``libgnnfd_b200.so``.  Mirrors ``GATConv.forward`` as called at
+``src/models/gat.py:80`` / ``src/models/tgn.py:94`` and its autograd backward (``src/train.py:142``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _abi
+from .graph import GraphCSR, _stream
+
+_DT = {torch.float32: _abi.F32, torch.bfloat16: _abi.BF16}
+
+
+def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _require_f32_cuda(name: str, t: torch.Tensor):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the B200 path has no CPU fallback")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+
+
+def project_fwd(x, W, att_src, att_dst, H, C_, xw_dtype=torch.float32, algo=_abi.GEMM_AUTO):
+    """xw [N,H*C] (xw_dtype), a_src [N,H], a_dst [N,H] = gnnfd_project_fwd(x, W, att)."""
+    L = _abi.lib()
+    N, K = x.shape
+    dev = x.device
+    xw = torch.empty(N, H * C_, dtype=xw_dtype, device=dev)
+    a_src = torch.empty(N, H, dtype=torch.float32, device=dev)
+    a_dst = torch.empty(N, H, dtype=torch.float32, device=dev)
+    nb = C.c_size_t()
+    _abi.check(L.gnnfd_project_workspace_bytes(N, K, H, C_, algo, C.byref(nb)))
+    ws = _ws(nb.value, dev)
+    _abi.check(L.gnnfd_project_fwd(x.data_ptr(), x.stride(0), W.data_ptr(), att_src.data_ptr(), att_dst.data_ptr(),
+                                   N, K, H, C_, _DT[xw_dtype], algo, xw.data_ptr(), a_src.data_ptr(),
+                                   a_dst.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return xw, a_src, a_dst
+
+
+def gat_fwd(g: GraphCSR, xw, a_src, a_dst, bias, H, C_, negative_slope, concat, act=_abi.ACT_NONE, keep_mask=None,
+            p_drop=0.0):
+    L = _abi.lib()
+    dev = xw.device
+    Co = H * C_ if concat else C_
+    out = torch.empty(g.n_dst, Co, dtype=torch.float32, device=dev)
+    rowmax = torch.empty(g.n_dst, H, dtype=torch.float32, device=dev)
+    rowsum = torch.empty(g.n_dst, H, dtype=torch.float32, device=dev)
+    nb = C.c_size_t()
+    _abi.check(L.gnnfd_gat_fwd_workspace_bytes(g.ref(), H, C_, C.byref(nb)))
+    ws = _ws(nb.value, dev)
+    _abi.check(L.gnnfd_gat_fwd(g.ref(), xw.data_ptr(), _DT[xw.dtype], a_src.data_ptr(), a_dst.data_ptr(),
+                               _abi.ptr(bias), H, C_, float(negative_slope), int(concat), int(act),
+                               _abi.ptr(keep_mask), float(p_drop), out.data_ptr(), rowmax.data_ptr(),
+                               rowsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return out, rowmax, rowsum
+
+
+def gat_alpha(g: GraphCSR, a_src, a_dst, rowmax, rowsum, H, negative_slope):
+    """alpha [E',H] in CSR (dst-sorted) order."""
+    L = _abi.lib()
+    alpha = torch.empty(g.n_edges, H, dtype=torch.float32, device=a_src.device)
+    _abi.check(L.gnnfd_gat_alpha(g.ref(), a_src.data_ptr(), a_dst.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(),
+                                 H, float(negative_slope), alpha.data_ptr(), _stream()))
+    return alpha
+
+
+def gat_bwd(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, att_src, att_dst, H, C_, negative_slope, concat,
+            keep_mask=None, p_drop=0.0, da_dst_full="same"):
+    """dst-major + src-major backward passes.  Returns dxw [n_src,H*C], da_src [n_src,H], da_dst [n_dst,H]."""
+    L = _abi.lib()
+    dev = xw.device
+    alpha_used = torch.empty(g.n_edges, H, dtype=torch.float32, device=dev)
+    dz = torch.empty(g.n_edges, H, dtype=torch.float32, device=dev)
+    da_dst = torch.empty(g.n_dst, H, dtype=torch.float32, device=dev)
+    nb = C.c_size_t()
+    _abi.check(L.gnnfd_gat_bwd_workspace_bytes(g.ref(), H, C_, C.byref(nb)))
+    ws = _ws(nb.value, dev)
+    _abi.check(L.gnnfd_gat_bwd_dst(g.ref(), xw.data_ptr(), _DT[xw.dtype], a_src.data_ptr(), a_dst.data_ptr(),
+                                   rowmax.data_ptr(), rowsum.data_ptr(), d_out.data_ptr(), H, C_,
+                                   float(negative_slope), int(concat), _abi.ptr(keep_mask), float(p_drop),
+                                   alpha_used.data_ptr(), dz.data_ptr(), da_dst.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), _stream()))
+    dxw = torch.empty(g.n_src, H * C_, dtype=torch.float32, device=dev)
+    da_src = torch.empty(g.n_src, H, dtype=torch.float32, device=dev)
+    full = da_dst if isinstance(da_dst_full, str) else da_dst_full
+    _abi.check(L.gnnfd_gat_bwd_src(g.ref(), alpha_used.data_ptr(), dz.data_ptr(), d_out.data_ptr(),
+                                   att_src.data_ptr(), att_dst.data_ptr(), _abi.ptr(full), H, C_, int(concat),
+                                   dxw.data_ptr(), da_src.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return dxw, da_src, da_dst
+
+
+def project_bwd(x, W, dxw, xw, da_src, da_dst, d_out, H, C_, Co, need_dx, algo=_abi.GEMM_AUTO):
+    L = _abi.lib()
+    N, K = x.shape
+    dev = x.device
+    dW = torch.empty(H * C_, K, dtype=torch.float32, device=dev)
+    datt_src = torch.empty(H * C_, dtype=torch.float32, device=dev)
+    datt_dst = torch.empty(H * C_, dtype=torch.float32, device=dev)
+    dbias = torch.empty(Co, dtype=torch.float32, device=dev)
+    dx = torch.empty(N, K, dtype=torch.float32, device=dev) if need_dx else None
+    nb = C.c_size_t()
+    _abi.check(L.gnnfd_project_bwd_workspace_bytes(N, K, H, C_, algo, C.byref(nb)))
+    ws = _ws(nb.value, dev)
+    _abi.check(L.gnnfd_project_bwd(x.data_ptr(), x.stride(0), W.data_ptr(), dxw.data_ptr(), xw.data_ptr(),
+                                   _DT[xw.dtype], da_src.data_ptr(), da_dst.data_ptr(), d_out.data_ptr(), N, K, H, C_,
+                                   Co, algo, dW.data_ptr(), datt_src.data_ptr(), datt_dst.data_ptr(),
+                                   dbias.data_ptr(), _abi.ptr(dx), K, ws.data_ptr(), ws.numel(), _stream()))
+    return dW, datt_src, datt_dst, dbias, dx
+
+
+class GATConvFunction(torch.autograd.Function):
+    """out = GATConv(x, edge_index') with every stage in the CUDA library."""
+
+    @staticmethod
+    def forward(ctx, x, W, att_src, att_dst, bias, g: GraphCSR, H, C_, concat, negative_slope, keep_mask, p_drop,
+                xw_dtype, algo, want_stats):
+        _require_f32_cuda("x", x)
+        _require_f32_cuda("lin_src.weight", W)
+        if x.dim() != 2 or x.size(1) != W.size(1):
+            raise ValueError(f"x must be [N,{W.size(1)}], got {tuple(x.shape)}")
+        if x.size(0) != g.n_src:
+            raise ValueError(f"x has {x.size(0)} rows but the graph has {g.n_src} source nodes")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        W = W.contiguous()
+        a_s, a_d = att_src.contiguous().view(-1), att_dst.contiguous().view(-1)
+        with torch.cuda.device(x.device):
+            xw, a_src, a_dst = project_fwd(x, W, a_s, a_d, H, C_, xw_dtype, algo)
+            out, rowmax, rowsum = gat_fwd(g, xw, a_src, a_dst, bias, H, C_, negative_slope, concat, _abi.ACT_NONE,
+                                          keep_mask, p_drop)
+        ctx.save_for_backward(x, W, a_s, a_d, xw, a_src, a_dst, rowmax, rowsum, keep_mask)
+        ctx.g, ctx.H, ctx.C, ctx.concat, ctx.slope, ctx.p, ctx.algo = g, H, C_, concat, negative_slope, p_drop, algo
+        ctx.has_bias = bias is not None
+        ctx.att_shape = att_src.shape
+        if want_stats:
+            ctx.mark_non_differentiable(a_src, a_dst, rowmax, rowsum)
+            return out, a_src, a_dst, rowmax, rowsum
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out, *unused):
+        x, W, a_s, a_d, xw, a_src, a_dst, rowmax, rowsum, keep_mask = ctx.saved_tensors
+        g, H, C_, concat = ctx.g, ctx.H, ctx.C, ctx.concat
+        if not g.has_csc:
+            raise RuntimeError("backward needs the CSC twin; build the graph with build_csc=True")
+        d_out = d_out.contiguous().float()
+        need_dx = ctx.needs_input_grad[0]
+        Co = H * C_ if concat else C_
+        with torch.cuda.device(x.device):
+            dxw, da_src, da_dst = gat_bwd(g, xw, a_src, a_dst, rowmax, rowsum, d_out, a_s, a_d, H, C_, ctx.slope,
+                                          concat, keep_mask, ctx.p)
+            dW, datt_src, datt_dst, dbias, dx = project_bwd(x, W, dxw, xw, da_src, da_dst, d_out, H, C_, Co, need_dx,
+                                                            ctx.algo)
+        return (dx, dW, datt_src.view(ctx.att_shape), datt_dst.view(ctx.att_shape),
+                dbias if ctx.has_bias else None, None, None, None, None, None, None, None, None, None, None)
+
+
+def gatconv(x, W, att_src, att_dst, bias, g: GraphCSR, heads, out_channels, concat=False, negative_slope=0.2,
+            keep_mask=None, p_drop=0.0, xw_dtype=torch.float32, algo=_abi.GEMM_AUTO, want_stats=False):
+    return GATConvFunction.apply(x, W, att_src, att_dst, bias, g, heads, out_channels, concat, negative_slope,
+                                 keep_mask, p_drop, xw_dtype, algo, want_stats)

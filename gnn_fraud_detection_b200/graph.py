@@ -1,0 +1,145 @@
+"""Host-side graph structures: destination-sorted CSR (+CSC twin, hub plans) built by the CUDA library.
+
+``edge_index`` is the reference's ``[2, E]`` int64 tensor (row 0 = source, row 1 = target,
+``src/models/gat.py:80``).  In full-batch training the same tensor is passed to every layer of every
+epoch (``src/train.py:124``), so the CSR is built once and cached on the tensor's identity
+(``data_ptr``, shape, ``_version``) instead of redoing the self-loop rewrite on every forward as PyG does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+
+from . import _abi
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class GraphCSR:
+    """Device-resident CSR/CSC of ``edge_index'`` plus the ``gnnfd_graph_t`` view handed to the kernels."""
+
+    def __init__(self, n_dst: int, n_src: int, n_edges: int, rowptr, col, perm, colptr=None, csc_row=None,
+                 csc_eid=None, hub_threshold: int = _abi.HUB_THRESHOLD, hub_chunk: int = _abi.HUB_CHUNK,
+                 plan_hubs: bool = True):
+        self.n_dst, self.n_src, self.n_edges = int(n_dst), int(n_src), int(n_edges)
+        self.rowptr, self.col, self.perm = rowptr, col, perm
+        self.colptr, self.csc_row, self.csc_eid = colptr, csc_row, csc_eid
+        self.device = rowptr.device
+        self._hub_tensors = []
+        self.c = _abi.Graph()
+        self.c.n_dst, self.c.n_src, self.c.n_edges = self.n_dst, self.n_src, self.n_edges
+        self.c.rowptr, self.c.col, self.c.perm = _abi.ptr(rowptr), _abi.ptr(col), _abi.ptr(perm)
+        self.c.colptr, self.c.csc_row, self.c.csc_eid = _abi.ptr(colptr), _abi.ptr(csc_row), _abi.ptr(csc_eid)
+        if plan_hubs:
+            self.c.hub_dst = self._plan(rowptr, self.n_dst, hub_threshold, hub_chunk)
+            if colptr is not None:
+                self.c.hub_src = self._plan(colptr, self.n_src, hub_threshold, hub_chunk)
+
+    @property
+    def has_csc(self) -> bool:
+        return self.colptr is not None
+
+    def _plan(self, ptr_t, n_rows, threshold, chunk) -> _abi.HubPlan:
+        plan = _abi.HubPlan()
+        plan.threshold, plan.chunk = threshold, chunk
+        if n_rows == 0 or self.n_edges <= threshold:
+            return plan
+        L = _abi.lib()
+        cap_hub = self.n_edges // (threshold + 1) + 1
+        cap_chunk = self.n_edges // chunk + cap_hub + 1
+        hub_row = torch.empty(cap_hub, dtype=torch.int32, device=self.device)
+        hub_chunk_ptr = torch.empty(cap_hub + 1, dtype=torch.int32, device=self.device)
+        chunk_hub = torch.empty(cap_chunk, dtype=torch.int32, device=self.device)
+        nbytes = C.c_size_t()
+        _abi.check(L.gnnfd_hub_plan_workspace_bytes(n_rows, C.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        counts = (C.c_int64 * 2)()
+        _abi.check(L.gnnfd_hub_plan(ptr_t.data_ptr(), n_rows, threshold, chunk, hub_row.data_ptr(),
+                                    hub_chunk_ptr.data_ptr(), chunk_hub.data_ptr(), cap_hub, cap_chunk, counts,
+                                    ws.data_ptr(), nbytes.value, _stream()))
+        n_hub, n_chunk = int(counts[0]), int(counts[1])
+        if n_hub == 0:
+            return plan
+        hub_row, hub_chunk_ptr, chunk_hub = hub_row[:n_hub].clone(), hub_chunk_ptr[:n_hub + 1].clone(), \
+            chunk_hub[:n_chunk].clone()
+        self._hub_tensors += [hub_row, hub_chunk_ptr, chunk_hub]
+        plan.n_hub, plan.n_chunk = n_hub, n_chunk
+        plan.hub_row, plan.hub_chunk_ptr, plan.chunk_hub = hub_row.data_ptr(), hub_chunk_ptr.data_ptr(), \
+            chunk_hub.data_ptr()
+        return plan
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+def build_csr(edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = True, build_csc: bool = True,
+              hub_threshold: int = _abi.HUB_THRESHOLD, hub_chunk: int = _abi.HUB_CHUNK) -> GraphCSR:
+    """edge_index [2,E] int64 (cuda) -> GraphCSR, via ``gnnfd_csr_build`` (stable radix sort on device)."""
+    if edge_index.dim() != 2 or edge_index.size(0) != 2:
+        raise ValueError(f"edge_index must be [2, E], got {tuple(edge_index.shape)}")
+    if edge_index.dtype != torch.int64:
+        raise TypeError(f"edge_index must be int64 (torch.long), got {edge_index.dtype}")
+    if not edge_index.is_cuda:
+        raise RuntimeError("edge_index must live on a CUDA device: this path has no CPU implementation")
+    L = _abi.lib()
+    ei = edge_index.contiguous()
+    E, N, dev = ei.size(1), int(num_nodes), ei.device
+    flags = (_abi.ADD_SELF_LOOPS if add_self_loops else 0) | (_abi.BUILD_CSC if build_csc else 0)
+    cap = E + (N if add_self_loops else 0)
+    with torch.cuda.device(dev):
+        nbytes = C.c_size_t()
+        _abi.check(L.gnnfd_csr_workspace_bytes(N, E, flags, C.byref(nbytes)))
+        ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+        rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(cap, dtype=torch.int32, device=dev)
+        perm = torch.empty(cap, dtype=torch.int32, device=dev)
+        colptr = csc_row = csc_eid = None
+        if build_csc:
+            colptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+            csc_row = torch.empty(cap, dtype=torch.int32, device=dev)
+            csc_eid = torch.empty(cap, dtype=torch.int32, device=dev)
+        e_out = C.c_int64()
+        _abi.check(L.gnnfd_csr_build(ei.data_ptr(), E, N, flags, rowptr.data_ptr(), col.data_ptr(), perm.data_ptr(),
+                                     _abi.ptr(colptr), _abi.ptr(csc_row), _abi.ptr(csc_eid), C.byref(e_out),
+                                     ws.data_ptr(), nbytes.value, _stream()))
+        Ep = int(e_out.value)
+        del ws
+        if Ep != cap:  # existing self-loops were dropped: trim the over-allocated tails
+            col, perm = col[:Ep].clone(), perm[:Ep].clone()
+            if build_csc:
+                csc_row, csc_eid = csc_row[:Ep].clone(), csc_eid[:Ep].clone()
+        return GraphCSR(N, N, Ep, rowptr, col, perm, colptr, csc_row, csc_eid, hub_threshold, hub_chunk)
+
+
+class CSRCache:
+    """Small LRU keyed on the identity of the edge_index tensor (full-batch training reuses it)."""
+
+    def __init__(self, capacity: int = 8):
+        self.capacity = capacity
+        self._d: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+    def get(self, edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool, build_csc: bool) -> GraphCSR:
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_index.device.index,
+               int(num_nodes), bool(add_self_loops))
+        hit = self._d.get(key)
+        if hit is not None and (hit[0].has_csc or not build_csc):
+            self._d.move_to_end(key)
+            return hit[0]
+        g = build_csr(edge_index, num_nodes, add_self_loops, build_csc)
+        # keep a reference to the tensor so its storage (and therefore data_ptr) cannot be recycled
+        self._d[key] = (g, edge_index)
+        self._d.move_to_end(key)
+        while len(self._d) > self.capacity:
+            self._d.popitem(last=False)
+        return g
+
+    def clear(self):
+        self._d.clear()
+
+
+GLOBAL_CSR_CACHE = CSRCache()

@@ -1,0 +1,83 @@
+"""Host-side mirror of the reference's model classes for the GAT hot path.
+
+``GAT`` and ``TemporalGNN`` keep the class names, constructor arguments, ``forward`` / ``predict``
+signatures, return types and ``state_dict`` keys of ``src/models/gat.py:10-122`` and
+``src/models/tgn.py:14-141`` so that callers (``src/train.py:117-128``, ``src/evaluate.py:75-86``,
+``compare_gnn_models.py:96-107``) and the shipped checkpoints work unchanged; the only difference is that
+``GATConv`` resolves to the B200-native layer in ``gnn_fraud_detection_b200.nn``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .nn import GATConv
+
+__all__ = ["GAT", "TemporalGNN"]
+
+_HEADS = 8  # hard-coded at every GATConv(...) call of the reference (gat.py:39,45,51; tgn.py:43,49,55)
+
+
+class _GATStack(nn.Module):
+    """The layer loop both reference models share (gat.py:78-91 == tgn.py:92-105)."""
+
+    def __init__(self, in_channels: int, hidden_channels: int, out_channels: int, num_layers: int, dropout: float,
+                 residual: bool, use_batch_norm: bool, **conv_kwargs):
+        super().__init__()
+        self.in_channels, self.hidden_channels, self.out_channels = in_channels, hidden_channels, out_channels
+        self.num_layers, self.dropout = num_layers, dropout
+        self.residual, self.use_batch_norm = residual, use_batch_norm
+        # one input layer always; (num_layers-2) hidden layers; one more iff num_layers > 1
+        fan_in = [in_channels] + [hidden_channels] * max(num_layers - 1, 0)
+        self.gat_layers = nn.ModuleList(
+            GATConv(k, hidden_channels, heads=_HEADS, concat=False, dropout=dropout, **conv_kwargs) for k in fan_in)
+        self.batch_norms = (nn.ModuleList(nn.BatchNorm1d(hidden_channels) for _ in fan_in)
+                            if use_batch_norm else None)
+
+    def _encode(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
+        h = x
+        for i, conv in enumerate(self.gat_layers):
+            z = conv(h, edge_index)
+            if self.use_batch_norm:
+                z = self.batch_norms[i](z)
+            z = F.dropout(F.relu(z), p=self.dropout, training=self.training)
+            h = h + z if (self.residual and h.size(-1) == z.size(-1)) else z
+        return h
+
+
+class GAT(_GATStack):
+    def __init__(self, in_channels: int, hidden_channels: int, out_channels: int, num_layers: int = 2,
+                 dropout: float = 0.2, residual: bool = True, use_batch_norm: bool = True, **conv_kwargs):
+        super().__init__(in_channels, hidden_channels, out_channels, num_layers, dropout, residual, use_batch_norm,
+                         **conv_kwargs)
+        self.out = nn.Linear(hidden_channels, out_channels)
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, batch: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.out(self._encode(x, edge_index))
+
+    def predict(self, x, edge_index, batch=None, apply_sigmoid: bool = True) -> torch.Tensor:
+        out = self.forward(x, edge_index, batch)
+        return torch.sigmoid(out) if apply_sigmoid else out
+
+
+class TemporalGNN(_GATStack):
+    def __init__(self, in_channels: int, hidden_channels: int, out_channels: int, num_layers: int = 2,
+                 dropout: float = 0.2, residual: bool = True, use_batch_norm: bool = True, **conv_kwargs):
+        super().__init__(in_channels, hidden_channels, out_channels, num_layers, dropout, residual, use_batch_norm,
+                         **conv_kwargs)
+        self.gru = nn.GRUCell(hidden_channels, hidden_channels)
+        self.out = nn.Linear(hidden_channels, out_channels)
+
+    def forward(self, x: torch.Tensor, edge_index: torch.Tensor, batch: Optional[torch.Tensor] = None,
+                hidden_state: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        if hidden_state is None:
+            hidden_state = torch.zeros(x.size(0), self.hidden_channels, device=x.device)
+        hidden_state = self.gru(self._encode(x, edge_index), hidden_state)
+        return self.out(hidden_state), hidden_state
+
+    def predict(self, x, edge_index, batch=None, hidden_state=None, apply_sigmoid: bool = True) -> torch.Tensor:
+        out, _ = self.forward(x, edge_index, batch, hidden_state)
+        return torch.sigmoid(out) if apply_sigmoid else out

@@ -1,0 +1,125 @@
+"""Drop-in ``GATConv``: the name the reference imports at ``src/models/gat.py:4`` / ``src/models/tgn.py:4``.
+
+Same constructor arguments, ``forward(x, edge_index)`` signature, parameter names and ``state_dict`` keys
+as ``torch_geometric.nn.GATConv`` 2.0-2.4 (``att_src``, ``att_dst``, ``bias``, ``lin_src.weight``,
+``lin_dst.weight`` with ``lin_dst`` an alias of ``lin_src``), so the reference's shipped checkpoints
+(``results/gat_model.pt``) load with ``strict=True``.  The arithmetic runs in ``libgnnfd_b200.so``; there
+is no PyG, Triton or CPU fallback -- a CPU tensor or a missing extension raises.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+from .functional import gat_alpha, gatconv
+from .graph import GLOBAL_CSR_CACHE, GraphCSR
+
+
+def glorot_(t: torch.Tensor) -> torch.Tensor:
+    """PyG ``inits.glorot``: U(-a, a) with a = sqrt(6 / (size(-2) + size(-1)))."""
+    a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+    with torch.no_grad():
+        return t.uniform_(-a, a)
+
+
+class _Linear(nn.Module):
+    """Bias-free projection holder; key ``weight`` has shape ``[heads*out_channels, in_channels]``."""
+
+    def __init__(self, in_channels: int, out_channels: int):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}, bias=False"
+
+
+class GATConv(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
+                 negative_slope: float = 0.2, dropout: float = 0.0, add_self_loops: bool = True,
+                 edge_dim: Optional[int] = None, fill_value="mean", bias: bool = True,
+                 feature_dtype: torch.dtype = torch.float32, gemm_algo: int = _abi.GEMM_AUTO, **kwargs):
+        super().__init__()
+        if isinstance(in_channels, (tuple, list)):
+            raise NotImplementedError("bipartite (x_src, x_dst) inputs are not part of the reference's hot path")
+        if edge_dim is not None:
+            raise NotImplementedError("edge_dim/edge_attr is never used by the reference models (src/config.py:36)")
+        if kwargs:
+            raise NotImplementedError(f"unsupported GATConv options: {sorted(kwargs)}")
+        if feature_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("feature_dtype must be torch.float32 or torch.bfloat16")
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.concat, self.negative_slope, self.dropout = concat, negative_slope, dropout
+        self.add_self_loops = add_self_loops
+        self.feature_dtype, self.gemm_algo = feature_dtype, gemm_algo
+        self.lin_src = _Linear(in_channels, heads * out_channels)
+        self.lin_dst = self.lin_src  # same module object: state_dict() emits both keys, as PyG does
+        self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
+        if bias:
+            self.bias = nn.Parameter(torch.empty(heads * out_channels if concat else out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot_(self.lin_src.weight)
+        glorot_(self.att_src)
+        glorot_(self.att_dst)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def _graph(self, edge_index, num_nodes: int) -> GraphCSR:
+        if isinstance(edge_index, GraphCSR):
+            return edge_index
+        if not isinstance(edge_index, torch.Tensor):
+            raise NotImplementedError("SparseTensor adjacency input is not supported; pass edge_index [2,E]")
+        need_csc = torch.is_grad_enabled()
+        return GLOBAL_CSR_CACHE.get(edge_index, num_nodes, self.add_self_loops, need_csc)
+
+    def forward(self, x: torch.Tensor, edge_index, edge_attr=None, size=None, return_attention_weights=None,
+                dropout_mask: Optional[torch.Tensor] = None):
+        """``x [N, in_channels]`` fp32 cuda, ``edge_index [2,E]`` int64 cuda -> ``[N, out_channels]``.
+
+        ``dropout_mask``: optional ``[E',H]`` keep-mask in ``edge_index'`` order for the attention dropout
+        (parity tests inject it); in training mode with ``dropout > 0`` one is drawn with ``torch.rand``.
+        """
+        if edge_attr is not None or size is not None:
+            raise NotImplementedError("edge_attr / size are not part of the reference's hot path")
+        if not x.is_cuda:
+            raise RuntimeError("gnn_fraud_detection_b200.GATConv runs on CUDA only (no CPU fallback)")
+        g = self._graph(edge_index, x.size(0))
+        H, C = self.heads, self.out_channels
+        p = self.dropout if self.training else 0.0
+        keep = None
+        if dropout_mask is not None:
+            keep = dropout_mask.to(device=x.device, dtype=torch.uint8).contiguous()
+            p = self.dropout
+        elif p > 0.0:
+            keep = (torch.rand(g.n_edges, H, device=x.device) >= p).to(torch.uint8)
+        if keep is not None and tuple(keep.shape) != (g.n_edges, H):
+            raise ValueError(f"dropout_mask must be [{g.n_edges},{H}], got {tuple(keep.shape)}")
+        res = gatconv(x, self.lin_src.weight, self.att_src, self.att_dst, self.bias, g, H, C, self.concat,
+                      self.negative_slope, keep, p, self.feature_dtype, self.gemm_algo,
+                      want_stats=bool(return_attention_weights))
+        if not return_attention_weights:
+            return res
+        out, a_src, a_dst, rowmax, rowsum = res
+        alpha_csr = gat_alpha(g, a_src, a_dst, rowmax, rowsum, H, self.negative_slope)
+        # PyG returns (edge_index', alpha) in edge_index' order: un-permute the CSR-ordered alpha
+        perm = g.perm.long()
+        alpha = torch.empty_like(alpha_csr)
+        alpha[perm] = alpha_csr
+        dst_sorted = torch.repeat_interleave(torch.arange(g.n_dst, device=x.device),
+                                             (g.rowptr[1:] - g.rowptr[:-1]).long())
+        ei = torch.empty(2, g.n_edges, dtype=torch.int64, device=x.device)
+        ei[0, perm] = g.col.long()
+        ei[1, perm] = dst_sorted
+        return out, (ei, alpha)
+
+    def extra_repr(self):
+        return f"{self.in_channels}, {self.out_channels}, heads={self.heads}, concat={self.concat}"

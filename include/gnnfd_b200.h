@@ -1,0 +1,175 @@
+/*
+ * libgnnfd_b200 -- C ABI of the B200-native GAT message-passing hot path.
+ *
+ * This is the drop-in boundary for ONE path of aum2606/GNN-Fraud-Detection: the GATConv layer that
+ * src/models/gat.py:39,45,51,80 and src/models/tgn.py:43,49,55,94 construct and call
+ * (`gat(h, edge_index) -> [N, out_channels]`), forward and backward.  The reference has no FFI of its
+ * own (the arithmetic sits in third-party torch_geometric.nn.GATConv); the entry points below are what
+ * a binding for that layer would bind, one per stage of GATConv.forward / its autograd mirror:
+ *
+ *   reference stage (PyG GATConv.forward)          entry point
+ *   ---------------------------------------------------------------  --------------------------------
+ *   remove_self_loops + add_self_loops, edge ordering (every call)   gnnfd_csr_build  (+ gnnfd_hub_plan)
+ *   x @ W^T, alpha_src/alpha_dst = (xw * att).sum(-1)                gnnfd_project_fwd
+ *   edge_update (leaky_relu, softmax, dropout) + message + aggregate
+ *     + head mean/concat + bias                                      gnnfd_gat_fwd   (gnnfd_gat_alpha)
+ *   loss.backward() through the layer (src/train.py:142)             gnnfd_gat_bwd_dst, gnnfd_gat_bwd_src,
+ *                                                                    gnnfd_project_bwd
+ *
+ * Conventions
+ *   - every pointer is DEVICE memory owned by the caller unless the parameter name ends in `_host`;
+ *   - all work is enqueued on `stream` (a cudaStream_t); no implicit synchronisation except where a
+ *     `_host` output is written (gnnfd_csr_build, gnnfd_hub_plan);
+ *   - return value 0 = ok, <0 = error code below; text via gnnfd_last_error() (thread-local);
+ *   - the library never allocates device memory: scratch comes in through (ws, ws_bytes), sized by the
+ *     matching *_workspace_bytes call;
+ *   - indices inside the library are int32 (E' < 2^31); the caller-facing edge_index is int64 [2,E]
+ *     exactly as the reference passes it;
+ *   - features/gradients are fp32; the projected features xw may be stored fp32 or bf16 (xw_dtype).
+ */
+#ifndef GNNFD_B200_H_
+#define GNNFD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNNFD_ABI_VERSION 1
+
+typedef void* gnnfd_stream_t; /* cudaStream_t */
+
+enum {
+    GNNFD_OK = 0,
+    GNNFD_ERR_ARG = -1,         /* null pointer, bad shape, misalignment */
+    GNNFD_ERR_CUDA = -2,        /* a CUDA runtime call or launch failed */
+    GNNFD_ERR_WORKSPACE = -3,   /* ws_bytes too small */
+    GNNFD_ERR_RANGE = -4,       /* edge_index entry outside [0,N) or E' >= 2^31 */
+    GNNFD_ERR_UNSUPPORTED = -5  /* (H,C), dtype or option not built */
+};
+
+enum { GNNFD_ADD_SELF_LOOPS = 1, GNNFD_BUILD_CSC = 2 };          /* gnnfd_csr_build flags */
+enum { GNNFD_F32 = 0, GNNFD_BF16 = 1 };                           /* xw_dtype */
+enum { GNNFD_ACT_NONE = 0, GNNFD_ACT_RELU = 1, GNNFD_ACT_ELU = 2 };/* fused epilogue activation */
+enum { GNNFD_GEMM_AUTO = 0, GNNFD_GEMM_SIMT = 1, GNNFD_GEMM_TC = 2 }; /* projection algorithm */
+
+/* Rows with more than GNNFD_HUB_THRESHOLD edges are split into chunks of GNNFD_HUB_CHUNK edges
+ * (edge-balanced hub splitting); both are what gnnfd_hub_plan is normally called with. */
+#define GNNFD_HUB_THRESHOLD 512
+#define GNNFD_HUB_CHUNK 512
+
+/* A segment plan for one orientation (dst-major CSR or src-major CSC): the hub rows and their chunks. */
+typedef struct gnnfd_hub_plan {
+    int32_t n_hub;                 /* rows with degree > threshold */
+    int32_t n_chunk;               /* sum over hub rows of ceil(degree / chunk) */
+    int32_t threshold;
+    int32_t chunk;
+    const int32_t* hub_row;        /* [n_hub]   row id, ascending */
+    const int32_t* hub_chunk_ptr;  /* [n_hub+1] first chunk of each hub row */
+    const int32_t* chunk_hub;      /* [n_chunk] hub slot of each chunk */
+} gnnfd_hub_plan_t;
+
+/* Destination-sorted CSR (+ optional source-sorted CSC twin) of the rewritten edge list.
+ * Rows are destinations [0,n_dst); col[] holds source ids in [0,n_src). */
+typedef struct gnnfd_graph {
+    int64_t n_dst;
+    int64_t n_src;
+    int64_t n_edges;               /* E' */
+    const int32_t* rowptr;         /* [n_dst+1] */
+    const int32_t* col;            /* [E'] source of each dst-sorted edge */
+    const int32_t* perm;           /* [E'] position of each dst-sorted edge in edge_index' (PyG order) */
+    const int32_t* colptr;         /* [n_src+1]  (NULL when no CSC was built) */
+    const int32_t* csc_row;        /* [E'] destination of each src-sorted edge */
+    const int32_t* csc_eid;        /* [E'] CSR position of each src-sorted edge */
+    gnnfd_hub_plan_t hub_dst;      /* plan over rowptr  (n_hub = 0 => none) */
+    gnnfd_hub_plan_t hub_src;      /* plan over colptr */
+} gnnfd_graph_t;
+
+/* ---- introspection ------------------------------------------------------------------------- */
+const char* gnnfd_last_error(void);
+int gnnfd_abi_version(void);
+size_t gnnfd_sizeof_graph(void);      /* sizeof(gnnfd_graph_t), for binding sanity checks */
+size_t gnnfd_sizeof_hub_plan(void);
+/* Number of kernel launches issued by this library since the last reset (bench.py "gpu_launches"). */
+int64_t gnnfd_launch_count(void);
+void gnnfd_launch_count_reset(void);
+
+/* ---- (1) edge_index -> destination-sorted CSR ------------------------------------------------
+ * Replaces: remove_self_loops/add_self_loops + the per-call scatter ordering inside GATConv.forward
+ * (reference call site src/models/gat.py:80).  Bit-exact contract: perm == torch.sort(dst',
+ * stable=True).indices, col == src'[perm], rowptr == row offsets; CSC twin == stable sort of col.
+ * Output capacity of col/perm/csc_* must be >= E + N (ADD_SELF_LOOPS) or E.  E_out_host receives E'. */
+int gnnfd_csr_workspace_bytes(int64_t N, int64_t E, int flags, size_t* bytes);
+int gnnfd_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int flags,
+                    int32_t* rowptr, int32_t* col, int32_t* perm,
+                    int32_t* colptr, int32_t* csc_row, int32_t* csc_eid,
+                    int64_t* E_out_host, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+
+/* Hub plan over a row-pointer array (rowptr or colptr).  cap_hub / cap_chunk are the capacities of the
+ * output arrays (hub_chunk_ptr needs cap_hub+1).  counts_host[0]=n_hub, counts_host[1]=n_chunk. */
+int gnnfd_hub_plan_workspace_bytes(int64_t n_rows, size_t* bytes);
+int gnnfd_hub_plan(const int32_t* ptr, int64_t n_rows, int32_t threshold, int32_t chunk,
+                   int32_t* hub_row, int32_t* hub_chunk_ptr, int32_t* chunk_hub,
+                   int64_t cap_hub, int64_t cap_chunk, int64_t* counts_host,
+                   void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+
+/* ---- (2) projection  xw = x @ W^T, a_src/a_dst in the epilogue --------------------------------
+ * Replaces: lin_src(x).view(-1,H,C); (x_src*att_src).sum(-1); (x_dst*att_dst).sum(-1).
+ * x [N,K] fp32 row-major with leading dimension ldx (elements); W [H*C,K] fp32 row-major;
+ * att_src/att_dst [H*C]; xw [N,H*C] (xw_dtype); a_src/a_dst [N,H] fp32. */
+int gnnfd_project_workspace_bytes(int64_t N, int64_t K, int H, int C, int algo, size_t* bytes);
+int gnnfd_project_fwd(const float* x, int64_t ldx, const float* W, const float* att_src,
+                      const float* att_dst, int64_t N, int64_t K, int H, int C, int xw_dtype, int algo,
+                      void* xw, float* a_src, float* a_dst, void* ws, size_t ws_bytes,
+                      gnnfd_stream_t stream);
+
+/* ---- (3) fused LeakyReLU + online segment softmax + weighted neighbour gather-sum ------------
+ * Replaces: edge_update + message + aggregate + head mean/concat + bias of GATConv.forward.
+ * out [n_dst, concat ? H*C : C]; rowmax/rowsum [n_dst,H] are saved for the backward (rowsum already
+ * includes PyG's +1e-16).  a_dst is indexed by LOCAL destination row, a_src/xw by source id.
+ * keep_mask: optional [E',H] uint8 attention-dropout keep mask in edge_index' (PyG) order, applied as
+ * alpha*keep/(1-p); NULL => no dropout. */
+int gnnfd_gat_fwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* bytes);
+int gnnfd_gat_fwd(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src,
+                  const float* a_dst, const float* bias, int H, int C, float negative_slope, int concat,
+                  int act, const uint8_t* keep_mask, float p_drop, float* out, float* rowmax,
+                  float* rowsum, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+/* alpha [E',H] in dst-sorted (CSR) order, recomputed from the saved row statistics
+ * (return_attention_weights=True; un-permute through perm to get PyG order). */
+int gnnfd_gat_alpha(const gnnfd_graph_t* g, const float* a_src, const float* a_dst, const float* rowmax,
+                    const float* rowsum, int H, float negative_slope, float* alpha,
+                    gnnfd_stream_t stream);
+
+/* ---- (4) backward ----------------------------------------------------------------------------
+ * dst-major pass: recomputes alpha, forms d_alpha = <dO_h[i], xw[j]>, softmax + LeakyReLU backward.
+ *   writes alpha_used [E',H] (alpha after dropout scaling), dz [E',H] (both CSR order), da_dst [n_dst,H].
+ * src-major pass (needs the CSC twin): dxw[j] = sum_e alpha_used*dO_h[i] + da_src[j]*att_src
+ *   + da_dst_full[j]*att_dst, da_src[j] = sum_e dz.  da_dst_full is indexed by SOURCE id (for a single
+ *   GPU it is the da_dst the dst pass produced; NULL => the att_dst term is skipped).
+ * d_out [n_dst, concat ? H*C : C]. */
+int gnnfd_gat_bwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* bytes);
+int gnnfd_gat_bwd_dst(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src,
+                      const float* a_dst, const float* rowmax, const float* rowsum, const float* d_out,
+                      int H, int C, float negative_slope, int concat, const uint8_t* keep_mask,
+                      float p_drop, float* alpha_used, float* dz, float* da_dst, void* ws,
+                      size_t ws_bytes, gnnfd_stream_t stream);
+int gnnfd_gat_bwd_src(const gnnfd_graph_t* g, const float* alpha_used, const float* dz,
+                      const float* d_out, const float* att_src, const float* att_dst,
+                      const float* da_dst_full, int H, int C, int concat, float* dxw, float* da_src,
+                      void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+
+/* Projection backward: dW [H*C,K] = dxw^T x ; dx [N,K] = dxw W (NULL => skipped, layer 1);
+ * datt_src/datt_dst [H*C] = sum_n da_*[n,h] * xw[n,h,:] ; dbias [Co] = sum_n d_out[n,:]. */
+int gnnfd_project_bwd_workspace_bytes(int64_t N, int64_t K, int H, int C, int algo, size_t* bytes);
+int gnnfd_project_bwd(const float* x, int64_t ldx, const float* W, const float* dxw, const void* xw,
+                      int xw_dtype, const float* da_src, const float* da_dst, const float* d_out,
+                      int64_t N, int64_t K, int H, int C, int Co, int algo, float* dW, float* datt_src,
+                      float* datt_dst, float* dbias, float* dx, int64_t lddx, void* ws, size_t ws_bytes,
+                      gnnfd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNFD_B200_H_ */

@@ -1,0 +1,185 @@
+"""GPU parity, floating point: the CUDA layer (through the C ABI) against the CPU oracle on identical seeded
+inputs.  Tolerances are BASELINE.json's: fp32 max-abs <= 1e-5 on logits, attention coefficients and
+gradients; bf16 feature storage <= 2e-2 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from gnn_fraud_detection_b200 import GATConv, _abi, build_csr, functional as Fn, synth
+from oracle import pyg_gatconv as O
+from util import maxabs, relerr, seeded_params
+
+pytestmark = pytest.mark.gpu
+TOL32 = 1e-5      # north_star: max-abs 1e-5 in fp32
+TOLBF = 2e-2      # north_star: 2e-2 relative in bf16
+
+
+def _layer(K, H, C, concat, W, a_s, a_d, b, dropout=0.0, **kw):
+    conv = GATConv(K, C, heads=H, concat=concat, dropout=dropout, **kw)
+    with torch.no_grad():
+        conv.lin_src.weight.copy_(W); conv.att_src.copy_(a_s); conv.att_dst.copy_(a_d); conv.bias.copy_(b)
+    return conv.cuda()
+
+
+def _fwd_bwd_case(N, E, K, H=8, C=64, concat=False, seed=0, algo=_abi.GEMM_SIMT, ei=None, need_dx=True, d_scale=None,
+                  feature_dtype=torch.float32):
+    W, a_s, a_d, b = seeded_params(K, H, C, concat, seed=seed + 1)
+    x = torch.randn(N, K, generator=torch.Generator().manual_seed(seed))
+    if ei is None:
+        ei = synth.random_graph(N, E, seed=seed + 2)
+    conv = _layer(K, H, C, concat, W, a_s, a_d, b, gemm_algo=algo, feature_dtype=feature_dtype)
+    xg = x.cuda().requires_grad_(need_dx)
+    out, (ei2, alpha) = conv(xg, ei.cuda(), return_attention_weights=True)
+    ref_out, (ref_ei, ref_alpha) = O.gatconv_forward(x, ei, W, a_s, a_d, b, H, C, concat)
+    # the reference's loss is a mean over nodes (BCEWithLogitsLoss default, src/train.py:361) => dOut ~ randn/N
+    d_out = torch.randn(ref_out.shape, generator=torch.Generator().manual_seed(seed + 3)) * (d_scale or 1.0 / max(N, 1))
+    out.backward(d_out.cuda())
+    cf = O.gatconv_backward_closed_form(x.double(), ei, W.double(), a_s.double(), a_d.double(), H, C,
+                                        d_out.double(), concat)
+    got = dict(out=out, alpha=alpha, ei=ei2, dW=conv.lin_src.weight.grad, datt_src=conv.att_src.grad,
+               datt_dst=conv.att_dst.grad, dbias=conv.bias.grad, dx=xg.grad)
+    ref = dict(out=ref_out, alpha=ref_alpha, ei=ref_ei, dW=cf["dW"], datt_src=cf["datt_src"], datt_dst=cf["datt_dst"],
+               dbias=cf["dbias"], dx=cf["dx"])
+    return got, ref
+
+
+def _assert_close(got, ref, tol=TOL32, keys=("out", "alpha", "dW", "datt_src", "datt_dst", "dbias", "dx")):
+    assert torch.equal(got["ei"].cpu(), ref["ei"])
+    for k in keys:
+        if got[k] is None:
+            continue
+        err = maxabs(got[k], ref[k])
+        assert err <= tol, f"{k}: max-abs {err:.3e} > {tol}"
+
+
+@pytest.mark.parametrize("N,E,K", [(1, 0, 5), (2, 1, 3), (64, 0, 16), (100, 300, 7), (1000, 5000, 166), (777, 9000, 165),
+                                   (5000, 20000, 64)])
+def test_layer_fwd_bwd_fp32_mean(N, E, K):
+    _assert_close(*_fwd_bwd_case(N, E, K))
+
+
+@pytest.mark.parametrize("N,E,K", [(100, 300, 7), (900, 6000, 64)])
+def test_layer_fwd_bwd_fp32_concat(N, E, K):
+    _assert_close(*_fwd_bwd_case(N, E, K, concat=True))
+
+
+def test_other_head_geometry():
+    _assert_close(*_fwd_bwd_case(300, 2000, 12, H=4, C=32))
+    _assert_close(*_fwd_bwd_case(300, 2000, 12, H=4, C=32, concat=True))
+
+
+def test_rows_longer_than_one_chunk_and_hub_rows():
+    # in-degrees 33..511 (second sweep) and > 512 (edge-balanced hub splitting with merge)
+    ei = synth.fraud_ring_skew(num_nodes=3000, background_edges=20000, num_hubs=4, hub_degree=2500, num_rings=20,
+                               ring_len=16, seed=7)
+    extra = torch.stack([torch.randint(0, 3000, (700,)), torch.full((700,), 11)])      # a 700-edge row
+    mid = torch.stack([torch.randint(0, 3000, (100,)), torch.full((100,), 12)])        # a 100-edge row
+    hub_src = torch.stack([torch.full((1500,), 13), torch.randint(0, 3000, (1500,))])  # an out-degree hub (CSC side)
+    ei = torch.cat([ei, extra, mid, hub_src], 1)
+    got, ref = _fwd_bwd_case(3000, 0, 40, ei=ei)
+    _assert_close(got, ref)
+    g = build_csr(ei.cuda(), 3000)
+    assert g.c.hub_dst.n_hub >= 5 and g.c.hub_src.n_hub >= 1
+
+
+def test_degree_skew_config5_scaled():
+    """BASELINE config #5 at reduced node count: hub in-degree 131,072 (>= 1e5) through the split path."""
+    N = 50_000
+    ei = synth.fraud_ring_skew(num_nodes=N, background_edges=200_000, num_hubs=2, hub_degree=131_072, num_rings=50,
+                               ring_len=64, seed=7)
+    got, ref = _fwd_bwd_case(N, 0, 32, ei=ei, d_scale=1.0 / N)
+    _assert_close(got, ref)
+
+
+def test_attention_dropout_with_injected_mask():
+    N, E, K, H, C = 400, 3000, 20, 8, 64
+    W, a_s, a_d, b = seeded_params(K, H, C, seed=5)
+    x = torch.randn(N, K, generator=torch.Generator().manual_seed(0))
+    ei = synth.random_graph(N, E, seed=1)
+    Ep = O.rewrite_self_loops(ei, N).size(1)
+    keep = torch.rand(Ep, H, generator=torch.Generator().manual_seed(2)) >= 0.2
+    conv = _layer(K, H, C, False, W, a_s, a_d, b, dropout=0.2, gemm_algo=_abi.GEMM_SIMT)
+    xg = x.cuda().requires_grad_(True)
+    out = conv(xg, ei.cuda(), dropout_mask=keep)
+    leaves = [t.clone().requires_grad_(True) for t in (x, W, a_s, a_d, b)]
+    ref, _ = O.gatconv_forward(leaves[0], ei, leaves[1], leaves[2], leaves[3], leaves[4], H, C, dropout_mask=keep, p=0.2)
+    d_out = torch.randn(N, C, generator=torch.Generator().manual_seed(3)) / N
+    out.backward(d_out.cuda()); ref.backward(d_out)
+    assert maxabs(out, ref) <= TOL32
+    for g_, r_ in ((xg.grad, leaves[0].grad), (conv.lin_src.weight.grad, leaves[1].grad), (conv.att_src.grad, leaves[2].grad),
+                   (conv.att_dst.grad, leaves[3].grad), (conv.bias.grad, leaves[4].grad)):
+        assert maxabs(g_, r_) <= TOL32
+    # training mode without an injected mask draws one: E[out] stays close, and eval mode is deterministic
+    conv.train(); o1 = conv(x.cuda(), ei.cuda()); o2 = conv(x.cuda(), ei.cuda())
+    assert not torch.equal(o1, o2)
+    conv.eval(); assert torch.equal(conv(x.cuda(), ei.cuda()), conv(x.cuda(), ei.cuda()))
+
+
+def test_bf16_feature_storage():
+    got, ref = _fwd_bwd_case(2000, 16000, 166, feature_dtype=torch.bfloat16, d_scale=1.0)
+    for k in ("out", "alpha", "dW", "datt_src", "datt_dst", "dbias", "dx"):
+        assert relerr(got[k], ref[k]) <= TOLBF, k
+
+
+def test_golden_layer0_with_reference_checkpoint(golden_dir):
+    from util import load_ckpt
+    from gnn_fraud_detection_b200 import GAT
+    gold = np.load(os.path.join(golden_dir, "golden_small.npz"))
+    x, ei = torch.from_numpy(gold["x"]).cuda(), torch.from_numpy(gold["edge_index"]).cuda()
+    gat = load_ckpt(GAT(x.size(1), 64, 1, num_layers=3), os.path.join(golden_dir, "gat_ckpt.npz")).cuda().eval()
+    with torch.no_grad():
+        out0, (ei2, alpha0) = gat.gat_layers[0](x, ei, return_attention_weights=True)
+    assert np.array_equal(ei2.cpu().numpy(), gold["edge_index_rewritten"])
+    assert np.abs(out0.cpu().numpy() - gold["layer0_out"]).max() <= TOL32
+    assert np.abs(alpha0.cpu().numpy() - gold["layer0_alpha"]).max() <= TOL32
+
+
+def test_elliptic_shape_full_size_layer1_and_hidden():
+    """BASELINE config #2 shape: N=203,769, E=234,355, K=166 (layer 1) and K=64 (hidden, dx needed)."""
+    x, ei, _ = synth.elliptic_synth(seed=0)
+    N = x.size(0)
+    for K, need_dx in ((166, False), (64, True)):
+        W, a_s, a_d, b = seeded_params(K, 8, 64, seed=1)
+        xk = x[:, :K].contiguous()
+        conv = _layer(K, 8, 64, False, W, a_s, a_d, b, gemm_algo=_abi.GEMM_SIMT)
+        xg = xk.cuda().requires_grad_(need_dx)
+        out, (ei2, alpha) = conv(xg, ei.cuda(), return_attention_weights=True)
+        ref_out, (ref_ei, ref_alpha) = O.gatconv_forward(xk, ei, W, a_s, a_d, b, 8, 64)
+        assert torch.equal(ei2.cpu(), ref_ei)
+        assert maxabs(out, ref_out) <= TOL32 and maxabs(alpha, ref_alpha) <= TOL32
+        d_out = torch.randn(N, 64, generator=torch.Generator().manual_seed(3)) / N
+        out.backward(d_out.cuda())
+        cf = O.gatconv_backward_closed_form(xk.double(), ei, W.double(), a_s.double(), a_d.double(), 8, 64,
+                                            d_out.double(), need_dx=need_dx)
+        assert maxabs(conv.lin_src.weight.grad, cf["dW"]) <= TOL32
+        assert maxabs(conv.att_src.grad, cf["datt_src"]) <= TOL32 and maxabs(conv.att_dst.grad, cf["datt_dst"]) <= TOL32
+        assert maxabs(conv.bias.grad, cf["dbias"]) <= TOL32
+        if need_dx:
+            assert maxabs(xg.grad, cf["dx"]) <= TOL32
+
+
+def test_size_independent_properties_large():
+    """2M-node power-law graph (too big for the oracle in seconds): attention rows sum to 1, out is a convex
+    combination (linearity in the bias, invariance to a permutation of the input edge list)."""
+    N, E, K = 2_000_000, 10_000_000, 64
+    ei = synth.powerlaw_graph(N, E, seed=5, device="cuda")
+    x = torch.randn(N, K, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    W, a_s, a_d, b = seeded_params(K, 8, 64, seed=1)
+    conv = _layer(K, 8, 64, False, W, a_s, a_d, b, gemm_algo=_abi.GEMM_SIMT)
+    with torch.no_grad():
+        out, (ei2, alpha) = conv(x, ei, return_attention_weights=True)
+        sums = torch.zeros(N, 8, device="cuda").index_add_(0, ei2[1], alpha)
+        assert float((sums - 1).abs().max()) < 1e-5
+        shuffled = ei[:, torch.randperm(E, device="cuda")].contiguous()
+        out2 = conv(x, shuffled)
+        assert float((out - out2).abs().max()) < 1e-5
+        conv.bias.add_(1.0)
+        assert float((conv(x, ei) - out - 1.0).abs().max()) < 1e-5
+
+
+def test_unsupported_geometry_raises():
+    conv = GATConv(8, 24, heads=3, concat=False).cuda()
+    with pytest.raises(_abi.GnnfdError):
+        conv(torch.randn(10, 8, device="cuda"), torch.zeros(2, 0, dtype=torch.long, device="cuda"))
