@@ -20,6 +20,8 @@ int project_bwd_dx_tc(const float* dxw, const float* W, int64_t N, int64_t K, in
                       size_t ws_bytes, cudaStream_t st);
 int project_bwd_dw_tc(const float* dxw, const float* x, int64_t ldx, int64_t N, int64_t K, int D, float* dW, void* ws,
                       size_t ws_bytes, cudaStream_t st);
+bool dw_tc_supported(int64_t K, int D);
+size_t dw_tc_ws_bytes(int64_t N, int64_t K, int D);
 }  // namespace gnnfd
 
 using namespace gnnfd;
@@ -88,12 +90,13 @@ int gnnfd_project_bwd(const float* x, int64_t ldx, const float* W, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const bool tc = a == GNNFD_GEMM_TC && N > 0;
     const size_t simt_bytes = project_bwd_ws_bytes(N, K, H, C);
+    const bool tc_dw = tc && dW && dw_tc_supported(K, H * C);
     int rc = project_bwd_simt(x, ldx, W, dxw, xw, xw_dtype, da_src, da_dst, d_out, N, K, H, C, Co, dW, datt_src,
-                              datt_dst, dbias, dx, lddx, ws, simt_bytes, st, /*skip_dw=*/tc, /*skip_dx=*/tc);
+                              datt_dst, dbias, dx, lddx, ws, simt_bytes, st, /*skip_dw=*/tc_dw, /*skip_dx=*/tc);
     if (rc || !tc) return rc;
     char* tws = reinterpret_cast<char*>(ws) + ((simt_bytes + 255) & ~size_t(255));
     const size_t tws_bytes = ws_bytes - ((simt_bytes + 255) & ~size_t(255));
-    if (dW) {
+    if (tc_dw) {
         rc = project_bwd_dw_tc(dxw, x, ldx, N, K, H * C, dW, tws, tws_bytes, st);
         if (rc) return rc;
     }

@@ -32,9 +32,10 @@ def _fwd_bwd_case(N, E, K, H=8, C=64, concat=False, seed=0, algo=_abi.GEMM_SIMT,
     conv = _layer(K, H, C, concat, W, a_s, a_d, b, gemm_algo=algo, feature_dtype=feature_dtype)
     xg = x.cuda().requires_grad_(need_dx)
     out, (ei2, alpha) = conv(xg, ei.cuda(), return_attention_weights=True)
-    ref_out, (ref_ei, ref_alpha) = O.gatconv_forward(x, ei, W, a_s, a_d, b, H, C, concat)
+    ref_out, (ref_ei, ref_alpha) = O.gatconv_forward(x.double(), ei, W.double(), a_s.double(), a_d.double(), b.double(),
+                                                     H, C, concat)
     # the reference's loss is a mean over nodes (BCEWithLogitsLoss default, src/train.py:361) => dOut ~ randn/N
-    d_out = torch.randn(ref_out.shape, generator=torch.Generator().manual_seed(seed + 3)) * (d_scale or 1.0 / max(N, 1))
+    d_out = torch.randn(tuple(ref_out.shape), generator=torch.Generator().manual_seed(seed + 3)) * (d_scale or 1.0 / max(N, 1))
     out.backward(d_out.cuda())
     cf = O.gatconv_backward_closed_form(x.double(), ei, W.double(), a_s.double(), a_d.double(), H, C,
                                         d_out.double(), concat)
@@ -45,19 +46,27 @@ def _fwd_bwd_case(N, E, K, H=8, C=64, concat=False, seed=0, algo=_abi.GEMM_SIMT,
     return got, ref
 
 
-def _assert_close(got, ref, tol=TOL32, keys=("out", "alpha", "dW", "datt_src", "datt_dst", "dbias", "dx")):
+REL32 = 1e-5     # additionally: relative L2 error against the fp64 oracle (gradients are scaled by 1/N, so the
+                 # absolute bound alone would be weak); measured on B200: <= 1e-6 for every tensor
+
+
+def _assert_close(got, ref, tol=TOL32, keys=("out", "alpha", "dW", "datt_src", "datt_dst", "dbias", "dx"), rel=REL32):
     assert torch.equal(got["ei"].cpu(), ref["ei"])
     for k in keys:
         if got[k] is None:
             continue
         err = maxabs(got[k], ref[k])
         assert err <= tol, f"{k}: max-abs {err:.3e} > {tol}"
+        if float(ref[k].double().norm()) > 1e-12:
+            r = relerr(got[k], ref[k])
+            assert r <= rel, f"{k}: relative L2 error {r:.3e} > {rel}"
 
 
 @pytest.mark.parametrize("N,E,K", [(1, 0, 5), (2, 1, 3), (64, 0, 16), (100, 300, 7), (1000, 5000, 166), (777, 9000, 165),
                                    (5000, 20000, 64)])
-def test_layer_fwd_bwd_fp32_mean(N, E, K):
-    _assert_close(*_fwd_bwd_case(N, E, K))
+@pytest.mark.parametrize("algo", [_abi.GEMM_SIMT, _abi.GEMM_TC])
+def test_layer_fwd_bwd_fp32_mean(N, E, K, algo):
+    _assert_close(*_fwd_bwd_case(N, E, K, algo=algo))
 
 
 @pytest.mark.parametrize("N,E,K", [(100, 300, 7), (900, 6000, 64)])
@@ -183,3 +192,43 @@ def test_unsupported_geometry_raises():
     conv = GATConv(8, 24, heads=3, concat=False).cuda()
     with pytest.raises(_abi.GnnfdError):
         conv(torch.randn(10, 8, device="cuda"), torch.zeros(2, 0, dtype=torch.long, device="cuda"))
+
+
+@pytest.mark.parametrize("N,K", [(1, 7), (100, 64), (1000, 166), (777, 165), (4100, 33), (130, 200)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_projection_tensor_core_3xtf32(N, K, dtype):
+    """tcgen05 projection (error-compensated 3xTF32) against the fp64 product, and against the fp32 SIMT path."""
+    H, C = 8, 64
+    W, a_s, a_d, _ = seeded_params(K, H, C, seed=3)
+    x = torch.randn(N, K, generator=torch.Generator().manual_seed(N + K))
+    xg, Wg, asg, adg = x.cuda(), W.cuda(), a_s.cuda().view(-1), a_d.cuda().view(-1)
+    xw_t, as_t, ad_t = Fn.project_fwd(xg, Wg, asg, adg, H, C, dtype, _abi.GEMM_TC)
+    xw_s, as_s, ad_s = Fn.project_fwd(xg, Wg, asg, adg, H, C, dtype, _abi.GEMM_SIMT)
+    ref = x.double() @ W.double().t()
+    ra = (ref.view(N, H, C) * a_s.double()).sum(-1)
+    rd = (ref.view(N, H, C) * a_d.double()).sum(-1)
+    if dtype == torch.float32:
+        assert maxabs(xw_t, ref) <= TOL32 and maxabs(xw_s, ref) <= TOL32
+        assert relerr(xw_t, ref) <= 2e-6
+    else:
+        assert relerr(xw_t.float(), ref) <= 4e-3
+    assert maxabs(as_t, ra) <= TOL32 and maxabs(ad_t, rd) <= TOL32
+    assert maxabs(as_t, as_s) <= TOL32
+
+
+@pytest.mark.parametrize("N,K", [(1, 7), (1000, 166), (3000, 64), (500, 300), (10000, 166), (9000, 165), (33, 256)])
+def test_projection_backward_tensor_core(N, K):
+    H, C = 8, 64
+    D = H * C
+    W, _, _, _ = seeded_params(K, H, C, seed=4)
+    g = torch.Generator().manual_seed(N)
+    x, dxw, xw = torch.randn(N, K, generator=g), torch.randn(N, D, generator=g), torch.randn(N, D, generator=g)
+    das, dad, dout = torch.randn(N, H, generator=g), torch.randn(N, H, generator=g), torch.randn(N, C, generator=g)
+    args = [t.cuda() for t in (x, W, dxw, xw, das, dad, dout)]
+    for algo in (_abi.GEMM_TC, _abi.GEMM_SIMT):
+        dW, datt_s, datt_d, dbias, dx = Fn.project_bwd(*args, H, C, C, True, algo)
+        # the tensor core accumulates with round-toward-zero: ~4e-6 relative over a 512-long reduction (measured)
+        assert relerr(dx, dxw.double() @ W.double()) <= REL32
+        assert relerr(dW, dxw.double().t() @ x.double()) <= REL32
+        assert relerr(datt_s, (das.double()[:, :, None] * xw.double().view(N, H, C)).sum(0).view(-1)) <= 2e-6
+        assert relerr(dbias, dout.double().sum(0)) <= 2e-6

@@ -27,9 +27,9 @@ def load_ckpt(model, path):
 
 
 def maxabs(a, b):
-    return float((a.double().cpu() - b.double().cpu()).abs().max()) if a.numel() else 0.0
+    return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max()) if a.numel() else 0.0
 
 
 def relerr(a, b):
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).norm() / (b.norm() + 1e-30))
