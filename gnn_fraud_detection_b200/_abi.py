@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -28,11 +28,15 @@ class HubPlan(C.Structure):
                 ("hub_row", C.c_void_p), ("hub_chunk_ptr", C.c_void_p), ("chunk_hub", C.c_void_p)]
 
 
+class ItemPlan(C.Structure):
+    _fields_ = [("n_items", C.c_int32), ("target", C.c_int32), ("item_start", C.c_void_p)]
+
+
 class Graph(C.Structure):
     _fields_ = [("n_dst", C.c_int64), ("n_src", C.c_int64), ("n_edges", C.c_int64),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("perm", C.c_void_p),
                 ("colptr", C.c_void_p), ("csc_row", C.c_void_p), ("csc_eid", C.c_void_p),
-                ("hub_dst", HubPlan), ("hub_src", HubPlan)]
+                ("hub_dst", HubPlan), ("hub_src", HubPlan), ("items_dst", ItemPlan), ("items_src", ItemPlan)]
 
 
 # name -> (restype, argtypes); every symbol include/gnnfd_b200.h declares
@@ -43,6 +47,8 @@ SIGNATURES = {
     "gnnfd_abi_version": (_i, []),
     "gnnfd_sizeof_graph": (_sz, []),
     "gnnfd_sizeof_hub_plan": (_sz, []),
+    "gnnfd_sizeof_item_plan": (_sz, []),
+    "gnnfd_item_plan": (_i, [_vp, _i64, _i64, C.c_int32, _vp, _vp]),
     "gnnfd_launch_count": (_i64, []),
     "gnnfd_launch_count_reset": (None, []),
     "gnnfd_csr_workspace_bytes": (_i, [_i64, _i64, _i, _szp]),
@@ -89,7 +95,8 @@ def lib() -> C.CDLL:
         fn.argtypes = args
     if l.gnnfd_abi_version() != ABI_VERSION:
         raise ImportError(f"libgnnfd_b200 ABI {l.gnnfd_abi_version()} != binding {ABI_VERSION}; rebuild")
-    if l.gnnfd_sizeof_graph() != C.sizeof(Graph) or l.gnnfd_sizeof_hub_plan() != C.sizeof(HubPlan):
+    if (l.gnnfd_sizeof_graph() != C.sizeof(Graph) or l.gnnfd_sizeof_hub_plan() != C.sizeof(HubPlan)
+            or l.gnnfd_sizeof_item_plan() != C.sizeof(ItemPlan)):
         raise ImportError("gnnfd_graph_t layout mismatch between header and ctypes binding")
     _lib = l
     return l

@@ -398,6 +398,20 @@ struct HubEmit {
     }
 };
 
+// ---- work-item plan ---------------------------------------------------------------------------------------
+// item_start[t] = first row i with ptr[i] >= t*target  (t = 0..n_items-1), item_start[n_items] = n_rows
+__global__ void item_plan_kernel(const int32_t* __restrict__ ptr, int64_t n_rows, int32_t target, int32_t n_items,
+                                 int32_t* __restrict__ item_start)
+{
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i <= n_rows; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t cur = ptr[i];
+        const int64_t t0 = (i == 0) ? 0 : int64_t(ptr[i - 1]) / target + 1;
+        const int64_t t1 = cur / target;
+        for (int64_t t = t0; t <= t1 && t < n_items; ++t) item_start[t] = (int32_t)i;
+        if (i == n_rows) item_start[n_items] = (int32_t)n_rows;
+    }
+}
+
 }  // namespace gnnfd
 
 using namespace gnnfd;
@@ -408,6 +422,19 @@ const char* gnnfd_last_error(void) { return g_err; }
 int gnnfd_abi_version(void) { return GNNFD_ABI_VERSION; }
 size_t gnnfd_sizeof_graph(void) { return sizeof(gnnfd_graph_t); }
 size_t gnnfd_sizeof_hub_plan(void) { return sizeof(gnnfd_hub_plan_t); }
+size_t gnnfd_sizeof_item_plan(void) { return sizeof(gnnfd_item_plan_t); }
+
+int gnnfd_item_plan(const int32_t* ptr, int64_t n_rows, int64_t n_edges, int32_t target, int32_t* item_start,
+                    gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(ptr && item_start, GNNFD_ERR_ARG, "item_plan: NULL array");
+    GNNFD_REQUIRE(n_rows >= 0 && n_edges >= 0 && target >= 1, GNNFD_ERR_ARG, "item_plan: bad sizes");
+    const int32_t n_items = (int32_t)(n_edges / target + 1);
+    item_plan_kernel<<<grid_for(n_rows + 1, 256), 256, 0, (cudaStream_t)stream>>>(ptr, n_rows, target, n_items, item_start);
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
 int64_t gnnfd_launch_count(void) { return (int64_t)g_launches.load(); }
 void gnnfd_launch_count_reset(void) { g_launches.store(0); }
 

@@ -1,0 +1,458 @@
+// (4a) backward, dst-major pass (autograd mirror of GATConv.forward's edge_update/aggregate, triggered by
+// loss.backward() at src/train.py:142; closed forms in SURVEY.md 8(a3)).
+//
+// Same warp-stream structure as the forward (gat_stream.cuh): one warp per edge-balanced work item, the
+// 2 KB source rows arrive through the bulk-copy ring.  Per chunk of <= 32 edges:
+//   phase A  lane = edge: recompute alpha from the saved row statistics, remember the LeakyReLU slope and
+//            dropout bits; runs one chunk ahead of the feature traffic;
+//   phase B  per staged source row: d_alpha[e,h] = <dO_h[i], xw[j]> -- 16 FMAs per lane then a 16-lane
+//            butterfly per head slot;
+//   phase C  lane = edge: u = alpha * d_alpha; rows that fit one chunk finish in registers
+//            (t = sum u, dz = slope * (u - alpha t)); longer rows park u in the dz buffer and make a
+//            second, feature-free sweep once t is known; hub rows are split into chunks whose partial t /
+//            da_dst are merged in chunk order -- deterministic.
+// Writes alpha_used [E',H], dz [E',H] (CSR order) and da_dst [n_dst,H].
+#include "gat_stream.cuh"
+
+#include <atomic>
+#include <climits>
+
+namespace gnnfd {
+extern std::atomic<long long> g_launches;
+int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who);
+
+// per-warp scratch beyond the ring: dal_s [32][H] floats + bits_s [2][32] ints
+template <class GE>
+constexpr int bwd_extra() { return 32 * GE::H * 4 + 2 * 32 * 4; }
+
+template <int H>
+struct RowStat {            // saved forward statistics of one destination row (all lanes identical)
+    float adst[H], m[H], inv[H];
+};
+template <int H>
+__device__ __forceinline__ void load_row_stat(RowStat<H>& r, int64_t i, const float* __restrict__ a_dst,
+                                              const float* __restrict__ rowmax, const float* __restrict__ rowsum)
+{
+    float st[H];
+    load_vecH<H>(a_dst + i * H, r.adst);
+    load_vecH<H>(rowmax + i * H, r.m);
+    load_vecH<H>(rowsum + i * H, st);
+#pragma unroll
+    for (int h = 0; h < H; ++h) r.inv[h] = 1.f / st[h];
+}
+
+// dO_h slice owned by this lane (already divided by H for the head mean)
+template <class GE, bool CONCAT>
+__device__ __forceinline__ void load_g(float (&g)[GE::NS][GE::VW], int64_t i, const float* __restrict__ d_out, int lane)
+{
+    constexpr int NS = GE::NS, VW = GE::VW, C = GE::C, D = GE::D, H = GE::H;
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        const int e0 = VW * (lane + 32 * q);
+        const float* p = CONCAT ? d_out + i * D + e0 : d_out + i * C + (e0 % C);
+#pragma unroll
+        for (int k = 0; k < VW; k += 4) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(p + k));
+            const float sc = CONCAT ? 1.f : 1.f / H;
+            g[q][k] = t.x * sc; g[q][k + 1] = t.y * sc; g[q][k + 2] = t.z * sc; g[q][k + 3] = t.w * sc;
+        }
+    }
+}
+
+struct BwdChunk {
+    int row, beg, n;
+    bool first, last;
+};
+
+// phase A: alpha (into p_s[buf]), source ids (j_s[buf]), slope/keep bits (bits_s[buf])
+template <class GE, bool DROPOUT>
+__device__ __forceinline__ void bwd_phase_a(const BwdChunk& c, const int32_t* __restrict__ col,
+                                            const int32_t* __restrict__ perm, const float* __restrict__ a_src,
+                                            const float* __restrict__ a_dst, const float* __restrict__ rowmax,
+                                            const float* __restrict__ rowsum, float slope,
+                                            const uint8_t* __restrict__ keep, float* p_s, int* j_s, int* bits_s, int lane)
+{
+    constexpr int H = GE::H;
+    RowStat<H> r;
+    load_row_stat<H>(r, c.row, a_dst, rowmax, rowsum);
+    float alpha[H];
+    int j = 0, bits = 0;
+    if (lane < c.n) {
+        j = col[c.beg + lane];
+        float as[H];
+        load_vecH<H>(a_src + int64_t(j) * H, as);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float z = as[h] + r.adst[h];
+            const bool pos = z > 0.f;
+            bits |= int(pos) << h;
+            alpha[h] = expf((pos ? z : z * slope) - r.m[h]) * r.inv[h];
+        }
+        if (DROPOUT) {
+            const uint8_t* kb = keep + int64_t(perm[c.beg + lane]) * H;
+#pragma unroll
+            for (int h = 0; h < H; ++h) bits |= int(kb[h] != 0) << (8 + h);
+        } else {
+            bits |= 0xff00;
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) alpha[h] = 0.f;
+    }
+    store_vecH<H>(p_s + lane * H, alpha);
+    j_s[lane] = j;
+    bits_s[lane] = bits;
+    __syncwarp();
+}
+
+// second sweep of a long row: dz = slope * (u - alpha * t); returns the lane-local partial of da_dst
+template <class GE>
+__device__ __forceinline__ void dst_sweep2(const RowStat<GE::H>& r, int beg, int end, const int32_t* __restrict__ col,
+                                           const float* __restrict__ a_src, float slope, const float (&t)[GE::H],
+                                           int lane, float* __restrict__ dz, float (&dad)[GE::H])
+{
+    constexpr int H = GE::H;
+    for (int e = beg + lane; e < end; e += 32) {
+        float as[H], u[H], o[H];
+        load_vecH<H>(a_src + int64_t(col[e]) * H, as);
+        load_vecH<H>(dz + int64_t(e) * H, u);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float z = as[h] + r.adst[h];
+            const float sl = z > 0.f ? 1.f : slope;
+            const float al = expf(z * sl - r.m[h]) * r.inv[h];
+            o[h] = sl * (u[h] - al * t[h]);
+            dad[h] += o[h];
+        }
+        store_vecH<H>(dz + int64_t(e) * H, o);
+    }
+}
+
+// HUB = false: whole rows, results go to da_dst.  HUB = true: one (row, range) segment, the partial t of
+// the segment goes to part_t[chunk_id]; the second sweep is a separate kernel once every chunk's t is known.
+template <class GE, bool CONCAT, bool DROPOUT, bool HUB>
+__device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bwd_extra<GE>()>& ring,
+                                               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                               const int32_t* __restrict__ perm,
+                                               const typename GE::XT* __restrict__ xw,
+                                               const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                                               const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                                               const float* __restrict__ d_out, float slope,
+                                               const uint8_t* __restrict__ keep, float keep_scale,
+                                               float* __restrict__ alpha_used, float* __restrict__ dz,
+                                               float* __restrict__ da_dst, float* __restrict__ part_t, int chunk_id,
+                                               int lane)
+{
+    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP, G = GE::G;
+    const int sub = lane / G;
+    float* dal_s = reinterpret_cast<float*>(ring.extra);
+    int* bits_s = reinterpret_cast<int*>(ring.extra + 32 * H * 4);
+    auto on_empty = [&](int r) {
+        if (!HUB && lane < H) da_dst[int64_t(r) * H + lane] = 0.f;
+    };
+    BwdChunk c0, c1;
+    int b0 = 0;
+    if (!cur.next(rowptr, c0.row, c0.beg, c0.n, c0.first, c0.last, on_empty)) return;
+    bwd_phase_a<GE, DROPOUT>(c0, col, perm, a_src, a_dst, rowmax, rowsum, slope, keep, ring.p_s + b0 * 32 * H,
+                             ring.j_s + b0 * 32, bits_s + b0 * 32, lane);
+    float g0[NS][VW], g1[NS][VW];
+    load_g<GE, CONCAT>(g0, c0.row, d_out, lane);
+    int issued0 = 0, issued1 = 0;
+    float trow[H];               // running t = sum alpha*d_alpha of the current (multi-chunk) row
+    int row_beg = c0.beg;        // first edge of the current row / segment
+#pragma unroll
+    for (int h = 0; h < H; ++h) trow[h] = 0.f;
+    while (true) {
+        const int* j0 = ring.j_s + b0 * 32;
+        const int* j1 = ring.j_s + (b0 ^ 1) * 32;
+        while (ring.has_room() && issued0 < c0.n) ring.issue(xw, j0[issued0++], lane);
+        const bool have1 = cur.next(rowptr, c1.row, c1.beg, c1.n, c1.first, c1.last, on_empty);
+        issued1 = 0;
+        if (have1) {
+            bwd_phase_a<GE, DROPOUT>(c1, col, perm, a_src, a_dst, rowmax, rowsum, slope, keep,
+                                     ring.p_s + (b0 ^ 1) * 32 * H, ring.j_s + (b0 ^ 1) * 32, bits_s + (b0 ^ 1) * 32, lane);
+            if (c1.first) load_g<GE, CONCAT>(g1, c1.row, d_out, lane);
+        }
+        if (c0.first) {
+            row_beg = c0.beg;
+#pragma unroll
+            for (int h = 0; h < H; ++h) trow[h] = 0.f;
+        }
+        // phase B: dot products of the staged rows with this row's dO slice
+        for (int t = 0; t < c0.n; ++t) {
+            const uint8_t* row = ring.front();
+            float v[NS][VW];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) lds_slot(row, q, lane, v[q]);
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                float d = 0.f;
+#pragma unroll
+                for (int k = 0; k < VW; ++k) d = fmaf(g0[q][k], v[q][k], d);
+#pragma unroll
+                for (int o = G / 2; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
+                if ((lane & (G - 1)) == 0) dal_s[t * H + q * HP + sub] = d;
+            }
+            ring.pop();
+            if (issued0 < c0.n) ring.issue(xw, j0[issued0++], lane);
+            else if (have1 && issued1 < c1.n) ring.issue(xw, j1[issued1++], lane);
+        }
+        __syncwarp();
+        // phase C: lane = edge
+        {
+            float alpha[H], dal[H], u[H], au[H];
+            const float* p0 = ring.p_s + b0 * 32 * H;
+            const int bits = bits_s[b0 * 32 + lane];
+#pragma unroll
+            for (int k = 0; k < H / 4; ++k) {
+                const float4 a4 = *reinterpret_cast<const float4*>(p0 + lane * H + 4 * k);
+                const float4 d4 = *reinterpret_cast<const float4*>(dal_s + lane * H + 4 * k);
+                alpha[4 * k] = a4.x; alpha[4 * k + 1] = a4.y; alpha[4 * k + 2] = a4.z; alpha[4 * k + 3] = a4.w;
+                dal[4 * k] = d4.x; dal[4 * k + 1] = d4.y; dal[4 * k + 2] = d4.z; dal[4 * k + 3] = d4.w;
+            }
+            const bool live = lane < c0.n;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float ks = (bits >> (8 + h)) & 1 ? keep_scale : 0.f;
+                u[h] = live ? alpha[h] * dal[h] * ks : 0.f;
+                au[h] = alpha[h] * ks;
+            }
+            if (!HUB && c0.first && c0.last) {
+                // the whole row is in registers: finish it here
+                float o[H], dad[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float tt = warp_sum(u[h]);
+                    const float sl = (bits >> h) & 1 ? 1.f : slope;
+                    o[h] = live ? sl * (u[h] - alpha[h] * tt) : 0.f;
+                    dad[h] = warp_sum(o[h]);
+                }
+                if (live) {
+                    store_vecH<H>(alpha_used + int64_t(c0.beg + lane) * H, au);
+                    store_vecH<H>(dz + int64_t(c0.beg + lane) * H, o);
+                }
+                if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
+            } else {
+                if (live) {
+                    store_vecH<H>(alpha_used + int64_t(c0.beg + lane) * H, au);
+                    store_vecH<H>(dz + int64_t(c0.beg + lane) * H, u);       // parked until t is known
+                }
+#pragma unroll
+                for (int h = 0; h < H; ++h) trow[h] += warp_sum(u[h]);
+                if (c0.last) {
+                    if (HUB) {
+                        if (lane == 0) store_vecH<H>(part_t + int64_t(chunk_id) * H, trow);
+                    } else {
+                        __syncwarp();
+                        RowStat<H> r;
+                        load_row_stat<H>(r, c0.row, a_dst, rowmax, rowsum);
+                        float dad[H];
+#pragma unroll
+                        for (int h = 0; h < H; ++h) dad[h] = 0.f;
+                        dst_sweep2<GE>(r, row_beg, c0.beg + c0.n, col, a_src, slope, trow, lane, dz, dad);
+#pragma unroll
+                        for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
+                        if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (!have1) break;
+        if (c1.first) {
+#pragma unroll
+            for (int q = 0; q < NS; ++q)
+#pragma unroll
+                for (int k = 0; k < VW; ++k) g0[q][k] = g1[q][k];
+        }
+        c0 = c1;
+        issued0 = issued1;
+        b0 ^= 1;
+    }
+}
+
+template <class GE, bool CONCAT, bool DROPOUT>
+__global__ void __launch_bounds__(ST_THREADS)
+gat_bwd_dst_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                  const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+                  const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                  const float* __restrict__ d_out, gnnfd_item_plan_t items, int hub_threshold, float slope,
+                  const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
+                  float* __restrict__ dz, float* __restrict__ da_dst)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * ST_WARPS + warp;
+    if (item >= items.n_items) return;
+    WarpRing<GE, bwd_extra<GE>()> ring;
+    ring.init(smem + warp * StreamGeo<GE, bwd_extra<GE>()>::WARP_BYTES, lane);
+    ChunkCursor cur;
+    cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
+    bwd_dst_stream<GE, CONCAT, DROPOUT, false>(cur, ring, rowptr, col, perm, xw, a_src, a_dst, rowmax, rowsum, d_out, slope,
+                                               keep, keep_scale, alpha_used, dz, da_dst, nullptr, 0, lane);
+}
+
+// hub rows, step 1: one warp per chunk -- first sweep, partial t
+template <class GE, bool CONCAT, bool DROPOUT>
+__global__ void __launch_bounds__(ST_THREADS)
+gat_bwd_dst_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                 const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+                 const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                 const float* __restrict__ d_out, gnnfd_hub_plan_t plan, float slope,
+                 const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
+                 float* __restrict__ dz, float* __restrict__ part_t)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * ST_WARPS + warp;
+    if (c >= plan.n_chunk) return;
+    const int slot = plan.chunk_hub[c];
+    const int i = plan.hub_row[slot];
+    const int beg = rowptr[i] + (c - plan.hub_chunk_ptr[slot]) * plan.chunk;
+    const int end = min(rowptr[i + 1], beg + plan.chunk);
+    WarpRing<GE, bwd_extra<GE>()> ring;
+    ring.init(smem + warp * StreamGeo<GE, bwd_extra<GE>()>::WARP_BYTES, lane);
+    ChunkCursor cur;
+    cur.start_segment(i, beg, end);
+    bwd_dst_stream<GE, CONCAT, DROPOUT, true>(cur, ring, rowptr, col, perm, xw, a_src, a_dst, rowmax, rowsum, d_out, slope,
+                                              keep, keep_scale, alpha_used, dz, nullptr, part_t, c, lane);
+}
+// hub rows, step 2: total t of the row (chunk order), second sweep, partial da_dst
+template <class GE>
+__global__ void __launch_bounds__(ROW_THREADS)
+gat_bwd_dst_hub2(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ a_src,
+                 const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                 gnnfd_hub_plan_t plan, float slope, const float* __restrict__ part_t, float* __restrict__ dz,
+                 float* __restrict__ part_dad)
+{
+    constexpr int H = GE::H;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * ROW_WARPS + warp;
+    if (c >= plan.n_chunk) return;
+    const int slot = plan.chunk_hub[c];
+    const int64_t i = plan.hub_row[slot];
+    const int c0 = plan.hub_chunk_ptr[slot], c1 = plan.hub_chunk_ptr[slot + 1];
+    const int beg = rowptr[i] + (c - c0) * plan.chunk;
+    const int end = min(rowptr[i + 1], beg + plan.chunk);
+    RowStat<H> r;
+    load_row_stat<H>(r, i, a_dst, rowmax, rowsum);
+    float t[H], dad[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) { t[h] = 0.f; dad[h] = 0.f; }
+    for (int cc = c0; cc < c1; ++cc) {   // same order in every chunk of the row => identical t
+        float pt[H];
+        load_vecH<H>(part_t + int64_t(cc) * H, pt);
+#pragma unroll
+        for (int h = 0; h < H; ++h) t[h] += pt[h];
+    }
+    dst_sweep2<GE>(r, beg, end, col, a_src, slope, t, lane, dz, dad);
+#pragma unroll
+    for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
+    if (lane == 0) store_vecH<H>(part_dad + int64_t(c) * H, dad);
+}
+// hub rows, step 3: da_dst[i] = sum of the chunk partials in chunk order
+template <int H>
+__global__ void gat_bwd_dst_hub3(gnnfd_hub_plan_t plan, const float* __restrict__ part_dad, float* __restrict__ da_dst)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= plan.n_hub * H) return;
+    const int slot = idx / H, h = idx % H;
+    float s = 0.f;
+    for (int c = plan.hub_chunk_ptr[slot]; c < plan.hub_chunk_ptr[slot + 1]; ++c) s += part_dad[int64_t(c) * H + h];
+    da_dst[int64_t(plan.hub_row[slot]) * H + h] = s;
+}
+
+template <class K>
+static int set_smem_bwd(K kernel, int bytes)
+{
+    GNNFD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return GNNFD_OK;
+}
+
+template <class GE>
+static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* a_src, const float* a_dst,
+                          const float* rowmax, const float* rowsum, const float* d_out, float slope, int concat,
+                          const uint8_t* keep, float p_drop, float* alpha_used, float* dz, float* da_dst, void* ws,
+                          size_t ws_bytes, cudaStream_t st)
+{
+    using XT = typename GE::XT;
+    constexpr int SMEM = StreamGeo<GE, bwd_extra<GE>()>::CTA_BYTES;
+    const XT* xw = reinterpret_cast<const XT*>(xw_);
+    const int64_t n = g->n_dst;
+    if (n == 0) return GNNFD_OK;
+    GNNFD_REQUIRE(g->items_dst.n_items > 0 && g->items_dst.item_start, GNNFD_ERR_ARG,
+                  "gat_bwd_dst: the graph has no work-item plan over rowptr (gnnfd_item_plan)");
+    const bool drop = keep != nullptr && p_drop > 0.f;
+    const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
+    const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
+    const unsigned grid = (unsigned)((g->items_dst.n_items + ST_WARPS - 1) / ST_WARPS);
+    int rc = GNNFD_OK;
+#define GNNFD_BWD_ITEMS(CC, DD)                                                                                        \
+    rc = set_smem_bwd(gat_bwd_dst_items<GE, CC, DD>, SMEM);                                                            \
+    if (rc) return rc;                                                                                                 \
+    gat_bwd_dst_items<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, rowmax,  \
+                                                                  rowsum, d_out, g->items_dst, thr, slope, keep, ks,    \
+                                                                  alpha_used, dz, da_dst)
+    if (concat) { if (drop) { GNNFD_BWD_ITEMS(true, true); } else { GNNFD_BWD_ITEMS(true, false); } }
+    else        { if (drop) { GNNFD_BWD_ITEMS(false, true); } else { GNNFD_BWD_ITEMS(false, false); } }
+#undef GNNFD_BWD_ITEMS
+    g_launches += 1;
+    if (g->hub_dst.n_hub > 0) {
+        const gnnfd_hub_plan_t& pl = g->hub_dst;
+        const size_t need = 2 * carve_bytes(size_t(pl.n_chunk) * GE::H, 4);
+        GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "gat_bwd_dst: workspace %zu < %zu", ws_bytes, need);
+        char* p = reinterpret_cast<char*>(ws);
+        float* part_t = carve<float>(p, size_t(pl.n_chunk) * GE::H);
+        float* part_dad = carve<float>(p, size_t(pl.n_chunk) * GE::H);
+        const unsigned gc = (unsigned)((pl.n_chunk + ST_WARPS - 1) / ST_WARPS);
+        const unsigned gc2 = (unsigned)((pl.n_chunk + ROW_WARPS - 1) / ROW_WARPS);
+#define GNNFD_BWD_HUB1(CC, DD)                                                                                         \
+    rc = set_smem_bwd(gat_bwd_dst_hub1<GE, CC, DD>, SMEM);                                                             \
+    if (rc) return rc;                                                                                                 \
+    gat_bwd_dst_hub1<GE, CC, DD><<<gc, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, rowmax,     \
+                                                               rowsum, d_out, pl, slope, keep, ks, alpha_used, dz, part_t)
+        if (concat) { if (drop) { GNNFD_BWD_HUB1(true, true); } else { GNNFD_BWD_HUB1(true, false); } }
+        else        { if (drop) { GNNFD_BWD_HUB1(false, true); } else { GNNFD_BWD_HUB1(false, false); } }
+#undef GNNFD_BWD_HUB1
+        gat_bwd_dst_hub2<GE><<<gc2, ROW_THREADS, 0, st>>>(g->rowptr, g->col, a_src, a_dst, rowmax, rowsum, pl, slope,
+                                                          part_t, dz, part_dad);
+        gat_bwd_dst_hub3<GE::H><<<(unsigned)((pl.n_hub * GE::H + 255) / 256), 256, 0, st>>>(pl, part_dad, da_dst);
+        g_launches += 3;
+    }
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+
+}  // namespace gnnfd
+
+using namespace gnnfd;
+
+extern "C" {
+
+int gnnfd_gat_bwd_dst(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src, const float* a_dst,
+                      const float* rowmax, const float* rowsum, const float* d_out, int H, int C,
+                      float negative_slope, int concat, const uint8_t* keep_mask, float p_drop, float* alpha_used,
+                      float* dz, float* da_dst, void* ws, size_t ws_bytes, gnnfd_stream_t stream)
+{
+    int rc = check_graph(g, false, "gat_bwd_dst");
+    if (rc) return rc;
+    GNNFD_REQUIRE(g->n_dst == 0 || (xw && a_src && a_dst && rowmax && rowsum && d_out && da_dst), GNNFD_ERR_ARG,
+                  "gat_bwd_dst: NULL tensor");
+    GNNFD_REQUIRE(g->n_edges == 0 || (alpha_used && dz), GNNFD_ERR_ARG, "gat_bwd_dst: alpha_used/dz is NULL");
+    GNNFD_REQUIRE(p_drop >= 0.f && p_drop < 1.f, GNNFD_ERR_ARG, "gat_bwd_dst: dropout p must be in [0,1)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (H == 8 && C == 64 && xw_dtype == GNNFD_F32)
+        return launch_bwd_dst<Geo<8, 64, float>>(g, xw, a_src, a_dst, rowmax, rowsum, d_out, negative_slope, concat,
+                                                 keep_mask, p_drop, alpha_used, dz, da_dst, ws, ws_bytes, st);
+    if (H == 8 && C == 64 && xw_dtype == GNNFD_BF16)
+        return launch_bwd_dst<Geo<8, 64, __nv_bfloat16>>(g, xw, a_src, a_dst, rowmax, rowsum, d_out, negative_slope,
+                                                         concat, keep_mask, p_drop, alpha_used, dz, da_dst, ws, ws_bytes, st);
+    if (H == 4 && C == 32 && xw_dtype == GNNFD_F32)
+        return launch_bwd_dst<Geo<4, 32, float>>(g, xw, a_src, a_dst, rowmax, rowsum, d_out, negative_slope, concat,
+                                                 keep_mask, p_drop, alpha_used, dz, da_dst, ws, ws_bytes, st);
+    GNNFD_REQUIRE(false, GNNFD_ERR_UNSUPPORTED, "gat_bwd_dst: (heads=%d, out_channels=%d, dtype=%d) is not built", H, C,
+                  xw_dtype);
+    return GNNFD_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -2,100 +2,23 @@
 //
 // Replaces edge_update + message + aggregate + head mean/concat + bias of PyG's GATConv.forward at the
 // reference call sites src/models/gat.py:80 / src/models/tgn.py:94.
-// One warp per destination row.  Per chunk of 32 edges:
-//   phase A  lane = edge: gather the source logits (32 B), LeakyReLU, chunk max / sum by warp shuffles,
-//            online-softmax rescale of the running (m, s, acc); exp() is evaluated once per (edge, head)
-//            and the weights are staged in shared memory;
-//   phase B  lane = feature slot: every edge's 2 KB (fp32) / 1 KB (bf16) source row is read with
-//            fully coalesced 128-bit loads, four edges in flight per warp, FMA into 16 accumulators.
+//
+// One warp streams one edge-balanced work item (gat_stream.cuh).  Per chunk of <= 32 edges of a row:
+//   phase A  lane = edge: gather the source logits (32 B), LeakyReLU, chunk max / sum by warp shuffles;
+//            exp() is evaluated once per (edge, head), relative to the CHUNK max, and staged in shared
+//            memory, so phase A needs no row state and can run one chunk ahead of the feature traffic;
+//   phase B  the chunk's source rows arrive through the bulk-copy ring; per row one online-softmax
+//            rescale (m, s, acc) by the chunk statistics, then per edge 4 conflict-free 128-bit shared
+//            loads and 16 FMAs per lane.
 // Rows longer than the hub threshold are split edge-balanced into chunks (one warp each) whose partial
 // (m, s, acc) are merged in chunk order by the online-softmax combine rule -- deterministic.
-#include "gat_common.cuh"
+#include "gat_stream.cuh"
 
 #include <atomic>
 #include <climits>
 
 namespace gnnfd {
 extern std::atomic<long long> g_launches;
-
-constexpr int FWD_U = 4;  // edges in flight per warp in phase B
-
-template <class GE, bool DROPOUT>
-__device__ __forceinline__ void fwd_range(int beg, int end, const int32_t* __restrict__ col,
-                                          const int32_t* __restrict__ perm,
-                                          const typename GE::XT* __restrict__ xw,
-                                          const float* __restrict__ a_src, const float (&adst)[GE::H], float slope,
-                                          const uint8_t* __restrict__ keep, float keep_scale, float (&m)[GE::H],
-                                          float (&s)[GE::H], float (&acc)[GE::NS][GE::VW], float* p_s, int* j_s,
-                                          int lane)
-{
-    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP, D = GE::D;
-    const int sub = lane / GE::G;
-    for (int base = beg; base < end; base += 32) {
-        const int n = min(32, end - base);
-        float e[H], kp[H];
-        int j = 0;
-        if (lane < n) {
-            j = col[base + lane];
-            float as[H];
-            load_vecH<H>(a_src + int64_t(j) * H, as);
-#pragma unroll
-            for (int h = 0; h < H; ++h) e[h] = leaky(as[h] + adst[h], slope);
-            if (DROPOUT) {
-                const uint8_t* kb = keep + int64_t(perm[base + lane]) * H;
-#pragma unroll
-                for (int h = 0; h < H; ++h) kp[h] = kb[h] ? keep_scale : 0.f;
-            }
-        } else {
-#pragma unroll
-            for (int h = 0; h < H; ++h) { e[h] = -INFINITY; kp[h] = 0.f; }
-        }
-        float sc[H], w[H];
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-            const float mn = fmaxf(m[h], warp_max(e[h]));
-            sc[h] = expf(m[h] - mn);
-            const float p = (lane < n) ? expf(e[h] - mn) : 0.f;
-            s[h] = s[h] * sc[h] + warp_sum(p);
-            m[h] = mn;
-            w[h] = DROPOUT ? p * kp[h] : p;
-        }
-        store_vecH<H>(p_s + lane * H, w);
-        j_s[lane] = j;
-#pragma unroll
-        for (int q = 0; q < NS; ++q) {
-            const float f = pick<HP>(sc, q, sub);
-#pragma unroll
-            for (int k = 0; k < VW; ++k) acc[q][k] *= f;
-        }
-        __syncwarp();
-        for (int t = 0; t < n; t += FWD_U) {
-            float v[FWD_U][NS][VW], wq[FWD_U][NS];
-#pragma unroll
-            for (int u = 0; u < FWD_U; ++u) {
-                const bool ok = t + u < n;
-                const int tt = ok ? t + u : t;
-                const typename GE::XT* row = xw + int64_t(j_s[tt]) * D;
-#pragma unroll
-                for (int q = 0; q < NS; ++q) {
-                    if (ok) load_slot(row, q, lane, v[u][q]);
-                    else {
-#pragma unroll
-                        for (int k = 0; k < VW; ++k) v[u][q][k] = 0.f;
-                    }
-                    wq[u][q] = ok ? p_s[tt * H + q * HP + sub] : 0.f;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < FWD_U; ++u)
-#pragma unroll
-                for (int q = 0; q < NS; ++q)
-#pragma unroll
-                    for (int k = 0; k < VW; ++k) acc[q][k] = fmaf(wq[u][q], v[u][q][k], acc[q][k]);
-        }
-        __syncwarp();
-    }
-}
 
 __device__ __forceinline__ float apply_act(float v, int act)
 {
@@ -161,75 +84,227 @@ __device__ __forceinline__ void fwd_epilogue(int64_t i, const float (&m)[GE::H],
     }
 }
 
-template <class GE, bool CONCAT, bool DROPOUT>
-__global__ void __launch_bounds__(ROW_THREADS)
-gat_fwd_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-             const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
-             const float* __restrict__ a_dst, const float* __restrict__ bias, int64_t n_dst, int hub_threshold,
-             float slope, int act, const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ out,
-             float* __restrict__ rowmax, float* __restrict__ rowsum)
+// statistics of one chunk, relative to its own maximum (all lanes hold the same values)
+template <int H>
+struct ChunkStat {
+    int row, n;
+    bool first, last;
+    float cm[H], cs[H];
+};
+
+// phase A of one chunk: writes the per-edge weights exp(e - cm) (x dropout scale) and the source ids into
+// staging buffer `buf`
+template <class GE, bool DROPOUT>
+__device__ __forceinline__ void fwd_phase_a(ChunkStat<GE::H>& c, int beg, const int32_t* __restrict__ col,
+                                            const int32_t* __restrict__ perm, const float* __restrict__ a_src,
+                                            const float* __restrict__ a_dst, float slope,
+                                            const uint8_t* __restrict__ keep, float keep_scale, float* p_s, int* j_s,
+                                            int lane)
 {
-    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW;
-    __shared__ __align__(16) float p_sh[ROW_WARPS][32 * H];
-    __shared__ int j_sh[ROW_WARPS][32];
+    constexpr int H = GE::H;
+    float e[H], kp[H], adst[H];
+    load_vecH<H>(a_dst + int64_t(c.row) * H, adst);
+    int j = 0;
+    if (lane < c.n) {
+        j = col[beg + lane];
+        float as[H];
+        load_vecH<H>(a_src + int64_t(j) * H, as);
+#pragma unroll
+        for (int h = 0; h < H; ++h) e[h] = leaky(as[h] + adst[h], slope);
+        if (DROPOUT) {
+            const uint8_t* kb = keep + int64_t(perm[beg + lane]) * H;
+#pragma unroll
+            for (int h = 0; h < H; ++h) kp[h] = kb[h] ? keep_scale : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) { e[h] = -INFINITY; kp[h] = 0.f; }
+    }
+    float w[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        c.cm[h] = warp_max(e[h]);
+        const float p = (lane < c.n) ? expf(e[h] - c.cm[h]) : 0.f;
+        c.cs[h] = warp_sum(p);
+        w[h] = DROPOUT ? p * kp[h] : p;
+    }
+    store_vecH<H>(p_s + lane * H, w);
+    j_s[lane] = j;
+    __syncwarp();
+}
+
+// What happens when a row (or a hub chunk) is complete.
+template <class GE, bool CONCAT>
+struct RowEpilogue {
+    const float* bias; int act; float* out; float* rowmax; float* rowsum;
+    __device__ __forceinline__ void finish(int row, const float (&m)[GE::H], const float (&s)[GE::H],
+                                           float (&acc)[GE::NS][GE::VW], int lane) const
+    {
+        fwd_epilogue<GE, CONCAT>(row, m, s, acc, bias, act, out, rowmax, rowsum, lane);
+    }
+    __device__ __forceinline__ void empty(int row, int lane) const
+    {
+        float m[GE::H], s[GE::H], acc[GE::NS][GE::VW];
+#pragma unroll
+        for (int h = 0; h < GE::H; ++h) { m[h] = 0.f; s[h] = 0.f; }
+#pragma unroll
+        for (int q = 0; q < GE::NS; ++q)
+#pragma unroll
+            for (int k = 0; k < GE::VW; ++k) acc[q][k] = 0.f;
+        fwd_epilogue<GE, CONCAT>(row, m, s, acc, bias, act, out, rowmax, rowsum, lane);
+    }
+};
+template <class GE>
+struct PartialSink {   // hub chunk: unnormalised partial (m, s, acc) of chunk c
+    float* part_ms; float* part_acc; int c;
+    __device__ __forceinline__ void finish(int, const float (&m)[GE::H], const float (&s)[GE::H],
+                                           float (&acc)[GE::NS][GE::VW], int lane) const
+    {
+        if (lane == 0) {
+            store_vecH<GE::H>(part_ms + int64_t(c) * 2 * GE::H, m);
+            store_vecH<GE::H>(part_ms + int64_t(c) * 2 * GE::H + GE::H, s);
+        }
+#pragma unroll
+        for (int q = 0; q < GE::NS; ++q)
+#pragma unroll
+            for (int k = 0; k < GE::VW; k += 4)
+                *reinterpret_cast<float4*>(part_acc + int64_t(c) * GE::D + GE::VW * (lane + 32 * q) + k) =
+                    make_float4(acc[q][k], acc[q][k + 1], acc[q][k + 2], acc[q][k + 3]);
+    }
+    __device__ __forceinline__ void empty(int, int) const {}
+};
+
+// The stream loop: phase A runs one chunk ahead of the ring consumption.
+template <class GE, bool DROPOUT, class Sink>
+__device__ __forceinline__ void fwd_stream(ChunkCursor& cur, WarpRing<GE>& ring, const Sink& sink,
+                                           const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                           const int32_t* __restrict__ perm,
+                                           const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+                                           const float* __restrict__ a_dst, float slope,
+                                           const uint8_t* __restrict__ keep, float keep_scale, int lane)
+{
+    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP;
+    const int sub = lane / GE::G;
+    auto on_empty = [&](int r) { sink.empty(r, lane); };
+    ChunkStat<H> c0, c1;
+    int b0 = 0;                         // staging buffer of the current chunk
+    int beg;
+    if (!cur.next(rowptr, c0.row, beg, c0.n, c0.first, c0.last, on_empty)) return;
+    fwd_phase_a<GE, DROPOUT>(c0, beg, col, perm, a_src, a_dst, slope, keep, keep_scale, ring.p_s + b0 * 32 * H,
+                             ring.j_s + b0 * 32, lane);
+    int issued0 = 0, issued1 = 0;       // edges of the current / next chunk already handed to the copy engine
+    float m[H], s[H], acc[NS][VW];
+    while (true) {
+        const int* j0 = ring.j_s + b0 * 32;
+        const int* j1 = ring.j_s + (b0 ^ 1) * 32;
+        while (ring.has_room() && issued0 < c0.n) ring.issue(xw, j0[issued0++], lane);
+        // phase A of the next chunk while the current chunk's rows are in flight
+        const bool have1 = cur.next(rowptr, c1.row, beg, c1.n, c1.first, c1.last, on_empty);
+        issued1 = 0;
+        if (have1)
+            fwd_phase_a<GE, DROPOUT>(c1, beg, col, perm, a_src, a_dst, slope, keep, keep_scale,
+                                     ring.p_s + (b0 ^ 1) * 32 * H, ring.j_s + (b0 ^ 1) * 32, lane);
+        // online-softmax combine of the running row state with this chunk
+        if (c0.first) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; }
+#pragma unroll
+            for (int q = 0; q < NS; ++q)
+#pragma unroll
+                for (int k = 0; k < VW; ++k) acc[q][k] = 0.f;
+        }
+        float fch[H];
+        {
+            float fold[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float mn = fmaxf(m[h], c0.cm[h]);
+                fold[h] = expf(m[h] - mn);          // 0 on the first chunk (m = -inf)
+                fch[h] = expf(c0.cm[h] - mn);
+                s[h] = s[h] * fold[h] + c0.cs[h] * fch[h];
+                m[h] = mn;
+            }
+            if (!c0.first) {
+#pragma unroll
+                for (int q = 0; q < NS; ++q) {
+                    const float f = pick<HP>(fold, q, sub);
+#pragma unroll
+                    for (int k = 0; k < VW; ++k) acc[q][k] *= f;
+                }
+            }
+        }
+        float fq[NS];
+#pragma unroll
+        for (int q = 0; q < NS; ++q) fq[q] = pick<HP>(fch, q, sub);
+        const float* p0 = ring.p_s + b0 * 32 * H;
+        for (int t = 0; t < c0.n; ++t) {
+            const uint8_t* row = ring.front();
+            float v[NS][VW], wq[NS];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                lds_slot(row, q, lane, v[q]);
+                wq[q] = p0[t * H + q * HP + sub] * fq[q];
+            }
+#pragma unroll
+            for (int q = 0; q < NS; ++q)
+#pragma unroll
+                for (int k = 0; k < VW; ++k) acc[q][k] = fmaf(wq[q], v[q][k], acc[q][k]);
+            ring.pop();
+            // refill the freed slot: rest of this chunk first, then run ahead into the next one
+            if (issued0 < c0.n) ring.issue(xw, j0[issued0++], lane);
+            else if (have1 && issued1 < c1.n) ring.issue(xw, j1[issued1++], lane);
+        }
+        if (c0.last) sink.finish(c0.row, m, s, acc, lane);
+        if (!have1) break;
+        c0 = c1;
+        issued0 = issued1;
+        b0 ^= 1;
+    }
+}
+
+template <class GE, bool CONCAT, bool DROPOUT>
+__global__ void __launch_bounds__(ST_THREADS)
+gat_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+              const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+              const float* __restrict__ a_dst, const float* __restrict__ bias, gnnfd_item_plan_t items,
+              int hub_threshold, float slope, int act, const uint8_t* __restrict__ keep, float keep_scale,
+              float* __restrict__ out, float* __restrict__ rowmax, float* __restrict__ rowsum)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t i = int64_t(blockIdx.x) * ROW_WARPS + warp;
-    if (i >= n_dst) return;
-    const int beg = rowptr[i], end = rowptr[i + 1];
-    if (end - beg > hub_threshold) return;  // split rows are produced by the hub kernels
-    float adst[H], m[H], s[H], acc[NS][VW];
-    load_vecH<H>(a_dst + i * H, adst);
-#pragma unroll
-    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; }
-#pragma unroll
-    for (int q = 0; q < NS; ++q)
-#pragma unroll
-        for (int k = 0; k < VW; ++k) acc[q][k] = 0.f;
-    fwd_range<GE, DROPOUT>(beg, end, col, perm, xw, a_src, adst, slope, keep, keep_scale, m, s, acc, p_sh[warp],
-                           j_sh[warp], lane);
-    fwd_epilogue<GE, CONCAT>(i, m, s, acc, bias, act, out, rowmax, rowsum, lane);
+    const int item = blockIdx.x * ST_WARPS + warp;
+    if (item >= items.n_items) return;
+    WarpRing<GE> ring;
+    ring.init(smem + warp * StreamGeo<GE>::WARP_BYTES, lane);
+    ChunkCursor cur;
+    cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
+    RowEpilogue<GE, CONCAT> sink{bias, act, out, rowmax, rowsum};
+    fwd_stream<GE, DROPOUT>(cur, ring, sink, rowptr, col, perm, xw, a_src, a_dst, slope, keep, keep_scale, lane);
 }
 
 // one warp per (hub row, chunk): partial (m, s, unnormalised acc)
 template <class GE, bool DROPOUT>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ST_THREADS)
 gat_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                    const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                    const float* __restrict__ a_dst, gnnfd_hub_plan_t plan, float slope,
                    const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ part_ms,
                    float* __restrict__ part_acc)
 {
-    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, D = GE::D;
-    __shared__ __align__(16) float p_sh[ROW_WARPS][32 * H];
-    __shared__ int j_sh[ROW_WARPS][32];
+    extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int c = blockIdx.x * ROW_WARPS + warp;
+    const int c = blockIdx.x * ST_WARPS + warp;
     if (c >= plan.n_chunk) return;
     const int slot = plan.chunk_hub[c];
-    const int64_t i = plan.hub_row[slot];
-    const int k = c - plan.hub_chunk_ptr[slot];
-    const int beg = rowptr[i] + k * plan.chunk;
+    const int i = plan.hub_row[slot];
+    const int beg = rowptr[i] + (c - plan.hub_chunk_ptr[slot]) * plan.chunk;
     const int end = min(rowptr[i + 1], beg + plan.chunk);
-    float adst[H], m[H], s[H], acc[NS][VW];
-    load_vecH<H>(a_dst + i * H, adst);
-#pragma unroll
-    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; }
-#pragma unroll
-    for (int q = 0; q < NS; ++q)
-#pragma unroll
-        for (int kk = 0; kk < VW; ++kk) acc[q][kk] = 0.f;
-    fwd_range<GE, DROPOUT>(beg, end, col, perm, xw, a_src, adst, slope, keep, keep_scale, m, s, acc, p_sh[warp],
-                           j_sh[warp], lane);
-    if (lane == 0) {
-        store_vecH<H>(part_ms + int64_t(c) * 2 * H, m);
-        store_vecH<H>(part_ms + int64_t(c) * 2 * H + H, s);
-    }
-#pragma unroll
-    for (int q = 0; q < NS; ++q)
-#pragma unroll
-        for (int kk = 0; kk < VW; kk += 4)
-            *reinterpret_cast<float4*>(part_acc + int64_t(c) * D + VW * (lane + 32 * q) + kk) =
-                make_float4(acc[q][kk], acc[q][kk + 1], acc[q][kk + 2], acc[q][kk + 3]);
+    WarpRing<GE> ring;
+    ring.init(smem + warp * StreamGeo<GE>::WARP_BYTES, lane);
+    ChunkCursor cur;
+    cur.start_segment(i, beg, end);
+    PartialSink<GE> sink{part_ms, part_acc, c};
+    fwd_stream<GE, DROPOUT>(cur, ring, sink, rowptr, col, perm, xw, a_src, a_dst, slope, keep, keep_scale, lane);
 }
 
 // one warp per hub row: merge the chunk partials in chunk order
@@ -308,25 +383,39 @@ gat_alpha_rows(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ c
     }
 }
 
+template <class K>
+static int set_smem(K kernel, int bytes)
+{
+    GNNFD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return GNNFD_OK;
+}
+
 template <class GE>
 static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_src, const float* a_dst,
                       const float* bias, float slope, int concat, int act, const uint8_t* keep, float p_drop,
                       float* out, float* rowmax, float* rowsum, void* ws, size_t ws_bytes, cudaStream_t st)
 {
     using XT = typename GE::XT;
+    constexpr int SMEM = StreamGeo<GE>::CTA_BYTES;
     const XT* xw = reinterpret_cast<const XT*>(xw_);
     const int64_t n = g->n_dst;
     if (n == 0) return GNNFD_OK;
+    GNNFD_REQUIRE(g->items_dst.n_items > 0 && g->items_dst.item_start, GNNFD_ERR_ARG,
+                  "gat_fwd: the graph has no work-item plan over rowptr (gnnfd_item_plan)");
     const bool drop = keep != nullptr && p_drop > 0.f;
     const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
     const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
-    const unsigned grid = (unsigned)((n + ROW_WARPS - 1) / ROW_WARPS);
-#define GNNFD_FWD_ROWS(CC, DD)                                                                                      \
-    gat_fwd_rows<GE, CC, DD><<<grid, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, bias, n,    \
-                                                           thr, slope, act, keep, ks, out, rowmax, rowsum)
-    if (concat) { if (drop) GNNFD_FWD_ROWS(true, true); else GNNFD_FWD_ROWS(true, false); }
-    else        { if (drop) GNNFD_FWD_ROWS(false, true); else GNNFD_FWD_ROWS(false, false); }
-#undef GNNFD_FWD_ROWS
+    const unsigned grid = (unsigned)((g->items_dst.n_items + ST_WARPS - 1) / ST_WARPS);
+    int rc = GNNFD_OK;
+#define GNNFD_FWD_ITEMS(CC, DD)                                                                                       \
+    rc = set_smem(gat_fwd_items<GE, CC, DD>, SMEM);                                                                   \
+    if (rc) return rc;                                                                                                \
+    gat_fwd_items<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, bias,       \
+                                                              g->items_dst, thr, slope, act, keep, ks, out, rowmax,    \
+                                                              rowsum)
+    if (concat) { if (drop) { GNNFD_FWD_ITEMS(true, true); } else { GNNFD_FWD_ITEMS(true, false); } }
+    else        { if (drop) { GNNFD_FWD_ITEMS(false, true); } else { GNNFD_FWD_ITEMS(false, false); } }
+#undef GNNFD_FWD_ITEMS
     g_launches += 1;
     if (g->hub_dst.n_hub > 0) {
         const gnnfd_hub_plan_t& pl = g->hub_dst;
@@ -335,14 +424,19 @@ static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_sr
         char* p = reinterpret_cast<char*>(ws);
         float* part_ms = carve<float>(p, size_t(pl.n_chunk) * 2 * GE::H);
         float* part_acc = carve<float>(p, size_t(pl.n_chunk) * GE::D);
-        const unsigned gc = (unsigned)((pl.n_chunk + ROW_WARPS - 1) / ROW_WARPS);
+        const unsigned gc = (unsigned)((pl.n_chunk + ST_WARPS - 1) / ST_WARPS);
         const unsigned gh = (unsigned)((pl.n_hub + ROW_WARPS - 1) / ROW_WARPS);
-        if (drop)
-            gat_fwd_hub_chunks<GE, true><<<gc, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, pl,
-                                                                     slope, keep, ks, part_ms, part_acc);
-        else
-            gat_fwd_hub_chunks<GE, false><<<gc, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, pl,
-                                                                      slope, keep, ks, part_ms, part_acc);
+        if (drop) {
+            rc = set_smem(gat_fwd_hub_chunks<GE, true>, SMEM);
+            if (rc) return rc;
+            gat_fwd_hub_chunks<GE, true><<<gc, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, pl,
+                                                                       slope, keep, ks, part_ms, part_acc);
+        } else {
+            rc = set_smem(gat_fwd_hub_chunks<GE, false>, SMEM);
+            if (rc) return rc;
+            gat_fwd_hub_chunks<GE, false><<<gc, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, pl,
+                                                                        slope, keep, ks, part_ms, part_acc);
+        }
         if (concat)
             gat_fwd_hub_merge<GE, true><<<gh, ROW_THREADS, 0, st>>>(pl, part_ms, part_acc, bias, act, out, rowmax, rowsum);
         else

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 1
+#define GNNFD_ABI_VERSION 2
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -71,6 +71,15 @@ typedef struct gnnfd_hub_plan {
     const int32_t* chunk_hub;      /* [n_chunk] hub slot of each chunk */
 } gnnfd_hub_plan_t;
 
+/* Edge-balanced work items over a row-pointer array: item t owns the rows whose first edge lies in
+ * [t*target, (t+1)*target), i.e. rows [item_start[t], item_start[t+1]).  One warp streams one item, so
+ * every warp moves about the same number of bytes whatever the degree distribution. */
+typedef struct gnnfd_item_plan {
+    int32_t n_items;
+    int32_t target;                /* edges per item */
+    const int32_t* item_start;     /* [n_items+1] */
+} gnnfd_item_plan_t;
+
 /* Destination-sorted CSR (+ optional source-sorted CSC twin) of the rewritten edge list.
  * Rows are destinations [0,n_dst); col[] holds source ids in [0,n_src). */
 typedef struct gnnfd_graph {
@@ -85,6 +94,8 @@ typedef struct gnnfd_graph {
     const int32_t* csc_eid;        /* [E'] CSR position of each src-sorted edge */
     gnnfd_hub_plan_t hub_dst;      /* plan over rowptr  (n_hub = 0 => none) */
     gnnfd_hub_plan_t hub_src;      /* plan over colptr */
+    gnnfd_item_plan_t items_dst;   /* work items over rowptr (required by gat_fwd / gat_bwd_dst) */
+    gnnfd_item_plan_t items_src;   /* work items over colptr (required by gat_bwd_src) */
 } gnnfd_graph_t;
 
 /* ---- introspection ------------------------------------------------------------------------- */
@@ -92,6 +103,7 @@ const char* gnnfd_last_error(void);
 int gnnfd_abi_version(void);
 size_t gnnfd_sizeof_graph(void);      /* sizeof(gnnfd_graph_t), for binding sanity checks */
 size_t gnnfd_sizeof_hub_plan(void);
+size_t gnnfd_sizeof_item_plan(void);
 /* Number of kernel launches issued by this library since the last reset (bench.py "gpu_launches"). */
 int64_t gnnfd_launch_count(void);
 void gnnfd_launch_count_reset(void);
@@ -114,6 +126,11 @@ int gnnfd_hub_plan(const int32_t* ptr, int64_t n_rows, int32_t threshold, int32_
                    int32_t* hub_row, int32_t* hub_chunk_ptr, int32_t* chunk_hub,
                    int64_t cap_hub, int64_t cap_chunk, int64_t* counts_host,
                    void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+
+/* Work-item plan over a row-pointer array.  item_start needs n_edges/target + 2 entries;
+ * n_items = n_edges/target + 1.  Fully asynchronous on `stream`. */
+int gnnfd_item_plan(const int32_t* ptr, int64_t n_rows, int64_t n_edges, int32_t target, int32_t* item_start,
+                    gnnfd_stream_t stream);
 
 /* ---- (2) projection  xw = x @ W^T, a_src/a_dst in the epilogue --------------------------------
  * Replaces: lin_src(x).view(-1,H,C); (x_src*att_src).sum(-1); (x_dst*att_dst).sum(-1).
