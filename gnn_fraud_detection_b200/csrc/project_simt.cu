@@ -242,6 +242,73 @@ __global__ void alpha_dots(const void* __restrict__ xw_, const float* __restrict
     }
 }
 
+// ---- attention-vector gradients without re-reading xw ------------------------------------------------------
+// datt_src[h,c] = sum_n da_src[n,h] * xw[n,h,c] and xw = x W^T, so
+//   datt_src[h,c] = sum_k W[hC+c,k] * G_src[h,k],   G_src = da_src^T x   ([H,K], reduction over nodes)
+// which needs x (K*4 bytes/node) instead of xw (D*s bytes/node).  Pg[s][2H][K] are slab partials.
+template <int H>
+__global__ void __launch_bounds__(256)
+dax_partial(const float* __restrict__ x, int64_t ldx, const float* __restrict__ da_src, const float* __restrict__ da_dst,
+            int64_t N, int K, int64_t rows_per_slice, float* __restrict__ Pg)
+{
+    const int64_t nb = int64_t(blockIdx.x) * rows_per_slice;
+    const int64_t ne = (nb + rows_per_slice < N) ? nb + rows_per_slice : N;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float acc[2 * H];
+#pragma unroll
+        for (int h = 0; h < 2 * H; ++h) acc[h] = 0.f;
+        int64_t n = nb;
+        for (; n + 8 <= ne; n += 8) {       // eight independent row loads in flight per thread
+            float xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = __ldg(x + (n + u) * ldx + k);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+#pragma unroll
+                for (int q = 0; q < H / 4; ++q) {
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(da_src + (n + u) * H) + q);
+                    const float4 d4 = __ldg(reinterpret_cast<const float4*>(da_dst + (n + u) * H) + q);
+                    acc[4 * q + 0] = fmaf(s4.x, xv[u], acc[4 * q + 0]); acc[4 * q + 1] = fmaf(s4.y, xv[u], acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(s4.z, xv[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(s4.w, xv[u], acc[4 * q + 3]);
+                    acc[H + 4 * q + 0] = fmaf(d4.x, xv[u], acc[H + 4 * q + 0]); acc[H + 4 * q + 1] = fmaf(d4.y, xv[u], acc[H + 4 * q + 1]);
+                    acc[H + 4 * q + 2] = fmaf(d4.z, xv[u], acc[H + 4 * q + 2]); acc[H + 4 * q + 3] = fmaf(d4.w, xv[u], acc[H + 4 * q + 3]);
+                }
+            }
+        }
+        for (; n < ne; ++n) {
+            const float xv = __ldg(x + n * ldx + k);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                acc[h] = fmaf(da_src[n * H + h], xv, acc[h]);
+                acc[H + h] = fmaf(da_dst[n * H + h], xv, acc[H + h]);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2 * H; ++h) Pg[(int64_t(blockIdx.x) * 2 * H + h) * K + k] = acc[h];
+    }
+}
+// datt_src[o] = sum_k W[o,k] * G[h(o),k],  datt_dst[o] = sum_k W[o,k] * G[H + h(o),k];  one warp per o
+__global__ void datt_from_g(const float* __restrict__ W, const float* __restrict__ G, int D, int K, int H, int C,
+                            float* __restrict__ datt_src, float* __restrict__ datt_dst)
+{
+    const int lane = threadIdx.x & 31;
+    const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (o >= D) return;
+    const int h = o / C;
+    float s = 0.f, d = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = W[int64_t(o) * K + k];
+        s = fmaf(w, G[int64_t(h) * K + k], s);
+        d = fmaf(w, G[int64_t(H + h) * K + k], d);
+    }
+    s = warp_sum(s);
+    d = warp_sum(d);
+    if (lane == 0) {
+        datt_src[o] = s;
+        datt_dst[o] = d;
+    }
+}
+
 int slices_for(int64_t N)
 {
     int64_t s = (N + 2047) / 2048;
@@ -284,7 +351,8 @@ size_t project_bwd_ws_bytes(int64_t N, int64_t K, int H, int C)
 {
     const int S = slices_for(N);
     const size_t D = size_t(H) * C;
-    return carve_bytes(size_t(S) * D * K, 4) + carve_bytes(size_t(S) * 2 * D, 4) + carve_bytes(size_t(S) * D, 4);
+    return carve_bytes(size_t(S) * D * K, 4) + carve_bytes(size_t(S) * 2 * D, 4) + carve_bytes(size_t(S) * D, 4) +
+           carve_bytes(size_t(S) * 2 * H * K, 4) + carve_bytes(size_t(2) * H * K, 4);
 }
 
 int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* dxw, const void* xw, int xw_dtype,
@@ -299,6 +367,8 @@ int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* d
     float* Pw = carve<float>(p, size_t(S) * D * K);
     float* Pa = carve<float>(p, size_t(S) * 2 * D);
     float* Pb = carve<float>(p, size_t(S) * D);
+    float* Pg = carve<float>(p, size_t(S) * 2 * H * K);
+    float* Gm = carve<float>(p, size_t(2) * H * K);
     if (N == 0) {
         if (dW) cudaMemsetAsync(dW, 0, sizeof(float) * D * K, st);
         if (datt_src) cudaMemsetAsync(datt_src, 0, sizeof(float) * D, st);
@@ -314,15 +384,23 @@ int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* d
         g_launches += 2;
     }
     if (datt_src && datt_dst) {
-        if (xw_dtype == GNNFD_BF16)
-            datt_partial<true><<<S, 512, 0, st>>>(xw, da_src, da_dst, N, D, H, C, rps, Pa);
-        else
-            datt_partial<false><<<S, 512, 0, st>>>(xw, da_src, da_dst, N, D, H, C, rps, Pa);
-        // Pa is [S][2][D]; reduce both halves in one pass, then split
-        reduce_slices<<<(unsigned)((2 * D + 255) / 256), 256, 0, st>>>(Pa, 2 * int64_t(D), S, Pb);
-        cudaMemcpyAsync(datt_src, Pb, sizeof(float) * D, cudaMemcpyDeviceToDevice, st);
-        cudaMemcpyAsync(datt_dst, Pb + D, sizeof(float) * D, cudaMemcpyDeviceToDevice, st);
-        g_launches += 2;
+        if (H == 8 || H == 4) {
+            // G = [da_src | da_dst]^T x over node slabs, then datt = W . G  (xw is not re-read)
+            if (H == 8) dax_partial<8><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);
+            else        dax_partial<4><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);
+            reduce_slices<<<(unsigned)((2 * H * K + 255) / 256), 256, 0, st>>>(Pg, int64_t(2) * H * K, S, Gm);
+            datt_from_g<<<(unsigned)((D * 32 + 255) / 256), 256, 0, st>>>(W, Gm, D, (int)K, H, C, datt_src, datt_dst);
+            g_launches += 3;
+        } else {
+            if (xw_dtype == GNNFD_BF16)
+                datt_partial<true><<<S, 512, 0, st>>>(xw, da_src, da_dst, N, D, H, C, rps, Pa);
+            else
+                datt_partial<false><<<S, 512, 0, st>>>(xw, da_src, da_dst, N, D, H, C, rps, Pa);
+            reduce_slices<<<(unsigned)((2 * D + 255) / 256), 256, 0, st>>>(Pa, 2 * int64_t(D), S, Pb);
+            cudaMemcpyAsync(datt_src, Pb, sizeof(float) * D, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(datt_dst, Pb + D, sizeof(float) * D, cudaMemcpyDeviceToDevice, st);
+            g_launches += 2;
+        }
     }
     if (dbias) {
         colsum_partial<<<S, 512, 0, st>>>(d_out, N, Co, rps, Pa);

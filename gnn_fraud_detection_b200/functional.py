@@ -28,14 +28,22 @@ def _require_f32_cuda(name: str, t: torch.Tensor):
         raise TypeError(f"{name} must be float32, got {t.dtype}")
 
 
-def project_fwd(x, W, att_src, att_dst, H, C_, xw_dtype=torch.float32, algo=_abi.GEMM_AUTO):
-    """xw [N,H*C] (xw_dtype), a_src [N,H], a_dst [N,H] = gnnfd_project_fwd(x, W, att)."""
+def project_fwd(x, W, att_src, att_dst, H, C_, xw_dtype=torch.float32, algo=_abi.GEMM_AUTO, out=None):
+    """xw [N,H*C] (xw_dtype), a_src [N,H], a_dst [N,H] = gnnfd_project_fwd(x, W, att).
+
+    ``out=(xw, a_src, a_dst)`` writes into caller-provided contiguous buffers (e.g. this rank's slice of an
+    all-gather buffer)."""
     L = _abi.lib()
     N, K = x.shape
     dev = x.device
-    xw = torch.empty(N, H * C_, dtype=xw_dtype, device=dev)
-    a_src = torch.empty(N, H, dtype=torch.float32, device=dev)
-    a_dst = torch.empty(N, H, dtype=torch.float32, device=dev)
+    if out is not None:
+        xw, a_src, a_dst = out
+        assert xw.is_contiguous() and a_src.is_contiguous() and a_dst.is_contiguous() and xw.dtype == xw_dtype
+        assert xw.shape == (N, H * C_) and a_src.shape == (N, H) and a_dst.shape == (N, H)
+    else:
+        xw = torch.empty(N, H * C_, dtype=xw_dtype, device=dev)
+        a_src = torch.empty(N, H, dtype=torch.float32, device=dev)
+        a_dst = torch.empty(N, H, dtype=torch.float32, device=dev)
     nb = C.c_size_t()
     _abi.check(L.gnnfd_project_workspace_bytes(N, K, H, C_, algo, C.byref(nb)))
     ws = _ws(nb.value, dev)
@@ -73,8 +81,11 @@ def gat_alpha(g: GraphCSR, a_src, a_dst, rowmax, rowsum, H, negative_slope):
 
 
 def gat_bwd(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, att_src, att_dst, H, C_, negative_slope, concat,
-            keep_mask=None, p_drop=0.0, da_dst_full="same"):
-    """dst-major + src-major backward passes.  Returns dxw [n_src,H*C], da_src [n_src,H], da_dst [n_dst,H]."""
+            keep_mask=None, p_drop=0.0, da_dst_full="same", da_dst_view=None):
+    """dst-major + src-major backward passes.  Returns dxw [n_src,H*C], da_src [n_src,H], da_dst [n_dst,H].
+
+    For a destination-range partition ``da_dst_full`` is a zero ``[n_src,H]`` buffer in source-position space
+    and ``da_dst_view=(lo, n)`` says where this rank's ``da_dst`` rows belong in it."""
     L = _abi.lib()
     dev = xw.device
     alpha_used = torch.empty(g.n_edges, H, dtype=torch.float32, device=dev)
@@ -91,6 +102,9 @@ def gat_bwd(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, att_src, att_d
     dxw = torch.empty(g.n_src, H * C_, dtype=torch.float32, device=dev)
     da_src = torch.empty(g.n_src, H, dtype=torch.float32, device=dev)
     full = da_dst if isinstance(da_dst_full, str) else da_dst_full
+    if da_dst_view is not None:
+        lo, n = da_dst_view
+        full[lo:lo + n].copy_(da_dst)
     _abi.check(L.gnnfd_gat_bwd_src(g.ref(), alpha_used.data_ptr(), dz.data_ptr(), d_out.data_ptr(),
                                    att_src.data_ptr(), att_dst.data_ptr(), _abi.ptr(full), H, C_, int(concat),
                                    dxw.data_ptr(), da_src.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))

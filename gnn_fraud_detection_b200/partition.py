@@ -1,0 +1,236 @@
+"""Multi-GPU partitioning of the GAT hot path on one 8xB200 NVSwitch box (one process per GPU).
+
+Two seams, both from the dataset's structure (BASELINE.json north_star item 5):
+
+* **time-step sharding** (`lpt_assign`, `snapshot_batches`): the 49 Elliptic time steps are disconnected
+  subgraphs (`create_temporal_subgraph`, ``src/data/dataset.py:198-240`` keeps only intra-step edges), so
+  snapshots are dealt to GPUs by longest-processing-time and each GPU runs its block-diagonal batch with
+  **no data-path collective**;
+* **destination-range partition** (`DstRangePlan`, `DstRangePartition`): for a scaled graph every GPU
+  owns a contiguous range of destination rows chosen on the in-degree prefix sum so that each owns
+  ~E'/G edges.  Forward: each GPU projects its own rows and the projected rows (+ source logits) are
+  exchanged with one NCCL all-gather; softmax/aggregation are then local.  Backward: the partial dxw /
+  da_src over all sources are reduce-scattered back to their owners; the small weight gradients are
+  all-reduced.
+
+Node ids are remapped to a *padded position space* ``pos(g) = owner(g) * P + (g - start[owner])`` with
+``P = max rows per rank`` so that every rank contributes an equal-sized chunk to the collectives.
+The plan (`DstRangePlan`) is pure index arithmetic and runs on any device; `DstRangePartition` executes it
+with the CUDA library.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+# ------------------------------------------------------------------------------------------------
+# time-step sharding
+# ------------------------------------------------------------------------------------------------
+def lpt_assign(weights: Sequence[float], n_bins: int) -> List[List[int]]:
+    """Longest-processing-time assignment of items (snapshots, cost = n_t + e_t) to ``n_bins`` GPUs."""
+    order = sorted(range(len(weights)), key=lambda i: (-weights[i], i))
+    loads = [0.0] * n_bins
+    bins: List[List[int]] = [[] for _ in range(n_bins)]
+    for i in order:
+        b = min(range(n_bins), key=lambda k: (loads[k], k))
+        bins[b].append(i)
+        loads[b] += weights[i]
+    return [sorted(b) for b in bins]
+
+
+def snapshot_batches(x: torch.Tensor, edge_index: torch.Tensor, time_steps: torch.Tensor, rank: int, world: int):
+    """Block-diagonal batch of the snapshots owned by ``rank``.
+
+    Returns ``(x_local, edge_index_local, node_ids)``: the nodes of the owned time steps (ascending original
+    id), the edges with both endpoints inside (original order), relabelled to the local numbering.  Because
+    no edge crosses a time step this is exactly the union of the per-snapshot subgraphs
+    (``create_temporal_subgraph`` semantics) and needs no communication.
+    """
+    steps = torch.unique(time_steps)
+    n_t = torch.stack([(time_steps == t).sum() for t in steps]).tolist()
+    e_t = torch.stack([(time_steps[edge_index[1]] == t).sum() for t in steps]).tolist()
+    mine = lpt_assign([a + b for a, b in zip(n_t, e_t)], world)[rank]
+    own = torch.zeros(int(steps.max()) + 1, dtype=torch.bool, device=x.device)
+    own[steps[torch.tensor(mine, dtype=torch.long, device=steps.device)]] = True
+    nmask = own[time_steps]
+    node_ids = torch.nonzero(nmask).reshape(-1)
+    relabel = torch.full((x.size(0),), -1, dtype=torch.int64, device=x.device)
+    relabel[node_ids] = torch.arange(node_ids.numel(), device=x.device)
+    emask = nmask[edge_index[0]] & nmask[edge_index[1]]
+    return x[node_ids], relabel[edge_index[:, emask]].contiguous(), node_ids
+
+
+# ------------------------------------------------------------------------------------------------
+# destination-range partition: the plan (index arithmetic only)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class DstRangePlan:
+    num_nodes: int
+    world: int
+    start: torch.Tensor        # [world+1] int64 row boundaries (global ids)
+    rows_padded: int           # P
+
+    @staticmethod
+    def build(edge_index: torch.Tensor, num_nodes: int, world: int) -> "DstRangePlan":
+        """Boundaries on the prefix sum of (in-degree without self-loops + 1) so each rank owns ~E'/world edges."""
+        keep = edge_index[0] != edge_index[1]
+        deg = torch.bincount(edge_index[1][keep], minlength=num_nodes) + 1
+        csum = torch.cumsum(deg, 0)
+        total = int(csum[-1]) if num_nodes > 0 else 0
+        targets = torch.tensor([total * r / world for r in range(1, world)], dtype=csum.dtype, device=csum.device)
+        cuts = torch.searchsorted(csum, targets, right=False) + 1 if world > 1 else targets.long()
+        start = torch.cat([torch.zeros(1, dtype=torch.int64, device=csum.device), cuts.long().clamp(max=num_nodes),
+                           torch.tensor([num_nodes], dtype=torch.int64, device=csum.device)])
+        start = torch.cummax(start, 0).values
+        rows = (start[1:] - start[:-1])
+        return DstRangePlan(num_nodes, world, start.cpu(), int(rows.max()) if num_nodes > 0 else 0)
+
+    def owner(self, ids: torch.Tensor) -> torch.Tensor:
+        return torch.bucketize(ids, self.start[1:].to(ids.device), right=True)
+
+    def to_pos(self, ids: torch.Tensor) -> torch.Tensor:
+        """global node id -> padded position."""
+        own = self.owner(ids)
+        return own * self.rows_padded + (ids - self.start.to(ids.device)[own])
+
+    def local_edges(self, edge_index: torch.Tensor, rank: int) -> torch.Tensor:
+        """Edges whose destination is owned by ``rank`` (self-loops rewritten PyG-style), in padded positions.
+
+        Order: the surviving original edges in their original order, then one self-loop per owned node --
+        the same relative order as the reference's ``edge_index'`` restricted to these destinations, so the
+        stable destination sort gives rows identical to the single-GPU CSR.
+        """
+        lo, hi = int(self.start[rank]), int(self.start[rank + 1])
+        src, dst = edge_index[0], edge_index[1]
+        m = (dst >= lo) & (dst < hi) & (src != dst)
+        loops = torch.arange(lo, hi, dtype=edge_index.dtype, device=edge_index.device)
+        s = torch.cat([src[m], loops])
+        d = torch.cat([dst[m], loops])
+        return torch.stack([self.to_pos(s), self.to_pos(d)]).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# destination-range partition: execution with the CUDA library + NCCL
+# ------------------------------------------------------------------------------------------------
+class DstRangePartition:
+    def __init__(self, plan: DstRangePlan, rank: int, device):
+        self.plan, self.rank, self.device = plan, rank, device
+        self.world, self.rows_padded = plan.world, plan.rows_padded
+        self.n_local = int(plan.start[rank + 1] - plan.start[rank])
+        self.n_pos = plan.world * plan.rows_padded
+        self.graph = None
+        self.build_ms = 0.0
+        self.local_ei: Optional[torch.Tensor] = None
+
+    @classmethod
+    def build(cls, edge_index: torch.Tensor, num_nodes: int, rank: int, world: int, device) -> "DstRangePartition":
+        plan = DstRangePlan.build(edge_index, num_nodes, world)
+        self = cls(plan, rank, device)
+        self.local_ei = plan.local_edges(edge_index, rank)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        self.graph = self.build_graph(self.local_ei)
+        torch.cuda.synchronize()
+        self.build_ms = (time.perf_counter() - t0) * 1e3
+        return self
+
+    def build_graph(self, local_ei: torch.Tensor):
+        """CSR over the padded position space, then the row view of this rank's destinations."""
+        from .graph import GraphCSR, build_csr
+        full = build_csr(local_ei, self.n_pos, add_self_loops=False, build_csc=True)
+        lo = self.rank * self.rows_padded
+        rowptr = full.rowptr[lo: lo + self.n_local + 1].contiguous()     # earlier rows are empty => starts at 0
+        csc_row = (full.csc_row - lo).contiguous()                        # local destination row of each CSC entry
+        g = GraphCSR(self.n_local, self.n_pos, full.n_edges, rowptr, full.col, full.perm, full.colptr, csc_row,
+                     full.csc_eid)
+        return g
+
+    def layer_fwd_bwd(self, x_local, W, a_s, a_d, bias, d_out, H, C, xw_dtype, algo, marks=None, graph=None):
+        """One GATConv layer forward + backward on this rank's destination rows.
+
+        ``x_local`` is ``[rows_padded, K]`` (rows beyond ``n_local`` are padding).  Returns
+        ``(out [n_local, C], (dW, datt_src, datt_dst, dbias))`` with the weight gradients already all-reduced.
+        """
+        from . import functional as Fn
+        g = graph or self.graph
+        P, D, dev = self.rows_padded, H * C, self.device
+        lo = self.rank * P
+        if marks: marks[0].record()
+        # forward: project own rows straight into this rank's slice of the gathered buffers
+        xw_full = torch.empty(self.n_pos, D, dtype=xw_dtype, device=dev)
+        asrc_full = torch.empty(self.n_pos, H, dtype=torch.float32, device=dev)
+        a_dst = torch.empty(P, H, dtype=torch.float32, device=dev)
+        Fn.project_fwd(x_local, W, a_s, a_d, H, C, xw_dtype, algo, out=(xw_full[lo:lo + P], asrc_full[lo:lo + P], a_dst))
+        if self.world > 1:
+            dist.all_gather_into_tensor(xw_full, xw_full[lo:lo + P])
+            dist.all_gather_into_tensor(asrc_full, asrc_full[lo:lo + P])
+        if marks: marks[1].record()
+        out, rowmax, rowsum = Fn.gat_fwd(g, xw_full, asrc_full, a_dst, bias, H, C, 0.2, False)
+        if marks: marks[2].record()
+        # backward: partials over every source position, reduce-scattered to the owners
+        da_dst_pos = torch.zeros(self.n_pos, H, dtype=torch.float32, device=dev)
+        dxw_part, dasrc_part, da_dst = Fn.gat_bwd(g, xw_full, asrc_full, a_dst, rowmax, rowsum, d_out, a_s, a_d, H, C, 0.2,
+                                                  False, da_dst_full=da_dst_pos, da_dst_view=(lo, self.n_local))
+        if self.world > 1:
+            dxw = torch.empty(P, D, dtype=torch.float32, device=dev)
+            da_src = torch.empty(P, H, dtype=torch.float32, device=dev)
+            dist.reduce_scatter_tensor(dxw, dxw_part)
+            dist.reduce_scatter_tensor(da_src, dasrc_part)
+        else:
+            dxw, da_src = dxw_part, dasrc_part
+        if marks: marks[3].record()
+        n = self.n_local
+        grads = Fn.project_bwd(x_local[:n], W, dxw[:n], xw_full[lo:lo + n], da_src[:n], da_dst, d_out, H, C, C, False, algo)
+        dW, datt_s, datt_d, dbias, _ = grads
+        if self.world > 1:
+            flat = torch.cat([dW.reshape(-1), datt_s, datt_d, dbias])
+            dist.all_reduce(flat)
+            k = dW.numel()
+            dW, datt_s, datt_d, dbias = flat[:k].view_as(dW), flat[k:k + D], flat[k + D:k + 2 * D], flat[k + 2 * D:]
+        if marks: marks[4].record()
+        return out, (dW, datt_s, datt_d, dbias)
+
+    def e2e(self, args, conv, x_local, N, E_total, K, dev):
+        """End-to-end with HOST buffers on every rank: per step H2D of this rank's feature rows and of its
+        destination-range edge list, CSR/CSC rebuild, forward + backward with the collectives, D2H of the
+        (all-reduced) weight gradients."""
+        H, C = conv.heads, conv.out_channels
+        x_host = torch.empty(x_local.shape, dtype=x_local.dtype, pin_memory=True).copy_(x_local)
+        ei_host = torch.empty(self.local_ei.shape, dtype=self.local_ei.dtype, pin_memory=True).copy_(self.local_ei)
+        W = conv.lin_src.weight.detach()
+        a_s, a_d = conv.att_src.detach().view(-1).contiguous(), conv.att_dst.detach().view(-1).contiguous()
+        bias = conv.bias.detach()
+        d_out = torch.full((self.n_local, C), 1.0 / N, device=dev)
+        steps = max(1, min(args.steps, args.e2e_steps))
+        self.graph = None
+        torch.cuda.empty_cache()
+
+        def one():
+            xd = x_host.to(dev, non_blocking=True)
+            ed = ei_host.to(dev, non_blocking=True)
+            g = self.build_graph(ed)
+            out, grads = self.layer_fwd_bwd(xd, W, a_s, a_d, bias, d_out, H, C, conv.feature_dtype, args.algo, graph=g)
+            return [t.cpu() for t in grads] + [out[:1].cpu()]
+
+        one()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = one()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        h2d = x_host.numel() * x_host.element_size() + ei_host.numel() * ei_host.element_size()
+        d2h = sum(t.numel() * t.element_size() for t in res)
+        return {"value": E_total / dt, "unit": "edges/s", "h2d_bytes_per_step": h2d * self.world,
+                "d2h_bytes_per_step": d2h * self.world, "steps": steps, "ms_per_step": dt * 1e3,
+                "includes": "per rank: H2D of own x rows + own edge list, CSR/CSC rebuild, fwd+bwd with all-gather/"
+                            "reduce-scatter/all-reduce, D2H of grads"}
