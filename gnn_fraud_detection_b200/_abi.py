@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -35,7 +35,7 @@ class ItemPlan(C.Structure):
 class Graph(C.Structure):
     _fields_ = [("n_dst", C.c_int64), ("n_src", C.c_int64), ("n_edges", C.c_int64),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("perm", C.c_void_p),
-                ("colptr", C.c_void_p), ("csc_row", C.c_void_p), ("csc_eid", C.c_void_p),
+                ("colptr", C.c_void_p), ("csc_row", C.c_void_p), ("csc_eid", C.c_void_p), ("csr2csc", C.c_void_p),
                 ("hub_dst", HubPlan), ("hub_src", HubPlan), ("items_dst", ItemPlan), ("items_src", ItemPlan)]
 
 
@@ -49,6 +49,7 @@ SIGNATURES = {
     "gnnfd_sizeof_hub_plan": (_sz, []),
     "gnnfd_sizeof_item_plan": (_sz, []),
     "gnnfd_item_plan": (_i, [_vp, _i64, _i64, C.c_int32, _vp, _vp]),
+    "gnnfd_invert_perm": (_i, [_vp, _i64, _vp, _vp]),
     "gnnfd_launch_count": (_i64, []),
     "gnnfd_launch_count_reset": (None, []),
     "gnnfd_csr_workspace_bytes": (_i, [_i64, _i64, _i, _szp]),

@@ -412,6 +412,12 @@ __global__ void item_plan_kernel(const int32_t* __restrict__ ptr, int64_t n_rows
     }
 }
 
+__global__ void invert_perm_kernel(const int32_t* __restrict__ perm, int64_t n, int32_t* __restrict__ inv)
+{
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        inv[perm[i]] = (int32_t)i;
+}
+
 }  // namespace gnnfd
 
 using namespace gnnfd;
@@ -423,6 +429,16 @@ int gnnfd_abi_version(void) { return GNNFD_ABI_VERSION; }
 size_t gnnfd_sizeof_graph(void) { return sizeof(gnnfd_graph_t); }
 size_t gnnfd_sizeof_hub_plan(void) { return sizeof(gnnfd_hub_plan_t); }
 size_t gnnfd_sizeof_item_plan(void) { return sizeof(gnnfd_item_plan_t); }
+
+int gnnfd_invert_perm(const int32_t* perm, int64_t n, int32_t* inv, gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(n >= 0 && (n == 0 || (perm && inv)), GNNFD_ERR_ARG, "invert_perm: bad arguments");
+    if (n == 0) return GNNFD_OK;
+    invert_perm_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(perm, n, inv);
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
 
 int gnnfd_item_plan(const int32_t* ptr, int64_t n_rows, int64_t n_edges, int32_t target, int32_t* item_start,
                     gnnfd_stream_t stream)

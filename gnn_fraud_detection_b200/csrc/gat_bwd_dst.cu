@@ -11,7 +11,9 @@
 //            (t = sum u, dz = slope * (u - alpha t)); longer rows park u in the dz buffer and make a
 //            second, feature-free sweep once t is known; hub rows are split into chunks whose partial t /
 //            da_dst are merged in chunk order -- deterministic.
-// Writes alpha_used [E',H], dz [E',H] (CSR order) and da_dst [n_dst,H].
+// Writes alpha_used [E',H] and dz [E',H] in SOURCE-MAJOR order (slot csr2csc[e] for dst-sorted edge e), so the
+// src-major pass -- and across GPUs the exchange to the source owners -- reads them contiguously; and
+// da_dst [n_dst,H].
 #include "gat_stream.cuh"
 
 #include <atomic>
@@ -108,14 +110,16 @@ __device__ __forceinline__ void bwd_phase_a(const BwdChunk& c, const int32_t* __
 // second sweep of a long row: dz = slope * (u - alpha * t); returns the lane-local partial of da_dst
 template <class GE>
 __device__ __forceinline__ void dst_sweep2(const RowStat<GE::H>& r, int beg, int end, const int32_t* __restrict__ col,
-                                           const float* __restrict__ a_src, float slope, const float (&t)[GE::H],
-                                           int lane, float* __restrict__ dz, float (&dad)[GE::H])
+                                           const int32_t* __restrict__ csr2csc, const float* __restrict__ a_src,
+                                           float slope, const float (&t)[GE::H], int lane, float* __restrict__ dz,
+                                           float (&dad)[GE::H])
 {
     constexpr int H = GE::H;
     for (int e = beg + lane; e < end; e += 32) {
         float as[H], u[H], o[H];
+        const int64_t pos = csr2csc[e];          // edge gradients live in source-major order
         load_vecH<H>(a_src + int64_t(col[e]) * H, as);
-        load_vecH<H>(dz + int64_t(e) * H, u);
+        load_vecH<H>(dz + pos * H, u);
 #pragma unroll
         for (int h = 0; h < H; ++h) {
             const float z = as[h] + r.adst[h];
@@ -124,7 +128,7 @@ __device__ __forceinline__ void dst_sweep2(const RowStat<GE::H>& r, int beg, int
             o[h] = sl * (u[h] - al * t[h]);
             dad[h] += o[h];
         }
-        store_vecH<H>(dz + int64_t(e) * H, o);
+        store_vecH<H>(dz + pos * H, o);
     }
 }
 
@@ -133,7 +137,7 @@ __device__ __forceinline__ void dst_sweep2(const RowStat<GE::H>& r, int beg, int
 template <class GE, bool CONCAT, bool DROPOUT, bool HUB>
 __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bwd_extra<GE>()>& ring,
                                                const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                               const int32_t* __restrict__ perm,
+                                               const int32_t* __restrict__ perm, const int32_t* __restrict__ csr2csc,
                                                const typename GE::XT* __restrict__ xw,
                                                const float* __restrict__ a_src, const float* __restrict__ a_dst,
                                                const float* __restrict__ rowmax, const float* __restrict__ rowsum,
@@ -211,6 +215,7 @@ __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bw
                 dal[4 * k] = d4.x; dal[4 * k + 1] = d4.y; dal[4 * k + 2] = d4.z; dal[4 * k + 3] = d4.w;
             }
             const bool live = lane < c0.n;
+            const int64_t pos = live ? csr2csc[c0.beg + lane] : 0;    // source-major slot of this edge
 #pragma unroll
             for (int h = 0; h < H; ++h) {
                 const float ks = (bits >> (8 + h)) & 1 ? keep_scale : 0.f;
@@ -228,14 +233,14 @@ __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bw
                     dad[h] = warp_sum(o[h]);
                 }
                 if (live) {
-                    store_vecH<H>(alpha_used + int64_t(c0.beg + lane) * H, au);
-                    store_vecH<H>(dz + int64_t(c0.beg + lane) * H, o);
+                    store_vecH<H>(alpha_used + pos * H, au);
+                    store_vecH<H>(dz + pos * H, o);
                 }
                 if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
             } else {
                 if (live) {
-                    store_vecH<H>(alpha_used + int64_t(c0.beg + lane) * H, au);
-                    store_vecH<H>(dz + int64_t(c0.beg + lane) * H, u);       // parked until t is known
+                    store_vecH<H>(alpha_used + pos * H, au);
+                    store_vecH<H>(dz + pos * H, u);       // parked until t is known
                 }
 #pragma unroll
                 for (int h = 0; h < H; ++h) trow[h] += warp_sum(u[h]);
@@ -249,7 +254,7 @@ __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bw
                         float dad[H];
 #pragma unroll
                         for (int h = 0; h < H; ++h) dad[h] = 0.f;
-                        dst_sweep2<GE>(r, row_beg, c0.beg + c0.n, col, a_src, slope, trow, lane, dz, dad);
+                        dst_sweep2<GE>(r, row_beg, c0.beg + c0.n, col, csr2csc, a_src, slope, trow, lane, dz, dad);
 #pragma unroll
                         for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
                         if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
@@ -274,7 +279,7 @@ __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bw
 template <class GE, bool CONCAT, bool DROPOUT>
 __global__ void __launch_bounds__(ST_THREADS)
 gat_bwd_dst_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                  const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+                  const int32_t* __restrict__ csr2csc, const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                   const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                   const float* __restrict__ d_out, gnnfd_item_plan_t items, int hub_threshold, float slope,
                   const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
@@ -288,7 +293,7 @@ gat_bwd_dst_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     ring.init(smem + warp * StreamGeo<GE, bwd_extra<GE>()>::WARP_BYTES, lane);
     ChunkCursor cur;
     cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
-    bwd_dst_stream<GE, CONCAT, DROPOUT, false>(cur, ring, rowptr, col, perm, xw, a_src, a_dst, rowmax, rowsum, d_out, slope,
+    bwd_dst_stream<GE, CONCAT, DROPOUT, false>(cur, ring, rowptr, col, perm, csr2csc, xw, a_src, a_dst, rowmax, rowsum, d_out, slope,
                                                keep, keep_scale, alpha_used, dz, da_dst, nullptr, 0, lane);
 }
 
@@ -296,7 +301,7 @@ gat_bwd_dst_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
 template <class GE, bool CONCAT, bool DROPOUT>
 __global__ void __launch_bounds__(ST_THREADS)
 gat_bwd_dst_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                 const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+                 const int32_t* __restrict__ csr2csc, const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                  const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                  const float* __restrict__ d_out, gnnfd_hub_plan_t plan, float slope,
                  const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
@@ -314,13 +319,14 @@ gat_bwd_dst_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     ring.init(smem + warp * StreamGeo<GE, bwd_extra<GE>()>::WARP_BYTES, lane);
     ChunkCursor cur;
     cur.start_segment(i, beg, end);
-    bwd_dst_stream<GE, CONCAT, DROPOUT, true>(cur, ring, rowptr, col, perm, xw, a_src, a_dst, rowmax, rowsum, d_out, slope,
+    bwd_dst_stream<GE, CONCAT, DROPOUT, true>(cur, ring, rowptr, col, perm, csr2csc, xw, a_src, a_dst, rowmax, rowsum, d_out, slope,
                                               keep, keep_scale, alpha_used, dz, nullptr, part_t, c, lane);
 }
 // hub rows, step 2: total t of the row (chunk order), second sweep, partial da_dst
 template <class GE>
 __global__ void __launch_bounds__(ROW_THREADS)
-gat_bwd_dst_hub2(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ a_src,
+gat_bwd_dst_hub2(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                 const int32_t* __restrict__ csr2csc, const float* __restrict__ a_src,
                  const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                  gnnfd_hub_plan_t plan, float slope, const float* __restrict__ part_t, float* __restrict__ dz,
                  float* __restrict__ part_dad)
@@ -345,7 +351,7 @@ gat_bwd_dst_hub2(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
 #pragma unroll
         for (int h = 0; h < H; ++h) t[h] += pt[h];
     }
-    dst_sweep2<GE>(r, beg, end, col, a_src, slope, t, lane, dz, dad);
+    dst_sweep2<GE>(r, beg, end, col, csr2csc, a_src, slope, t, lane, dz, dad);
 #pragma unroll
     for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
     if (lane == 0) store_vecH<H>(part_dad + int64_t(c) * H, dad);
@@ -390,7 +396,7 @@ static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* 
 #define GNNFD_BWD_ITEMS(CC, DD)                                                                                        \
     rc = set_smem_bwd(gat_bwd_dst_items<GE, CC, DD>, SMEM);                                                            \
     if (rc) return rc;                                                                                                 \
-    gat_bwd_dst_items<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, rowmax,  \
+    gat_bwd_dst_items<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, xw, a_src, a_dst, rowmax,  \
                                                                   rowsum, d_out, g->items_dst, thr, slope, keep, ks,    \
                                                                   alpha_used, dz, da_dst)
     if (concat) { if (drop) { GNNFD_BWD_ITEMS(true, true); } else { GNNFD_BWD_ITEMS(true, false); } }
@@ -409,12 +415,12 @@ static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* 
 #define GNNFD_BWD_HUB1(CC, DD)                                                                                         \
     rc = set_smem_bwd(gat_bwd_dst_hub1<GE, CC, DD>, SMEM);                                                             \
     if (rc) return rc;                                                                                                 \
-    gat_bwd_dst_hub1<GE, CC, DD><<<gc, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, rowmax,     \
+    gat_bwd_dst_hub1<GE, CC, DD><<<gc, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, xw, a_src, a_dst, rowmax,     \
                                                                rowsum, d_out, pl, slope, keep, ks, alpha_used, dz, part_t)
         if (concat) { if (drop) { GNNFD_BWD_HUB1(true, true); } else { GNNFD_BWD_HUB1(true, false); } }
         else        { if (drop) { GNNFD_BWD_HUB1(false, true); } else { GNNFD_BWD_HUB1(false, false); } }
 #undef GNNFD_BWD_HUB1
-        gat_bwd_dst_hub2<GE><<<gc2, ROW_THREADS, 0, st>>>(g->rowptr, g->col, a_src, a_dst, rowmax, rowsum, pl, slope,
+        gat_bwd_dst_hub2<GE><<<gc2, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->csr2csc, a_src, a_dst, rowmax, rowsum, pl, slope,
                                                           part_t, dz, part_dad);
         gat_bwd_dst_hub3<GE::H><<<(unsigned)((pl.n_hub * GE::H + 255) / 256), 256, 0, st>>>(pl, part_dad, da_dst);
         g_launches += 3;
@@ -439,6 +445,8 @@ int gnnfd_gat_bwd_dst(const gnnfd_graph_t* g, const void* xw, int xw_dtype, cons
     GNNFD_REQUIRE(g->n_dst == 0 || (xw && a_src && a_dst && rowmax && rowsum && d_out && da_dst), GNNFD_ERR_ARG,
                   "gat_bwd_dst: NULL tensor");
     GNNFD_REQUIRE(g->n_edges == 0 || (alpha_used && dz), GNNFD_ERR_ARG, "gat_bwd_dst: alpha_used/dz is NULL");
+    GNNFD_REQUIRE(g->n_edges == 0 || g->csr2csc, GNNFD_ERR_ARG,
+                  "gat_bwd_dst: csr2csc is NULL (edge gradients are emitted in source-major order)");
     GNNFD_REQUIRE(p_drop >= 0.f && p_drop < 1.f, GNNFD_ERR_ARG, "gat_bwd_dst: dropout p must be in [0,1)");
     cudaStream_t st = (cudaStream_t)stream;
     if (H == 8 && C == 64 && xw_dtype == GNNFD_F32)

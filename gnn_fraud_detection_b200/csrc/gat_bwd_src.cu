@@ -33,7 +33,7 @@ __device__ __forceinline__ void src_range(int beg, int end, const int32_t* __res
         const int n = min(32, end - base);
         int i = 0;
         if (lane < n) {
-            const int64_t eid = csc_eid[base + lane];
+            const int64_t eid = base + lane;      // alpha_used / dz are stored in source-major order
             i = csc_row[base + lane];
             float al[H], dzv[H];
             load_vecH<H>(alpha_used + eid * H, al);

@@ -35,6 +35,11 @@ class GraphCSR:
         self.c.n_dst, self.c.n_src, self.c.n_edges = self.n_dst, self.n_src, self.n_edges
         self.c.rowptr, self.c.col, self.c.perm = _abi.ptr(rowptr), _abi.ptr(col), _abi.ptr(perm)
         self.c.colptr, self.c.csc_row, self.c.csc_eid = _abi.ptr(colptr), _abi.ptr(csc_row), _abi.ptr(csc_eid)
+        self.csr2csc = None
+        if csc_eid is not None and self.n_edges > 0:
+            self.csr2csc = torch.empty(self.n_edges, dtype=torch.int32, device=self.device)
+            _abi.check(_abi.lib().gnnfd_invert_perm(csc_eid.data_ptr(), self.n_edges, self.csr2csc.data_ptr(), _stream()))
+        self.c.csr2csc = _abi.ptr(self.csr2csc)
         if plan_hubs:
             self.c.hub_dst = self._plan(rowptr, self.n_dst, hub_threshold, hub_chunk)
             if colptr is not None:

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 2
+#define GNNFD_ABI_VERSION 3
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -92,6 +92,7 @@ typedef struct gnnfd_graph {
     const int32_t* colptr;         /* [n_src+1]  (NULL when no CSC was built) */
     const int32_t* csc_row;        /* [E'] destination of each src-sorted edge */
     const int32_t* csc_eid;        /* [E'] CSR position of each src-sorted edge */
+    const int32_t* csr2csc;        /* [E'] inverse of csc_eid: source-major position of each dst-sorted edge */
     gnnfd_hub_plan_t hub_dst;      /* plan over rowptr  (n_hub = 0 => none) */
     gnnfd_hub_plan_t hub_src;      /* plan over colptr */
     gnnfd_item_plan_t items_dst;   /* work items over rowptr (required by gat_fwd / gat_bwd_dst) */
@@ -127,6 +128,9 @@ int gnnfd_hub_plan(const int32_t* ptr, int64_t n_rows, int32_t threshold, int32_
                    int64_t cap_hub, int64_t cap_chunk, int64_t* counts_host,
                    void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 
+/* inv[perm[i]] = i for a permutation of [0,n) (used for csr2csc = inverse of csc_eid). */
+int gnnfd_invert_perm(const int32_t* perm, int64_t n, int32_t* inv, gnnfd_stream_t stream);
+
 /* Work-item plan over a row-pointer array.  item_start needs n_edges/target + 2 entries;
  * n_items = n_edges/target + 1.  Fully asynchronous on `stream`. */
 int gnnfd_item_plan(const int32_t* ptr, int64_t n_rows, int64_t n_edges, int32_t target, int32_t* item_start,
@@ -161,7 +165,10 @@ int gnnfd_gat_alpha(const gnnfd_graph_t* g, const float* a_src, const float* a_d
 
 /* ---- (4) backward ----------------------------------------------------------------------------
  * dst-major pass: recomputes alpha, forms d_alpha = <dO_h[i], xw[j]>, softmax + LeakyReLU backward.
- *   writes alpha_used [E',H] (alpha after dropout scaling), dz [E',H] (both CSR order), da_dst [n_dst,H].
+ *   writes alpha_used [E',H] (alpha after dropout scaling) and dz [E',H] -- both in SOURCE-MAJOR (CSC)
+ *   order, i.e. the value of dst-sorted edge e lands at row csr2csc[e], so that the src-major pass (and,
+ *   across GPUs, the exchange to the source owners) reads them contiguously -- and da_dst [n_dst,H].
+ *   Needs the CSC twin and csr2csc.
  * src-major pass (needs the CSC twin): dxw[j] = sum_e alpha_used*dO_h[i] + da_src[j]*att_src
  *   + da_dst_full[j]*att_dst, da_src[j] = sum_e dz.  da_dst_full is indexed by SOURCE id (for a single
  *   GPU it is the da_dst the dst pass produced; NULL => the att_dst term is skipped).

@@ -222,7 +222,8 @@ def test_projection_backward_tensor_core(N, K):
     D = H * C
     W, _, _, _ = seeded_params(K, H, C, seed=4)
     g = torch.Generator().manual_seed(N)
-    x, dxw, xw = torch.randn(N, K, generator=g), torch.randn(N, D, generator=g), torch.randn(N, D, generator=g)
+    x, dxw = torch.randn(N, K, generator=g), torch.randn(N, D, generator=g)
+    xw = x @ W.t()          # datt is computed as W . (da^T x), which equals sum_n da * xw only for the true xw
     das, dad, dout = torch.randn(N, H, generator=g), torch.randn(N, H, generator=g), torch.randn(N, C, generator=g)
     args = [t.cuda() for t in (x, W, dxw, xw, das, dad, dout)]
     for algo in (_abi.GEMM_TC, _abi.GEMM_SIMT):
@@ -230,5 +231,7 @@ def test_projection_backward_tensor_core(N, K):
         # the tensor core accumulates with round-toward-zero: ~4e-6 relative over a 512-long reduction (measured)
         assert relerr(dx, dxw.double() @ W.double()) <= REL32
         assert relerr(dW, dxw.double().t() @ x.double()) <= REL32
-        assert relerr(datt_s, (das.double()[:, :, None] * xw.double().view(N, H, C)).sum(0).view(-1)) <= 2e-6
+        xw64 = (x.double() @ W.double().t()).view(N, H, C)
+        assert relerr(datt_s, (das.double()[:, :, None] * xw64).sum(0).view(-1)) <= 2e-6
+        assert relerr(datt_d, (dad.double()[:, :, None] * xw64).sum(0).view(-1)) <= 2e-6
         assert relerr(dbias, dout.double().sum(0)) <= 2e-6
