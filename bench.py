@@ -231,11 +231,15 @@ def run_gpu_arm(args):
         d_out = torch.full((N, C), 1.0 / N, device=dev)      # timing only; parity runs use randn/N
         n_local, part = N, None
     else:
-        part = partition.DstRangePartition.build(ei, N, rank, world, dev)
+        Part = partition.ReplicatedInputPartition if args.mgpu == "replicate" else partition.DstRangePartition
+        part = Part.build(ei, N, rank, world, dev)
         del ei
         g, Ep, n_local = part.graph, part.graph.n_edges, part.n_local
         csr_ms = part.build_ms
-        x = torch.randn(part.rows_padded, K, device=dev, generator=gen)   # this rank's rows of x
+        if args.mgpu == "replicate":   # the layer input is resident on every GPU (same seed => identical copies)
+            x = torch.randn(part.n_pos, K, device=dev, generator=gen)
+        else:                          # this rank's rows of x
+            x = torch.randn(part.rows_padded, K, device=dev, generator=gen)
         d_out = torch.full((n_local, C), 1.0 / N, device=dev)
     gen_s = time.perf_counter() - t_gen
 
@@ -363,7 +367,10 @@ def run_gpu_arm(args):
             "config": {"workload": workload, "nodes": N, "edges": E_total, "edges_after_self_loop_rewrite": Ep_total,
                        "in_features": K, "heads": H, "out_channels": C, "concat": False,
                        "l2": "inputs larger than L2 (xw %.1f GB per pass)" % (N * H * C * s_bytes / 1e9),
-                       "parallelism": "1 GPU" if world == 1 else f"dst-range x{world}, NCCL all-gather of projected features",
+                       "parallelism": "1 GPU" if world == 1 else (
+                           f"dst-range x{world}: replicated input + redundant projection, all-to-all of per-edge grads, "
+                           f"all-gather of dOut" if args.mgpu == "replicate" else
+                           f"dst-range x{world}: NCCL all-gather of projected features, reduce-scatter of dxw"),
                        "csr_build_ms": csr_ms, "setup_s": gen_s, "gemm_algo": args.algo, "note": note},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
@@ -420,6 +427,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--mgpu", default="replicate", choices=["replicate", "allgather"],
+                    help="multi-GPU variant of the destination-range partition (see partition.py)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -36,7 +36,8 @@ class Graph(C.Structure):
     _fields_ = [("n_dst", C.c_int64), ("n_src", C.c_int64), ("n_edges", C.c_int64),
                 ("rowptr", C.c_void_p), ("col", C.c_void_p), ("perm", C.c_void_p),
                 ("colptr", C.c_void_p), ("csc_row", C.c_void_p), ("csc_eid", C.c_void_p), ("csr2csc", C.c_void_p),
-                ("hub_dst", HubPlan), ("hub_src", HubPlan), ("items_dst", ItemPlan), ("items_src", ItemPlan)]
+                ("hub_dst", HubPlan), ("hub_src", HubPlan), ("items_dst", ItemPlan), ("items_src", ItemPlan),
+                ("edge_grads_indirect", C.c_int32), ("reserved_", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/gnnfd_b200.h declares

@@ -33,7 +33,8 @@ __device__ __forceinline__ void src_range(int beg, int end, const int32_t* __res
         const int n = min(32, end - base);
         int i = 0;
         if (lane < n) {
-            const int64_t eid = base + lane;      // alpha_used / dz are stored in source-major order
+            // edge gradients are normally stored in source-major order; csc_eid != NULL = indirect (multi-GPU receive buffer)
+            const int64_t eid = csc_eid ? int64_t(csc_eid[base + lane]) : int64_t(base + lane);
             i = csc_row[base + lane];
             float al[H], dzv[H];
             load_vecH<H>(alpha_used + eid * H, al);
@@ -205,13 +206,14 @@ static int launch_bwd_src(const gnnfd_graph_t* g, const float* alpha_used, const
 {
     const int64_t n = g->n_src;
     if (n == 0) return GNNFD_OK;
+    const int32_t* eid_ptr = g->edge_grads_indirect ? g->csc_eid : nullptr;
     const int thr = g->hub_src.n_hub > 0 ? g->hub_src.threshold : INT_MAX;
     const unsigned grid = (unsigned)((n + ROW_WARPS - 1) / ROW_WARPS);
     if (concat)
-        gat_bwd_src_rows<GE, true><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, g->csc_eid, alpha_used, dz, d_out,
+        gat_bwd_src_rows<GE, true><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, d_out,
                                                                  att_src, att_dst, da_dst_full, n, thr, dxw, da_src);
     else
-        gat_bwd_src_rows<GE, false><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, g->csc_eid, alpha_used, dz, d_out,
+        gat_bwd_src_rows<GE, false><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, d_out,
                                                                   att_src, att_dst, da_dst_full, n, thr, dxw, da_src);
     g_launches += 1;
     if (g->hub_src.n_hub > 0) {
@@ -224,12 +226,12 @@ static int launch_bwd_src(const gnnfd_graph_t* g, const float* alpha_used, const
         const unsigned gc = (unsigned)((pl.n_chunk + ROW_WARPS - 1) / ROW_WARPS);
         const unsigned gh = (unsigned)((pl.n_hub + ROW_WARPS - 1) / ROW_WARPS);
         if (concat) {
-            gat_bwd_src_hub_chunks<GE, true><<<gc, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, g->csc_eid, alpha_used, dz,
+            gat_bwd_src_hub_chunks<GE, true><<<gc, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz,
                                                                          d_out, pl, part_acc, part_das);
             gat_bwd_src_hub_merge<GE, true><<<gh, ROW_THREADS, 0, st>>>(pl, part_acc, part_das, att_src, att_dst,
                                                                         da_dst_full, dxw, da_src);
         } else {
-            gat_bwd_src_hub_chunks<GE, false><<<gc, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, g->csc_eid, alpha_used, dz,
+            gat_bwd_src_hub_chunks<GE, false><<<gc, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz,
                                                                           d_out, pl, part_acc, part_das);
             gat_bwd_src_hub_merge<GE, false><<<gh, ROW_THREADS, 0, st>>>(pl, part_acc, part_das, att_src, att_dst,
                                                                          da_dst_full, dxw, da_src);

@@ -86,6 +86,19 @@ def gat_bwd(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, att_src, att_d
 
     For a destination-range partition ``da_dst_full`` is a zero ``[n_src,H]`` buffer in source-position space
     and ``da_dst_view=(lo, n)`` says where this rank's ``da_dst`` rows belong in it."""
+    alpha_used, dz, da_dst = gat_bwd_dst(g, xw, a_src, a_dst, rowmax, rowsum, d_out, H, C_, negative_slope, concat,
+                                         keep_mask, p_drop)
+    full = da_dst if isinstance(da_dst_full, str) else da_dst_full
+    if da_dst_view is not None:
+        lo, n = da_dst_view
+        full[lo:lo + n].copy_(da_dst)
+    dxw, da_src = gat_bwd_src(g, alpha_used, dz, d_out, att_src, att_dst, full, H, C_, concat)
+    return dxw, da_src, da_dst
+
+
+def gat_bwd_dst(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, H, C_, negative_slope, concat, keep_mask=None,
+                p_drop=0.0):
+    """dst-major pass: alpha_used [E',H], dz [E',H] (both in source-major order) and da_dst [n_dst,H]."""
     L = _abi.lib()
     dev = xw.device
     alpha_used = torch.empty(g.n_edges, H, dtype=torch.float32, device=dev)
@@ -99,16 +112,22 @@ def gat_bwd(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, att_src, att_d
                                    float(negative_slope), int(concat), _abi.ptr(keep_mask), float(p_drop),
                                    alpha_used.data_ptr(), dz.data_ptr(), da_dst.data_ptr(), ws.data_ptr(),
                                    ws.numel(), _stream()))
+    return alpha_used, dz, da_dst
+
+
+def gat_bwd_src(g: GraphCSR, alpha_used, dz, d_out, att_src, att_dst, da_dst_full, H, C_, concat):
+    """src-major pass over g's CSC: dxw [n_src,H*C] and da_src [n_src,H]."""
+    L = _abi.lib()
+    dev = alpha_used.device
     dxw = torch.empty(g.n_src, H * C_, dtype=torch.float32, device=dev)
     da_src = torch.empty(g.n_src, H, dtype=torch.float32, device=dev)
-    full = da_dst if isinstance(da_dst_full, str) else da_dst_full
-    if da_dst_view is not None:
-        lo, n = da_dst_view
-        full[lo:lo + n].copy_(da_dst)
+    nb = C.c_size_t()
+    _abi.check(L.gnnfd_gat_bwd_workspace_bytes(g.ref(), H, C_, C.byref(nb)))
+    ws = _ws(nb.value, dev)
     _abi.check(L.gnnfd_gat_bwd_src(g.ref(), alpha_used.data_ptr(), dz.data_ptr(), d_out.data_ptr(),
-                                   att_src.data_ptr(), att_dst.data_ptr(), _abi.ptr(full), H, C_, int(concat),
+                                   att_src.data_ptr(), att_dst.data_ptr(), _abi.ptr(da_dst_full), H, C_, int(concat),
                                    dxw.data_ptr(), da_src.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-    return dxw, da_src, da_dst
+    return dxw, da_src
 
 
 def project_bwd(x, W, dxw, xw, da_src, da_dst, d_out, H, C_, Co, need_dx, algo=_abi.GEMM_AUTO):

@@ -234,3 +234,148 @@ class DstRangePartition:
                 "d2h_bytes_per_step": d2h * self.world, "steps": steps, "ms_per_step": dt * 1e3,
                 "includes": "per rank: H2D of own x rows + own edge list, CSR/CSC rebuild, fwd+bwd with all-gather/"
                             "reduce-scatter/all-reduce, D2H of grads"}
+
+
+class ReplicatedInputPartition(DstRangePartition):
+    """Destination-range partition without the two feature-sized collectives (variant (c)).
+
+    * forward: the layer INPUT ``x [N,K]`` (664 B/row instead of 2 KB/row, and static for layer 1) is resident on
+      every GPU and projected redundantly -- writing xw locally at HBM speed is ~8x faster than receiving it
+      over NVLink -- so the forward needs no communication at all;
+    * backward: instead of reduce-scattering ``dxw [N,512]`` partials (41 GB on the 200M-edge graph) the
+      per-edge gradients (alpha_used, dz: 64 B/edge), which ``gat_bwd_dst`` already emits grouped by source
+      owner (source-major order), are sent to the owner of each source with one all-to-all, ``dOut [N,64]`` is
+      all-gathered, and every GPU runs the src-major pass for ITS OWN source rows over all of their out-edges.
+      ``dxw`` is then complete where it is needed: no reduce-scatter, and the projection backward is local.
+    Per step and GPU this moves ~(E'/G)*64 B + N*256 B over NVLink instead of ~2*N*2 KB.
+    """
+
+    @classmethod
+    def build(cls, edge_index, num_nodes, rank, world, device):
+        plan = DstRangePlan.build(edge_index, num_nodes, world)
+        self = cls(plan, rank, device)
+        self.local_ei = plan.local_edges(edge_index, rank)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        self.graph = self.build_graph(self.local_ei)
+        self.rgraph = self.build_exchange(self.graph)
+        torch.cuda.synchronize()
+        self.build_ms = (time.perf_counter() - t0) * 1e3
+        return self
+
+    def build_exchange(self, g):
+        """Receiver-side CSC: for every source row this rank owns, its out-edges on ALL ranks."""
+        from .graph import GraphCSR, build_csr
+        P, G, dev = self.rows_padded, self.world, self.device
+        colptr = g.colptr.long()
+        bounds = colptr[torch.arange(0, G + 1, device=dev) * P]
+        send = (bounds[1:] - bounds[:-1]).contiguous()
+        recv = torch.empty_like(send)
+        if G > 1:
+            dist.all_to_all_single(recv, send)
+        else:
+            recv.copy_(send)
+        self.send_splits, self.recv_splits = send.tolist(), recv.tolist()
+        M = int(sum(self.recv_splits))
+        src_pos = torch.repeat_interleave(torch.arange(self.n_pos, device=dev, dtype=torch.int32),
+                                          (colptr[1:] - colptr[:-1]))
+        dst_pos = g.csc_row + self.rank * P
+        meta_send = torch.stack([src_pos, dst_pos.to(torch.int32)], dim=1).contiguous()
+        meta_recv = torch.empty(M, 2, dtype=torch.int32, device=dev)
+        if G > 1:
+            dist.all_to_all_single(meta_recv, meta_send, self.recv_splits, self.send_splits)
+        else:
+            meta_recv.copy_(meta_send)
+        # stable sort of the received entries by (local) source row = CSR build of a surrogate edge list
+        fake = torch.stack([meta_recv[:, 1].long(), meta_recv[:, 0].long() - self.rank * P]).contiguous()
+        fg = build_csr(fake, self.n_pos, add_self_loops=False, build_csc=False)
+        rg = GraphCSR(self.n_pos, P, M, fg.rowptr, fg.col, fg.perm, fg.rowptr[:P + 1].contiguous(), fg.col, fg.perm)
+        rg.c.edge_grads_indirect = 1
+        self.n_recv = M
+        return rg
+
+    def layer_fwd_bwd(self, x_full, W, a_s, a_d, bias, d_out, H, C, xw_dtype, algo, marks=None, graph=None, rgraph=None):
+        """``x_full`` is the replicated input in padded position space ``[world*rows_padded, K]``."""
+        from . import functional as Fn
+        g, rg = graph or self.graph, rgraph or self.rgraph
+        P, D, dev, n = self.rows_padded, H * C, self.device, self.n_local
+        lo = self.rank * P
+        if marks: marks[0].record()
+        xw_full, asrc_full, adst_full = Fn.project_fwd(x_full, W, a_s, a_d, H, C, xw_dtype, algo)
+        a_dst = adst_full[lo:lo + P]
+        if marks: marks[1].record()
+        out, rowmax, rowsum = Fn.gat_fwd(g, xw_full, asrc_full, a_dst, bias, H, C, 0.2, False)
+        if marks: marks[2].record()
+        # backward
+        if self.world > 1:
+            dO_pad = torch.zeros(P, d_out.size(1), dtype=torch.float32, device=dev)
+            dO_pad[:n] = d_out
+            dO_full = torch.empty(self.n_pos, d_out.size(1), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(dO_full, dO_pad)
+        else:
+            dO_full = torch.zeros(self.n_pos, d_out.size(1), dtype=torch.float32, device=dev)
+            dO_full[lo:lo + n] = d_out
+        alpha_used, dz, da_dst = Fn.gat_bwd_dst(g, xw_full, asrc_full, a_dst, rowmax, rowsum, d_out, H, C, 0.2, False)
+        if self.world > 1:
+            r_alpha = torch.empty(self.n_recv, H, dtype=torch.float32, device=dev)
+            r_dz = torch.empty(self.n_recv, H, dtype=torch.float32, device=dev)
+            dist.all_to_all_single(r_alpha, alpha_used, self.recv_splits, self.send_splits)
+            dist.all_to_all_single(r_dz, dz, self.recv_splits, self.send_splits)
+        else:
+            r_alpha, r_dz = alpha_used, dz
+        da_dst_pad = torch.zeros(P, H, dtype=torch.float32, device=dev)
+        da_dst_pad[:n] = da_dst
+        dxw, da_src = Fn.gat_bwd_src(rg, r_alpha, r_dz, dO_full, a_s, a_d, da_dst_pad, H, C, False)
+        if marks: marks[3].record()
+        grads = Fn.project_bwd(x_full[lo:lo + n], W, dxw[:n], xw_full[lo:lo + n], da_src[:n], da_dst, d_out, H, C, C, False,
+                               algo)
+        dW, datt_s, datt_d, dbias, _ = grads
+        if self.world > 1:
+            flat = torch.cat([dW.reshape(-1), datt_s, datt_d, dbias])
+            dist.all_reduce(flat)
+            k = dW.numel()
+            dW, datt_s, datt_d, dbias = flat[:k].view_as(dW), flat[k:k + D], flat[k + D:k + 2 * D], flat[k + 2 * D:]
+        if marks: marks[4].record()
+        return out, (dW, datt_s, datt_d, dbias)
+
+    def e2e(self, args, conv, x_full, N, E_total, K, dev):
+        """End-to-end with HOST buffers: per step every rank copies the (replicated) input features and its own
+        destination-range edge list host->device, rebuilds CSR/CSC and the receive-side index, runs forward +
+        backward with the collectives, and reads the all-reduced weight gradients back."""
+        H, C = conv.heads, conv.out_channels
+        x_host = torch.empty(x_full.shape, dtype=x_full.dtype, pin_memory=True).copy_(x_full)
+        ei_host = torch.empty(self.local_ei.shape, dtype=self.local_ei.dtype, pin_memory=True).copy_(self.local_ei)
+        W = conv.lin_src.weight.detach()
+        a_s, a_d = conv.att_src.detach().view(-1).contiguous(), conv.att_dst.detach().view(-1).contiguous()
+        bias = conv.bias.detach()
+        d_out = torch.full((self.n_local, C), 1.0 / N, device=dev)
+        steps = max(1, min(args.steps, args.e2e_steps))
+        self.graph = self.rgraph = None
+        torch.cuda.empty_cache()
+
+        def one():
+            xd = x_host.to(dev, non_blocking=True)
+            ed = ei_host.to(dev, non_blocking=True)
+            g = self.build_graph(ed)
+            rg = self.build_exchange(g)
+            out, grads = self.layer_fwd_bwd(xd, W, a_s, a_d, bias, d_out, H, C, conv.feature_dtype, args.algo, graph=g,
+                                            rgraph=rg)
+            return [t.cpu() for t in grads] + [out[:1].cpu()]
+
+        one()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = one()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        h2d = x_host.numel() * x_host.element_size() + ei_host.numel() * ei_host.element_size()
+        d2h = sum(t.numel() * t.element_size() for t in res)
+        return {"value": E_total / dt, "unit": "edges/s", "h2d_bytes_per_step": h2d * self.world,
+                "d2h_bytes_per_step": d2h * self.world, "steps": steps, "ms_per_step": dt * 1e3,
+                "includes": "per rank: H2D of x + own edge list, CSR/CSC + exchange-index rebuild, fwd+bwd with "
+                            "all-to-all/all-gather/all-reduce, D2H of grads"}

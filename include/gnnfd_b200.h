@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 3
+#define GNNFD_ABI_VERSION 4
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -97,6 +97,10 @@ typedef struct gnnfd_graph {
     gnnfd_hub_plan_t hub_src;      /* plan over colptr */
     gnnfd_item_plan_t items_dst;   /* work items over rowptr (required by gat_fwd / gat_bwd_dst) */
     gnnfd_item_plan_t items_src;   /* work items over colptr (required by gat_bwd_src) */
+    /* gat_bwd_src only: 0 = alpha_used/dz rows are already in source-major order (what gat_bwd_dst writes);
+     * 1 = the row of src-sorted entry p is csc_eid[p] (edge gradients received from other GPUs, in arrival order) */
+    int32_t edge_grads_indirect;
+    int32_t reserved_;
 } gnnfd_graph_t;
 
 /* ---- introspection ------------------------------------------------------------------------- */

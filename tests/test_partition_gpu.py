@@ -17,7 +17,7 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from gnn_fraud_detection_b200 import _abi, build_csr, functional as Fn, synth
-        from gnn_fraud_detection_b200.partition import DstRangePartition, snapshot_batches
+        from gnn_fraud_detection_b200.partition import DstRangePartition, ReplicatedInputPartition, snapshot_batches
         from gnn_fraud_detection_b200 import GATConv
         H, C, K, N, E = 8, 64, 166, 200_000, 2_000_000
         ei = synth.powerlaw_graph(N, E, seed=5, device=dev)
@@ -43,6 +43,15 @@ def _worker(rank, world, port, ret):
         errs = [float((o2 - out[lo:hi]).abs().max()), float((dW2 - dW).abs().max()), float((ds2 - datt_s).abs().max()),
                 float((dd2 - datt_d).abs().max()), float((db2 - dbias).abs().max())]
         rel_dw = float((dW2 - dW).norm() / dW.norm())
+        # variant (c): replicated input, per-edge gradient exchange
+        part2 = ReplicatedInputPartition.build(ei, N, rank, world, dev)
+        x_pos = torch.zeros(part2.n_pos, K, device=dev)
+        x_pos[part2.plan.to_pos(torch.arange(N, device=dev))] = x
+        o3, (dW3, ds3, dd3, db3) = part2.layer_fwd_bwd(x_pos, W, a_s, a_d, bias, d_out[lo:hi].contiguous(), H, C,
+                                                      torch.float32, _abi.GEMM_AUTO)
+        errs += [float((o3 - out[lo:hi]).abs().max()), float((dW3 - dW).abs().max()), float((ds3 - datt_s).abs().max()),
+                 float((dd3 - datt_d).abs().max()), float((db3 - dbias).abs().max())]
+        rel_dw = max(rel_dw, float((dW3 - dW).norm() / dW.norm()))
         # time-step sharding: a rank's block-diagonal batch reproduces the full-graph rows it owns
         xs, es, ts = synth.elliptic_synth(num_nodes=40_000, num_edges=46_000, num_feats=K, seed=0, device=dev)
         full = conv.eval()(xs, es)
