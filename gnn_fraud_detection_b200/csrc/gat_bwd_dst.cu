@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 gat_bwd_dst_hub2(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                  const int32_t* __restrict__ csr2csc, const float* __restrict__ a_src,
                  const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
-                 gnnfd_hub_plan_t plan, float slope, const float* __restrict__ part_t, float* __restrict__ dz,
+                 gnnfd_hub_plan_t plan, float slope, const float* __restrict__ t_total, float* __restrict__ dz,
                  float* __restrict__ part_dad)
 {
     constexpr int H = GE::H;
@@ -343,29 +343,37 @@ gat_bwd_dst_hub2(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     RowStat<H> r;
     load_row_stat<H>(r, i, a_dst, rowmax, rowsum);
     float t[H], dad[H];
+    load_vecH<H>(t_total + int64_t(slot) * H, t);      // the same total in every chunk of the row
 #pragma unroll
-    for (int h = 0; h < H; ++h) { t[h] = 0.f; dad[h] = 0.f; }
-    for (int cc = c0; cc < c1; ++cc) {   // same order in every chunk of the row => identical t
-        float pt[H];
-        load_vecH<H>(part_t + int64_t(cc) * H, pt);
-#pragma unroll
-        for (int h = 0; h < H; ++h) t[h] += pt[h];
-    }
+    for (int h = 0; h < H; ++h) dad[h] = 0.f;
+    (void)c1;
     dst_sweep2<GE>(r, beg, end, col, csr2csc, a_src, slope, t, lane, dz, dad);
 #pragma unroll
     for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
     if (lane == 0) store_vecH<H>(part_dad + int64_t(c) * H, dad);
 }
-// hub rows, step 3: da_dst[i] = sum of the chunk partials in chunk order
-template <int H>
-__global__ void gat_bwd_dst_hub3(gnnfd_hub_plan_t plan, const float* __restrict__ part_dad, float* __restrict__ da_dst)
+// per hub row: out[dst_index] = sum over its chunks of part[c][0..H) -- one warp per hub, lanes stride over the
+// chunks, fixed-shape warp reduction => deterministic.  dst_index = hub slot (BY_ROW = false) or row id.
+template <int H, bool BY_ROW>
+__global__ void __launch_bounds__(ROW_THREADS)
+gat_hub_chunk_sum(gnnfd_hub_plan_t plan, const float* __restrict__ part, float* __restrict__ out)
 {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= plan.n_hub * H) return;
-    const int slot = idx / H, h = idx % H;
-    float s = 0.f;
-    for (int c = plan.hub_chunk_ptr[slot]; c < plan.hub_chunk_ptr[slot + 1]; ++c) s += part_dad[int64_t(c) * H + h];
-    da_dst[int64_t(plan.hub_row[slot]) * H + h] = s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slot = blockIdx.x * ROW_WARPS + warp;
+    if (slot >= plan.n_hub) return;
+    float s[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) s[h] = 0.f;
+    for (int c = plan.hub_chunk_ptr[slot] + lane; c < plan.hub_chunk_ptr[slot + 1]; c += 32) {
+        float p[H];
+        load_vecH<H>(part + int64_t(c) * H, p);
+#pragma unroll
+        for (int h = 0; h < H; ++h) s[h] += p[h];
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) s[h] = warp_sum(s[h]);
+    const int64_t o = BY_ROW ? int64_t(plan.hub_row[slot]) : int64_t(slot);
+    if (lane == 0) store_vecH<H>(out + o * H, s);
 }
 
 template <class K>
@@ -405,11 +413,13 @@ static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* 
     g_launches += 1;
     if (g->hub_dst.n_hub > 0) {
         const gnnfd_hub_plan_t& pl = g->hub_dst;
-        const size_t need = 2 * carve_bytes(size_t(pl.n_chunk) * GE::H, 4);
+        const size_t need = 2 * carve_bytes(size_t(pl.n_chunk) * GE::H, 4) + carve_bytes(size_t(pl.n_hub) * GE::H, 4);
         GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "gat_bwd_dst: workspace %zu < %zu", ws_bytes, need);
         char* p = reinterpret_cast<char*>(ws);
         float* part_t = carve<float>(p, size_t(pl.n_chunk) * GE::H);
         float* part_dad = carve<float>(p, size_t(pl.n_chunk) * GE::H);
+        float* t_total = carve<float>(p, size_t(pl.n_hub) * GE::H);
+        const unsigned gh = (unsigned)((pl.n_hub + ROW_WARPS - 1) / ROW_WARPS);
         const unsigned gc = (unsigned)((pl.n_chunk + ST_WARPS - 1) / ST_WARPS);
         const unsigned gc2 = (unsigned)((pl.n_chunk + ROW_WARPS - 1) / ROW_WARPS);
 #define GNNFD_BWD_HUB1(CC, DD)                                                                                         \
@@ -420,10 +430,11 @@ static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* 
         if (concat) { if (drop) { GNNFD_BWD_HUB1(true, true); } else { GNNFD_BWD_HUB1(true, false); } }
         else        { if (drop) { GNNFD_BWD_HUB1(false, true); } else { GNNFD_BWD_HUB1(false, false); } }
 #undef GNNFD_BWD_HUB1
+        gat_hub_chunk_sum<GE::H, false><<<gh, ROW_THREADS, 0, st>>>(pl, part_t, t_total);
         gat_bwd_dst_hub2<GE><<<gc2, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->csr2csc, a_src, a_dst, rowmax, rowsum, pl, slope,
-                                                          part_t, dz, part_dad);
-        gat_bwd_dst_hub3<GE::H><<<(unsigned)((pl.n_hub * GE::H + 255) / 256), 256, 0, st>>>(pl, part_dad, da_dst);
-        g_launches += 3;
+                                                          t_total, dz, part_dad);
+        gat_hub_chunk_sum<GE::H, true><<<gh, ROW_THREADS, 0, st>>>(pl, part_dad, da_dst);
+        g_launches += 4;
     }
     GNNFD_LAUNCH_CHECK();
     return GNNFD_OK;

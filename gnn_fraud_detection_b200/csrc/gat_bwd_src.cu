@@ -109,28 +109,32 @@ __global__ void __launch_bounds__(ROW_THREADS)
 gat_bwd_src_rows(const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_row,
                  const int32_t* __restrict__ csc_eid, const float* __restrict__ alpha_used,
                  const float* __restrict__ dz, const float* __restrict__ d_out, const float* __restrict__ att_src,
-                 const float* __restrict__ att_dst, const float* __restrict__ da_dst_full, int64_t n_src,
+                 const float* __restrict__ att_dst, const float* __restrict__ da_dst_full, gnnfd_item_plan_t items,
                  int hub_threshold, float* __restrict__ dxw, float* __restrict__ da_src)
 {
     constexpr int H = GE::H, NS = GE::NS;
     __shared__ __align__(16) float p_sh[ROW_WARPS][32 * H];
     __shared__ int i_sh[ROW_WARPS][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t j = int64_t(blockIdx.x) * ROW_WARPS + warp;
-    if (j >= n_src) return;
-    const int beg = colptr[j], end = colptr[j + 1];
-    if (end - beg > hub_threshold) return;
-    float acc[NS][4], das[H];
+    // one warp per edge-balanced work item (a run of whole source rows, ~target out-edges in total)
+    const int item = blockIdx.x * ROW_WARPS + warp;
+    if (item >= items.n_items) return;
+    const int j_end = items.item_start[item + 1];
+    for (int64_t j = items.item_start[item]; j < j_end; ++j) {
+        const int beg = colptr[j], end = colptr[j + 1];
+        if (end - beg > hub_threshold) continue;        // split rows are produced by the hub kernels
+        float acc[NS][4], das[H];
 #pragma unroll
-    for (int q = 0; q < NS; ++q)
+        for (int q = 0; q < NS; ++q)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[q][k] = 0.f;
+            for (int k = 0; k < 4; ++k) acc[q][k] = 0.f;
 #pragma unroll
-    for (int h = 0; h < H; ++h) das[h] = 0.f;
-    src_range<GE, CONCAT>(beg, end, csc_row, csc_eid, alpha_used, dz, d_out, acc, das, p_sh[warp], i_sh[warp], lane);
+        for (int h = 0; h < H; ++h) das[h] = 0.f;
+        src_range<GE, CONCAT>(beg, end, csc_row, csc_eid, alpha_used, dz, d_out, acc, das, p_sh[warp], i_sh[warp], lane);
 #pragma unroll
-    for (int h = 0; h < H; ++h) das[h] = warp_sum(das[h]);
-    src_epilogue<GE, CONCAT>(j, acc, das, att_src, att_dst, da_dst_full, dxw, da_src, lane);
+        for (int h = 0; h < H; ++h) das[h] = warp_sum(das[h]);
+        src_epilogue<GE, CONCAT>(j, acc, das, att_src, att_dst, da_dst_full, dxw, da_src, lane);
+    }
 }
 
 template <class GE, bool CONCAT>
@@ -208,13 +212,15 @@ static int launch_bwd_src(const gnnfd_graph_t* g, const float* alpha_used, const
     if (n == 0) return GNNFD_OK;
     const int32_t* eid_ptr = g->edge_grads_indirect ? g->csc_eid : nullptr;
     const int thr = g->hub_src.n_hub > 0 ? g->hub_src.threshold : INT_MAX;
-    const unsigned grid = (unsigned)((n + ROW_WARPS - 1) / ROW_WARPS);
+    GNNFD_REQUIRE(g->items_src.n_items > 0 && g->items_src.item_start, GNNFD_ERR_ARG,
+                  "gat_bwd_src: the graph has no work-item plan over colptr (gnnfd_item_plan)");
+    const unsigned grid = (unsigned)((g->items_src.n_items + ROW_WARPS - 1) / ROW_WARPS);
     if (concat)
         gat_bwd_src_rows<GE, true><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, d_out,
-                                                                 att_src, att_dst, da_dst_full, n, thr, dxw, da_src);
+                                                                 att_src, att_dst, da_dst_full, g->items_src, thr, dxw, da_src);
     else
         gat_bwd_src_rows<GE, false><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, d_out,
-                                                                  att_src, att_dst, da_dst_full, n, thr, dxw, da_src);
+                                                                  att_src, att_dst, da_dst_full, g->items_src, thr, dxw, da_src);
     g_launches += 1;
     if (g->hub_src.n_hub > 0) {
         const gnnfd_hub_plan_t& pl = g->hub_src;
@@ -252,7 +258,7 @@ int gnnfd_gat_bwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* 
 {
     GNNFD_REQUIRE(g && bytes, GNNFD_ERR_ARG, "gat_bwd_workspace_bytes: NULL argument");
     const size_t nd = (size_t)g->hub_dst.n_chunk, ns = (size_t)g->hub_src.n_chunk;
-    const size_t a = 2 * carve_bytes(nd * H, 4);
+    const size_t a = 2 * carve_bytes(nd * H, 4) + carve_bytes(size_t(g->hub_dst.n_hub) * H, 4);
     const size_t b = carve_bytes(ns * size_t(H) * C, 4) + carve_bytes(ns * H, 4);
     *bytes = (a > b ? a : b) + 256;
     return GNNFD_OK;

@@ -307,7 +307,8 @@ gat_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict
     fwd_stream<GE, DROPOUT>(cur, ring, sink, rowptr, col, perm, xw, a_src, a_dst, slope, keep, keep_scale, lane);
 }
 
-// one warp per hub row: merge the chunk partials in chunk order
+// one CTA per hub row: warp w folds chunks w, w+8, ... with the online-softmax combine rule, then the eight
+// warp states are folded in warp order -- a fixed order, so the result is deterministic
 template <class GE, bool CONCAT>
 __global__ void __launch_bounds__(ROW_THREADS)
 gat_fwd_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_ms, const float* __restrict__ part_acc,
@@ -315,46 +316,66 @@ gat_fwd_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_ms, cons
                   float* __restrict__ rowsum)
 {
     constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP, D = GE::D;
+    __shared__ __align__(16) float st_ms[ROW_WARPS][2 * H];
+    __shared__ __align__(16) float st_acc[ROW_WARPS][D];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int slot = blockIdx.x * ROW_WARPS + warp;
-    if (slot >= plan.n_hub) return;
+    const int slot = blockIdx.x;
     const int sub = lane / GE::G;
     const int64_t i = plan.hub_row[slot];
     const int c0 = plan.hub_chunk_ptr[slot], c1 = plan.hub_chunk_ptr[slot + 1];
     float M[H], s[H], acc[NS][VW];
 #pragma unroll
     for (int h = 0; h < H; ++h) { M[h] = -INFINITY; s[h] = 0.f; }
-    for (int c = c0; c < c1; ++c) {
-        float mc[H];
-        load_vecH<H>(part_ms + int64_t(c) * 2 * H, mc);
-#pragma unroll
-        for (int h = 0; h < H; ++h) M[h] = fmaxf(M[h], mc[h]);
-    }
 #pragma unroll
     for (int q = 0; q < NS; ++q)
 #pragma unroll
         for (int k = 0; k < VW; ++k) acc[q][k] = 0.f;
-    for (int c = c0; c < c1; ++c) {
-        float mc[H], sc[H], f[H];
-        load_vecH<H>(part_ms + int64_t(c) * 2 * H, mc);
-        load_vecH<H>(part_ms + int64_t(c) * 2 * H + H, sc);
+    auto fold = [&](const float (&mc)[H], const float (&sc)[H], const float* __restrict__ pacc) {
+        float fo[H], fn[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-            f[h] = expf(mc[h] - M[h]);
-            s[h] = fmaf(sc[h], f[h], s[h]);
+            const float mn = fmaxf(M[h], mc[h]);
+            fo[h] = (M[h] == -INFINITY) ? 0.f : expf(M[h] - mn);
+            fn[h] = (mc[h] == -INFINITY) ? 0.f : expf(mc[h] - mn);
+            s[h] = s[h] * fo[h] + sc[h] * fn[h];
+            M[h] = mn;
         }
 #pragma unroll
         for (int q = 0; q < NS; ++q) {
-            const float fq = pick<HP>(f, q, sub);
+            const float a = pick<HP>(fo, q, sub), bq = pick<HP>(fn, q, sub);
 #pragma unroll
             for (int k = 0; k < VW; k += 4) {
-                const float4 v = *reinterpret_cast<const float4*>(part_acc + int64_t(c) * D + VW * (lane + 32 * q) + k);
-                acc[q][k] = fmaf(v.x, fq, acc[q][k]);
-                acc[q][k + 1] = fmaf(v.y, fq, acc[q][k + 1]);
-                acc[q][k + 2] = fmaf(v.z, fq, acc[q][k + 2]);
-                acc[q][k + 3] = fmaf(v.w, fq, acc[q][k + 3]);
+                const float4 v = *reinterpret_cast<const float4*>(pacc + VW * (lane + 32 * q) + k);
+                acc[q][k] = fmaf(v.x, bq, acc[q][k] * a);
+                acc[q][k + 1] = fmaf(v.y, bq, acc[q][k + 1] * a);
+                acc[q][k + 2] = fmaf(v.z, bq, acc[q][k + 2] * a);
+                acc[q][k + 3] = fmaf(v.w, bq, acc[q][k + 3] * a);
             }
         }
+    };
+    for (int c = c0 + warp; c < c1; c += ROW_WARPS) {
+        float mc[H], sc[H];
+        load_vecH<H>(part_ms + int64_t(c) * 2 * H, mc);
+        load_vecH<H>(part_ms + int64_t(c) * 2 * H + H, sc);
+        fold(mc, sc, part_acc + int64_t(c) * D);
+    }
+    if (lane == 0) {
+        store_vecH<H>(&st_ms[warp][0], M);
+        store_vecH<H>(&st_ms[warp][H], s);
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q)
+#pragma unroll
+        for (int k = 0; k < VW; k += 4)
+            *reinterpret_cast<float4*>(&st_acc[warp][VW * (lane + 32 * q) + k]) =
+                make_float4(acc[q][k], acc[q][k + 1], acc[q][k + 2], acc[q][k + 3]);
+    __syncthreads();
+    if (warp != 0) return;
+    for (int w = 1; w < ROW_WARPS; ++w) {
+        float mc[H], sc[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) { mc[h] = st_ms[w][h]; sc[h] = st_ms[w][H + h]; }
+        fold(mc, sc, &st_acc[w][0]);
     }
     fwd_epilogue<GE, CONCAT>(i, M, s, acc, bias, act, out, rowmax, rowsum, lane);
 }
@@ -425,7 +446,7 @@ static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_sr
         float* part_ms = carve<float>(p, size_t(pl.n_chunk) * 2 * GE::H);
         float* part_acc = carve<float>(p, size_t(pl.n_chunk) * GE::D);
         const unsigned gc = (unsigned)((pl.n_chunk + ST_WARPS - 1) / ST_WARPS);
-        const unsigned gh = (unsigned)((pl.n_hub + ROW_WARPS - 1) / ROW_WARPS);
+        const unsigned gh = (unsigned)pl.n_hub;   // one CTA per hub row
         if (drop) {
             rc = set_smem(gat_fwd_hub_chunks<GE, true>, SMEM);
             if (rc) return rc;

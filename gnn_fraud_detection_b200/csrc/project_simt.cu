@@ -246,45 +246,60 @@ __global__ void alpha_dots(const void* __restrict__ xw_, const float* __restrict
 // datt_src[h,c] = sum_n da_src[n,h] * xw[n,h,c] and xw = x W^T, so
 //   datt_src[h,c] = sum_k W[hC+c,k] * G_src[h,k],   G_src = da_src^T x   ([H,K], reduction over nodes)
 // which needs x (K*4 bytes/node) instead of xw (D*s bytes/node).  Pg[s][2H][K] are slab partials.
-template <int H>
+template <int H, int KT>   // KT = ceil(K / 32) feature columns per lane
 __global__ void __launch_bounds__(256)
 dax_partial(const float* __restrict__ x, int64_t ldx, const float* __restrict__ da_src, const float* __restrict__ da_dst,
             int64_t N, int K, int64_t rows_per_slice, float* __restrict__ Pg)
 {
+    // warp w of the CTA takes rows nb+w, nb+w+8, ...; lane l owns features l, l+32, ... (coalesced 128-byte row
+    // segments), so one x row is read once and feeds 2H*KT FMAs per lane; the 8 warps are summed through smem.
+    __shared__ float red[8][2 * H][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t nb = int64_t(blockIdx.x) * rows_per_slice;
     const int64_t ne = (nb + rows_per_slice < N) ? nb + rows_per_slice : N;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
-        float acc[2 * H];
+    float acc[KT][2 * H];
 #pragma unroll
-        for (int h = 0; h < 2 * H; ++h) acc[h] = 0.f;
-        int64_t n = nb;
-        for (; n + 8 <= ne; n += 8) {       // eight independent row loads in flight per thread
-            float xv[8];
+    for (int t = 0; t < KT; ++t)
 #pragma unroll
-            for (int u = 0; u < 8; ++u) xv[u] = __ldg(x + (n + u) * ldx + k);
+        for (int h = 0; h < 2 * H; ++h) acc[t][h] = 0.f;
+    for (int64_t n = nb + warp; n < ne; n += 16) {          // two rows in flight per warp
+        float xv[2][KT], da[2][2 * H];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 2; ++u) {
+            const int64_t r = n + 8 * u;
+            const bool ok = r < ne;
 #pragma unroll
-                for (int q = 0; q < H / 4; ++q) {
-                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(da_src + (n + u) * H) + q);
-                    const float4 d4 = __ldg(reinterpret_cast<const float4*>(da_dst + (n + u) * H) + q);
-                    acc[4 * q + 0] = fmaf(s4.x, xv[u], acc[4 * q + 0]); acc[4 * q + 1] = fmaf(s4.y, xv[u], acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(s4.z, xv[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(s4.w, xv[u], acc[4 * q + 3]);
-                    acc[H + 4 * q + 0] = fmaf(d4.x, xv[u], acc[H + 4 * q + 0]); acc[H + 4 * q + 1] = fmaf(d4.y, xv[u], acc[H + 4 * q + 1]);
-                    acc[H + 4 * q + 2] = fmaf(d4.z, xv[u], acc[H + 4 * q + 2]); acc[H + 4 * q + 3] = fmaf(d4.w, xv[u], acc[H + 4 * q + 3]);
-                }
+            for (int t = 0; t < KT; ++t) {
+                const int k = lane + 32 * t;
+                xv[u][t] = (ok && k < K) ? __ldg(x + r * ldx + k) : 0.f;
             }
-        }
-        for (; n < ne; ++n) {
-            const float xv = __ldg(x + n * ldx + k);
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                acc[h] = fmaf(da_src[n * H + h], xv, acc[h]);
-                acc[H + h] = fmaf(da_dst[n * H + h], xv, acc[H + h]);
+            for (int q = 0; q < H / 4; ++q) {
+                const float4 s4 = ok ? __ldg(reinterpret_cast<const float4*>(da_src + r * H) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 d4 = ok ? __ldg(reinterpret_cast<const float4*>(da_dst + r * H) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                da[u][4 * q] = s4.x; da[u][4 * q + 1] = s4.y; da[u][4 * q + 2] = s4.z; da[u][4 * q + 3] = s4.w;
+                da[u][H + 4 * q] = d4.x; da[u][H + 4 * q + 1] = d4.y; da[u][H + 4 * q + 2] = d4.z; da[u][H + 4 * q + 3] = d4.w;
             }
         }
 #pragma unroll
-        for (int h = 0; h < 2 * H; ++h) Pg[(int64_t(blockIdx.x) * 2 * H + h) * K + k] = acc[h];
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int t = 0; t < KT; ++t)
+#pragma unroll
+                for (int h = 0; h < 2 * H; ++h) acc[t][h] = fmaf(da[u][h], xv[u][t], acc[t][h]);
+    }
+    for (int t = 0; t < KT; ++t) {
+#pragma unroll
+        for (int h = 0; h < 2 * H; ++h) red[warp][h][lane] = acc[t][h];
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * H * 32; i += 256) {
+            const int h = i >> 5, l = i & 31, k = l + 32 * t;
+            float sum = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) sum += red[w][h][l];
+            if (k < K) Pg[(int64_t(blockIdx.x) * 2 * H + h) * K + k] = sum;
+        }
+        __syncthreads();
     }
 }
 // datt_src[o] = sum_k W[o,k] * G[h(o),k],  datt_dst[o] = sum_k W[o,k] * G[H + h(o),k];  one warp per o
@@ -386,8 +401,16 @@ int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* d
     if (datt_src && datt_dst) {
         if (H == 8 || H == 4) {
             // G = [da_src | da_dst]^T x over node slabs, then datt = W . G  (xw is not re-read)
-            if (H == 8) dax_partial<8><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);
-            else        dax_partial<4><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);
+            const int kt = int((K + 31) / 32);
+#define GNNFD_DAX(HH)                                                                                              \
+    if (kt <= 2) dax_partial<HH, 2><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);                  \
+    else if (kt <= 6) dax_partial<HH, 6><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);             \
+    else if (kt <= 10) dax_partial<HH, 10><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);           \
+    else dax_fallback = true
+            bool dax_fallback = false;
+            if (H == 8) { GNNFD_DAX(8); } else { GNNFD_DAX(4); }
+#undef GNNFD_DAX
+            GNNFD_REQUIRE(!dax_fallback, GNNFD_ERR_UNSUPPORTED, "project_bwd: in_channels > 320 is not built for datt");
             reduce_slices<<<(unsigned)((2 * H * K + 255) / 256), 256, 0, st>>>(Pg, int64_t(2) * H * K, S, Gm);
             datt_from_g<<<(unsigned)((D * 32 + 255) / 256), 256, 0, st>>>(W, Gm, D, (int)K, H, C, datt_src, datt_dst);
             g_launches += 3;
