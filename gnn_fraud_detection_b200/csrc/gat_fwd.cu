@@ -263,7 +263,7 @@ __device__ __forceinline__ void fwd_stream(ChunkCursor& cur, WarpRing<GE>& ring,
 }
 
 template <class GE, bool CONCAT, bool DROPOUT>
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(ST_THREADS, 4)
 gat_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
               const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
               const float* __restrict__ a_dst, const float* __restrict__ bias, gnnfd_item_plan_t items,
@@ -284,7 +284,7 @@ gat_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
 
 // one warp per (hub row, chunk): partial (m, s, unnormalised acc)
 template <class GE, bool DROPOUT>
-__global__ void __launch_bounds__(ST_THREADS)
+__global__ void __launch_bounds__(ST_THREADS, 4)
 gat_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                    const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                    const float* __restrict__ a_dst, gnnfd_hub_plan_t plan, float slope,

@@ -51,7 +51,7 @@ __device__ __forceinline__ void st_bulk_g2s(void* smem_dst, const void* gsrc, ui
 template <class GE, int EXTRA = 0>
 struct StreamGeo {
     static constexpr int ROW_BYTES = GE::D * int(sizeof(typename GE::XT));
-    static constexpr int R = ROW_BYTES >= 2048 ? 6 : (ROW_BYTES >= 1024 ? 8 : 12);   // ring slots per warp
+    static constexpr int R = ROW_BYTES >= 2048 ? 5 : (ROW_BYTES >= 1024 ? 8 : 12);   // ring slots per warp
     static constexpr int RING_BYTES = R * ROW_BYTES;
     static constexpr int P_BYTES = 2 * 32 * GE::H * 4;        // two staging buffers of per-edge per-head floats
     static constexpr int J_BYTES = 2 * 32 * 4;

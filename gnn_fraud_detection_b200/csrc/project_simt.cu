@@ -202,15 +202,20 @@ datt_partial(const void* __restrict__ xw_, const float* __restrict__ da_src, con
         P[(int64_t(blockIdx.x) * 2 + 1) * D + t] = d;
     }
 }
-// column sums of a [N,Wd] matrix, sliced
-__global__ void __launch_bounds__(512)
-colsum_partial(const float* __restrict__ A, int64_t N, int Wd, int64_t rows_per_slice, float* __restrict__ P)
+// column sums of a [N,Wd] matrix, sliced; thread = column, sixteen independent row loads in flight
+__global__ void colsum_partial(const float* __restrict__ A, int64_t N, int Wd, int64_t rows_per_slice, float* __restrict__ P)
 {
     const int64_t nb = int64_t(blockIdx.x) * rows_per_slice;
     const int64_t ne = (nb + rows_per_slice < N) ? nb + rows_per_slice : N;
     for (int t = threadIdx.x; t < Wd; t += blockDim.x) {
         float s = 0.f;
-        for (int64_t n = nb; n < ne; ++n) s += A[n * Wd + t];
+        for (int64_t n = nb; n < ne; n += 16) {
+            float v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) v[u] = (n + u < ne) ? __ldg(A + (n + u) * Wd + t) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) s += v[u];
+        }
         P[int64_t(blockIdx.x) * Wd + t] = s;
     }
 }
@@ -246,60 +251,40 @@ __global__ void alpha_dots(const void* __restrict__ xw_, const float* __restrict
 // datt_src[h,c] = sum_n da_src[n,h] * xw[n,h,c] and xw = x W^T, so
 //   datt_src[h,c] = sum_k W[hC+c,k] * G_src[h,k],   G_src = da_src^T x   ([H,K], reduction over nodes)
 // which needs x (K*4 bytes/node) instead of xw (D*s bytes/node).  Pg[s][2H][K] are slab partials.
-template <int H, int KT>   // KT = ceil(K / 32) feature columns per lane
+template <int H>
 __global__ void __launch_bounds__(256)
 dax_partial(const float* __restrict__ x, int64_t ldx, const float* __restrict__ da_src, const float* __restrict__ da_dst,
             int64_t N, int K, int64_t rows_per_slice, float* __restrict__ Pg)
 {
-    // warp w of the CTA takes rows nb+w, nb+w+8, ...; lane l owns features l, l+32, ... (coalesced 128-byte row
-    // segments), so one x row is read once and feeds 2H*KT FMAs per lane; the 8 warps are summed through smem.
-    __shared__ float red[8][2 * H][33];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // thread = one feature column k (x rows are read as coalesced segments across the CTA), 2H accumulators,
+    // sixteen independent row loads in flight per thread; the 64-byte da rows are CTA-wide broadcasts (L1).
+    constexpr int U = 16;
     const int64_t nb = int64_t(blockIdx.x) * rows_per_slice;
     const int64_t ne = (nb + rows_per_slice < N) ? nb + rows_per_slice : N;
-    float acc[KT][2 * H];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float acc[2 * H];
 #pragma unroll
-    for (int t = 0; t < KT; ++t)
+        for (int h = 0; h < 2 * H; ++h) acc[h] = 0.f;
+        for (int64_t n = nb; n < ne; n += U) {
+            float xv[U];
 #pragma unroll
-        for (int h = 0; h < 2 * H; ++h) acc[t][h] = 0.f;
-    for (int64_t n = nb + warp; n < ne; n += 16) {          // two rows in flight per warp
-        float xv[2][KT], da[2][2 * H];
+            for (int u = 0; u < U; ++u) xv[u] = (n + u < ne) ? __ldg(x + (n + u) * ldx + k) : 0.f;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int64_t r = n + 8 * u;
-            const bool ok = r < ne;
+            for (int u = 0; u < U; ++u) {
+                const int64_t r = (n + u < ne) ? n + u : nb;     // clamped: xv is 0 there
 #pragma unroll
-            for (int t = 0; t < KT; ++t) {
-                const int k = lane + 32 * t;
-                xv[u][t] = (ok && k < K) ? __ldg(x + r * ldx + k) : 0.f;
-            }
-#pragma unroll
-            for (int q = 0; q < H / 4; ++q) {
-                const float4 s4 = ok ? __ldg(reinterpret_cast<const float4*>(da_src + r * H) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float4 d4 = ok ? __ldg(reinterpret_cast<const float4*>(da_dst + r * H) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                da[u][4 * q] = s4.x; da[u][4 * q + 1] = s4.y; da[u][4 * q + 2] = s4.z; da[u][4 * q + 3] = s4.w;
-                da[u][H + 4 * q] = d4.x; da[u][H + 4 * q + 1] = d4.y; da[u][H + 4 * q + 2] = d4.z; da[u][H + 4 * q + 3] = d4.w;
+                for (int q = 0; q < H / 4; ++q) {
+                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(da_src + r * H) + q);
+                    const float4 d4 = __ldg(reinterpret_cast<const float4*>(da_dst + r * H) + q);
+                    acc[4 * q + 0] = fmaf(s4.x, xv[u], acc[4 * q + 0]); acc[4 * q + 1] = fmaf(s4.y, xv[u], acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(s4.z, xv[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(s4.w, xv[u], acc[4 * q + 3]);
+                    acc[H + 4 * q + 0] = fmaf(d4.x, xv[u], acc[H + 4 * q + 0]); acc[H + 4 * q + 1] = fmaf(d4.y, xv[u], acc[H + 4 * q + 1]);
+                    acc[H + 4 * q + 2] = fmaf(d4.z, xv[u], acc[H + 4 * q + 2]); acc[H + 4 * q + 3] = fmaf(d4.w, xv[u], acc[H + 4 * q + 3]);
+                }
             }
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int t = 0; t < KT; ++t)
-#pragma unroll
-                for (int h = 0; h < 2 * H; ++h) acc[t][h] = fmaf(da[u][h], xv[u][t], acc[t][h]);
-    }
-    for (int t = 0; t < KT; ++t) {
-#pragma unroll
-        for (int h = 0; h < 2 * H; ++h) red[warp][h][lane] = acc[t][h];
-        __syncthreads();
-        for (int i = threadIdx.x; i < 2 * H * 32; i += 256) {
-            const int h = i >> 5, l = i & 31, k = l + 32 * t;
-            float sum = 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) sum += red[w][h][l];
-            if (k < K) Pg[(int64_t(blockIdx.x) * 2 * H + h) * K + k] = sum;
-        }
-        __syncthreads();
+        for (int h = 0; h < 2 * H; ++h) Pg[(int64_t(blockIdx.x) * 2 * H + h) * K + k] = acc[h];
     }
 }
 // datt_src[o] = sum_k W[o,k] * G[h(o),k],  datt_dst[o] = sum_k W[o,k] * G[H + h(o),k];  one warp per o
@@ -322,6 +307,16 @@ __global__ void datt_from_g(const float* __restrict__ W, const float* __restrict
         datt_src[o] = s;
         datt_dst[o] = d;
     }
+}
+
+// finer slabs for the column reductions (one thread per column): up to 16 CTAs per SM
+int col_slices(int64_t N)
+{
+    int64_t s = (N + 255) / 256;
+    const int64_t cap = 16 * int64_t(sm_count());
+    if (s > cap) s = cap;
+    if (s < 1) s = 1;
+    return (int)s;
 }
 
 int slices_for(int64_t N)
@@ -367,7 +362,8 @@ size_t project_bwd_ws_bytes(int64_t N, int64_t K, int H, int C)
     const int S = slices_for(N);
     const size_t D = size_t(H) * C;
     return carve_bytes(size_t(S) * D * K, 4) + carve_bytes(size_t(S) * 2 * D, 4) + carve_bytes(size_t(S) * D, 4) +
-           carve_bytes(size_t(S) * 2 * H * K, 4) + carve_bytes(size_t(2) * H * K, 4);
+           carve_bytes(size_t(col_slices(N)) * 2 * H * K, 4) + carve_bytes(size_t(2) * H * K, 4) +
+           carve_bytes(size_t(col_slices(N)) * D, 4);
 }
 
 int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* dxw, const void* xw, int xw_dtype,
@@ -382,8 +378,11 @@ int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* d
     float* Pw = carve<float>(p, size_t(S) * D * K);
     float* Pa = carve<float>(p, size_t(S) * 2 * D);
     float* Pb = carve<float>(p, size_t(S) * D);
-    float* Pg = carve<float>(p, size_t(S) * 2 * H * K);
+    const int Sg = col_slices(N);
+    const int64_t rpg = (N + Sg - 1) / Sg;
+    float* Pg = carve<float>(p, size_t(Sg) * 2 * H * K);
     float* Gm = carve<float>(p, size_t(2) * H * K);
+    float* Pc = carve<float>(p, size_t(Sg) * D);
     if (N == 0) {
         if (dW) cudaMemsetAsync(dW, 0, sizeof(float) * D * K, st);
         if (datt_src) cudaMemsetAsync(datt_src, 0, sizeof(float) * D, st);
@@ -401,17 +400,10 @@ int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* d
     if (datt_src && datt_dst) {
         if (H == 8 || H == 4) {
             // G = [da_src | da_dst]^T x over node slabs, then datt = W . G  (xw is not re-read)
-            const int kt = int((K + 31) / 32);
-#define GNNFD_DAX(HH)                                                                                              \
-    if (kt <= 2) dax_partial<HH, 2><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);                  \
-    else if (kt <= 6) dax_partial<HH, 6><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);             \
-    else if (kt <= 10) dax_partial<HH, 10><<<S, 256, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rps, Pg);           \
-    else dax_fallback = true
-            bool dax_fallback = false;
-            if (H == 8) { GNNFD_DAX(8); } else { GNNFD_DAX(4); }
-#undef GNNFD_DAX
-            GNNFD_REQUIRE(!dax_fallback, GNNFD_ERR_UNSUPPORTED, "project_bwd: in_channels > 320 is not built for datt");
-            reduce_slices<<<(unsigned)((2 * H * K + 255) / 256), 256, 0, st>>>(Pg, int64_t(2) * H * K, S, Gm);
+            const int bs = int(K >= 256 ? 256 : ((K + 31) / 32) * 32);
+            if (H == 8) dax_partial<8><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
+            else        dax_partial<4><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
+            reduce_slices<<<(unsigned)((2 * H * K + 255) / 256), 256, 0, st>>>(Pg, int64_t(2) * H * K, Sg, Gm);
             datt_from_g<<<(unsigned)((D * 32 + 255) / 256), 256, 0, st>>>(W, Gm, D, (int)K, H, C, datt_src, datt_dst);
             g_launches += 3;
         } else {
@@ -426,8 +418,8 @@ int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* d
         }
     }
     if (dbias) {
-        colsum_partial<<<S, 512, 0, st>>>(d_out, N, Co, rps, Pa);
-        reduce_slices<<<(unsigned)((Co + 255) / 256), 256, 0, st>>>(Pa, Co, S, dbias);
+        colsum_partial<<<Sg, Co >= 256 ? 256 : 64, 0, st>>>(d_out, N, Co, rpg, Pc);
+        reduce_slices<<<(unsigned)((Co + 63) / 64), 64, 0, st>>>(Pc, Co, Sg, dbias);
         g_launches += 2;
     }
     if (dx && !skip_dx) {

@@ -193,8 +193,10 @@ gemm_tc(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const float
     __shared__ float att_s[2][BN];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t m0 = int64_t(blockIdx.x) * BM;
-    const int nt = blockIdx.y;                    // column tile
+    // 1-D grid, column tile fastest: the CTAs sharing an A tile are co-scheduled, so its re-read hits L2
+    const int n_col_tiles = (n_valid + BN - 1) / BN;
+    const int nt = blockIdx.x % n_col_tiles;
+    const int64_t m0 = int64_t(blockIdx.x / n_col_tiles) * BM;
     const float* img = b_img + size_t(nt) * n_kb * 2 * (size_t(BN) * BK);
 
     if (tid == 0) {
@@ -540,7 +542,7 @@ int project_fwd_tc(const float* x, int64_t ldx, const float* W, const float* att
     float* img = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     tc::build_b_images<<<dim3(8, n_kb, n_tiles), 256, 0, st>>>(W, K, 1, D, (int)K, BN, n_kb, img);
     const size_t smem = tc::gemm_smem_bytes<BN>();
-    dim3 grid((unsigned)((N + tc::BM - 1) / tc::BM), n_tiles);
+    dim3 grid((unsigned)(int64_t(n_tiles) * ((N + tc::BM - 1) / tc::BM)));
     if (xw_dtype == GNNFD_BF16) {
         GNNFD_CUDA(cudaFuncSetAttribute(tc::gemm_tc<BN, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc::gemm_tc<BN, 1, true><<<grid, tc::THREADS, smem, st>>>(x, ldx, N, (int)K, img, n_kb, nullptr, (__nv_bfloat16*)xw, D,
@@ -569,7 +571,7 @@ int project_bwd_dx_tc(const float* dxw, const float* W, int64_t N, int64_t K, in
     tc::build_b_images<<<dim3(8, n_kb, n_tiles), 256, 0, st>>>(W, 1, K, (int)K, D, BN, n_kb, img);
     const size_t smem = tc::gemm_smem_bytes<BN>();
     GNNFD_CUDA(cudaFuncSetAttribute(tc::gemm_tc<BN, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((N + tc::BM - 1) / tc::BM), n_tiles);
+    dim3 grid((unsigned)(int64_t(n_tiles) * ((N + tc::BM - 1) / tc::BM)));
     tc::gemm_tc<BN, 0, false><<<grid, tc::THREADS, smem, st>>>(dxw, D, N, D, img, n_kb, dx, nullptr, lddx, (int)K, nullptr,
                                                               nullptr, nullptr, nullptr, 0);
     g_launches += 2;
