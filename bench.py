@@ -293,6 +293,9 @@ def run_gpu_arm(args):
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     stage_ms = {s: statistics.mean(m[i].elapsed_time(m[i + 1]) for m in all_marks) for i, s in enumerate(stages)}
+    if os.environ.get("GNNFD_BENCH_DEBUG"):
+        print(f"[rank {rank}] n_local={n_local} Ep={Ep} stages_ms={ {k: round(v, 2) for k, v in stage_ms.items()} }",
+              file=sys.stderr, flush=True)
 
     # ---- roofline ------------------------------------------------------------------------------------
     peak, peak_src = load_peaks()

@@ -399,13 +399,14 @@ struct HubEmit {
 };
 
 // ---- work-item plan ---------------------------------------------------------------------------------------
-// item_start[t] = first row i with ptr[i] >= t*target  (t = 0..n_items-1), item_start[n_items] = n_rows
-__global__ void item_plan_kernel(const int32_t* __restrict__ ptr, int64_t n_rows, int32_t target, int32_t n_items,
-                                 int32_t* __restrict__ item_start)
+// cost(i) = ptr[i] + i*w;  item_start[t] = first row i with cost(i) >= t*target  (t = 0..n_items-1),
+// item_start[n_items] = n_rows
+__global__ void item_plan_kernel(const int32_t* __restrict__ ptr, int64_t n_rows, int32_t target, int32_t w,
+                                 int32_t n_items, int32_t* __restrict__ item_start)
 {
     for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i <= n_rows; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t cur = ptr[i];
-        const int64_t t0 = (i == 0) ? 0 : int64_t(ptr[i - 1]) / target + 1;
+        const int64_t cur = int64_t(ptr[i]) + i * w;
+        const int64_t t0 = (i == 0) ? 0 : (int64_t(ptr[i - 1]) + (i - 1) * w) / target + 1;
         const int64_t t1 = cur / target;
         for (int64_t t = t0; t <= t1 && t < n_items; ++t) item_start[t] = (int32_t)i;
         if (i == n_rows) item_start[n_items] = (int32_t)n_rows;
@@ -440,13 +441,14 @@ int gnnfd_invert_perm(const int32_t* perm, int64_t n, int32_t* inv, gnnfd_stream
     return GNNFD_OK;
 }
 
-int gnnfd_item_plan(const int32_t* ptr, int64_t n_rows, int64_t n_edges, int32_t target, int32_t* item_start,
-                    gnnfd_stream_t stream)
+int gnnfd_item_plan(const int32_t* ptr, int64_t n_rows, int64_t n_edges, int32_t target, int32_t row_weight,
+                    int32_t* item_start, gnnfd_stream_t stream)
 {
     GNNFD_REQUIRE(ptr && item_start, GNNFD_ERR_ARG, "item_plan: NULL array");
-    GNNFD_REQUIRE(n_rows >= 0 && n_edges >= 0 && target >= 1, GNNFD_ERR_ARG, "item_plan: bad sizes");
-    const int32_t n_items = (int32_t)(n_edges / target + 1);
-    item_plan_kernel<<<grid_for(n_rows + 1, 256), 256, 0, (cudaStream_t)stream>>>(ptr, n_rows, target, n_items, item_start);
+    GNNFD_REQUIRE(n_rows >= 0 && n_edges >= 0 && target >= 1 && row_weight >= 0, GNNFD_ERR_ARG, "item_plan: bad sizes");
+    const int32_t n_items = (int32_t)((n_edges + n_rows * row_weight) / target + 1);
+    item_plan_kernel<<<grid_for(n_rows + 1, 256), 256, 0, (cudaStream_t)stream>>>(ptr, n_rows, target, row_weight, n_items,
+                                                                                  item_start);
     g_launches += 1;
     GNNFD_LAUNCH_CHECK();
     return GNNFD_OK;

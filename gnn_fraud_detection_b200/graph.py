@@ -44,26 +44,28 @@ class GraphCSR:
             self.c.hub_dst = self._plan(rowptr, self.n_dst, hub_threshold, hub_chunk)
             if colptr is not None:
                 self.c.hub_src = self._plan(colptr, self.n_src, hub_threshold, hub_chunk)
-        self.c.items_dst = self._items(rowptr, self.n_dst)
+        # per-row charge in edge units: a dst row costs ~one 256 B epilogue, a src row writes a 2 KB dxw row
+        self.c.items_dst = self._items(rowptr, self.n_dst, row_weight=1)
         if colptr is not None:
-            self.c.items_src = self._items(colptr, self.n_src)
+            self.c.items_src = self._items(colptr, self.n_src, row_weight=8)
 
     @property
     def has_csc(self) -> bool:
         return self.colptr is not None
 
-    def _items(self, ptr_t, n_rows) -> _abi.ItemPlan:
-        """Edge-balanced work items: ~target edges per warp, sized so that even a small graph yields several
-        items per resident warp (148 SMs x 32 warps)."""
+    def _items(self, ptr_t, n_rows, row_weight=1) -> _abi.ItemPlan:
+        """Cost-balanced work items: ~target (edges + rows*row_weight) per warp, sized so that even a small graph
+        yields several items per resident warp (148 SMs x 32 warps)."""
         plan = _abi.ItemPlan()
-        target = int(min(256, max(32, (self.n_edges // (148 * 32 * 4)) // 32 * 32)))
+        cost = self.n_edges + n_rows * row_weight
+        target = int(min(256, max(32, (cost // (148 * 32 * 4)) // 32 * 32)))
         plan.target = target
         if n_rows == 0:
             return plan
-        n_items = self.n_edges // target + 1
+        n_items = cost // target + 1
         item_start = torch.empty(n_items + 1, dtype=torch.int32, device=self.device)
-        _abi.check(_abi.lib().gnnfd_item_plan(ptr_t.data_ptr(), n_rows, self.n_edges, target, item_start.data_ptr(),
-                                              _stream()))
+        _abi.check(_abi.lib().gnnfd_item_plan(ptr_t.data_ptr(), n_rows, self.n_edges, target, row_weight,
+                                              item_start.data_ptr(), _stream()))
         self._hub_tensors.append(item_start)
         plan.n_items, plan.item_start = n_items, item_start.data_ptr()
         return plan

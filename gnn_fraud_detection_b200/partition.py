@@ -311,7 +311,8 @@ class ReplicatedInputPartition(DstRangePartition):
             dO_pad = torch.zeros(P, d_out.size(1), dtype=torch.float32, device=dev)
             dO_pad[:n] = d_out
             dO_full = torch.empty(self.n_pos, d_out.size(1), dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(dO_full, dO_pad)
+            # asynchronous: the gather of dOut rides NVLink while the dst-major pass runs
+            ag_work = dist.all_gather_into_tensor(dO_full, dO_pad, async_op=True)
         else:
             dO_full = torch.zeros(self.n_pos, d_out.size(1), dtype=torch.float32, device=dev)
             dO_full[lo:lo + n] = d_out
@@ -321,6 +322,7 @@ class ReplicatedInputPartition(DstRangePartition):
             r_dz = torch.empty(self.n_recv, H, dtype=torch.float32, device=dev)
             dist.all_to_all_single(r_alpha, alpha_used, self.recv_splits, self.send_splits)
             dist.all_to_all_single(r_dz, dz, self.recv_splits, self.send_splits)
+            ag_work.wait()
         else:
             r_alpha, r_dz = alpha_used, dz
         da_dst_pad = torch.zeros(P, H, dtype=torch.float32, device=dev)

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 4
+#define GNNFD_ABI_VERSION 5
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -71,12 +71,14 @@ typedef struct gnnfd_hub_plan {
     const int32_t* chunk_hub;      /* [n_chunk] hub slot of each chunk */
 } gnnfd_hub_plan_t;
 
-/* Edge-balanced work items over a row-pointer array: item t owns the rows whose first edge lies in
- * [t*target, (t+1)*target), i.e. rows [item_start[t], item_start[t+1]).  One warp streams one item, so
- * every warp moves about the same number of bytes whatever the degree distribution. */
+/* Cost-balanced work items over a row-pointer array.  The cost of the rows before row i is
+ * ptr[i] + i*row_weight (edges plus a per-row charge for the row epilogue, so that long runs of empty or
+ * tiny rows are bounded too); item t owns the rows whose cost offset lies in [t*target, (t+1)*target), i.e.
+ * rows [item_start[t], item_start[t+1]).  One warp streams one item, so every warp moves about the same
+ * number of bytes whatever the degree distribution. */
 typedef struct gnnfd_item_plan {
     int32_t n_items;
-    int32_t target;                /* edges per item */
+    int32_t target;                /* cost units (edges + rows*row_weight) per item */
     const int32_t* item_start;     /* [n_items+1] */
 } gnnfd_item_plan_t;
 
@@ -135,10 +137,10 @@ int gnnfd_hub_plan(const int32_t* ptr, int64_t n_rows, int32_t threshold, int32_
 /* inv[perm[i]] = i for a permutation of [0,n) (used for csr2csc = inverse of csc_eid). */
 int gnnfd_invert_perm(const int32_t* perm, int64_t n, int32_t* inv, gnnfd_stream_t stream);
 
-/* Work-item plan over a row-pointer array.  item_start needs n_edges/target + 2 entries;
- * n_items = n_edges/target + 1.  Fully asynchronous on `stream`. */
-int gnnfd_item_plan(const int32_t* ptr, int64_t n_rows, int64_t n_edges, int32_t target, int32_t* item_start,
-                    gnnfd_stream_t stream);
+/* Work-item plan over a row-pointer array.  n_items = (n_edges + n_rows*row_weight)/target + 1 and
+ * item_start needs n_items + 1 entries.  Fully asynchronous on `stream`. */
+int gnnfd_item_plan(const int32_t* ptr, int64_t n_rows, int64_t n_edges, int32_t target, int32_t row_weight,
+                    int32_t* item_start, gnnfd_stream_t stream);
 
 /* ---- (2) projection  xw = x @ W^T, a_src/a_dst in the epilogue --------------------------------
  * Replaces: lin_src(x).view(-1,H,C); (x_src*att_src).sum(-1); (x_dst*att_dst).sum(-1).
