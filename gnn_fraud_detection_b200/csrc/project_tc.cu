@@ -22,6 +22,7 @@
 #include "common.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace gnnfd {
 extern std::atomic<long long> g_launches;
@@ -496,9 +497,23 @@ inline int kblocks(int64_t Kd) { return int((Kd + BK - 1) / BK); }
 
 }  // namespace tc
 
+}  // namespace gnnfd
+#include "project_tc_ws.cuh"
+namespace gnnfd {
+
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
+// GNNFD_GEMM_WS=0 selects the simpler one-tile-per-CTA kernel (kept for A/B measurements)
+static bool use_ws()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GNNFD_GEMM_WS");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 static int g_tc_state = 0;   // 0 unknown, 1 usable, -1 not an sm_100 device
 static bool tc_device_ok()
 {
@@ -541,6 +556,22 @@ int project_fwd_tc(const float* x, int64_t ldx, const float* W, const float* att
     const int n_kb = tc::kblocks(K), n_tiles = D / BN;
     float* img = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     tc::build_b_images<<<dim3(8, n_kb, n_tiles), 256, 0, st>>>(W, K, 1, D, (int)K, BN, n_kb, img);
+    if (use_ws()) {
+        const int64_t tiles = int64_t(n_tiles) * ((N + tc::BM - 1) / tc::BM);
+        const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+        if (xw_dtype == GNNFD_BF16) {
+            GNNFD_CUDA(cudaFuncSetAttribute(tc::gemm_tc_ws<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS_SMEM));
+            tc::gemm_tc_ws<1, true><<<grid, tc::WS_THREADS, tc::WS_SMEM, st>>>(x, ldx, N, (int)K, img, n_kb, n_tiles, nullptr,
+                                                                             (__nv_bfloat16*)xw, D, D, att_src, att_dst, a_src, a_dst, H);
+        } else {
+            GNNFD_CUDA(cudaFuncSetAttribute(tc::gemm_tc_ws<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS_SMEM));
+            tc::gemm_tc_ws<1, false><<<grid, tc::WS_THREADS, tc::WS_SMEM, st>>>(x, ldx, N, (int)K, img, n_kb, n_tiles, (float*)xw,
+                                                                              nullptr, D, D, att_src, att_dst, a_src, a_dst, H);
+        }
+        g_launches += 2;
+        GNNFD_LAUNCH_CHECK();
+        return GNNFD_OK;
+    }
     const size_t smem = tc::gemm_smem_bytes<BN>();
     dim3 grid((unsigned)(int64_t(n_tiles) * ((N + tc::BM - 1) / tc::BM)));
     if (xw_dtype == GNNFD_BF16) {
@@ -569,6 +600,16 @@ int project_bwd_dx_tc(const float* dxw, const float* W, int64_t N, int64_t K, in
     float* img = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     // B row r = input feature k, reduction index = output column o: element = W[o*K + k]
     tc::build_b_images<<<dim3(8, n_kb, n_tiles), 256, 0, st>>>(W, 1, K, (int)K, D, BN, n_kb, img);
+    if (use_ws()) {
+        const int64_t tiles = int64_t(n_tiles) * ((N + tc::BM - 1) / tc::BM);
+        const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+        GNNFD_CUDA(cudaFuncSetAttribute(tc::gemm_tc_ws<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS_SMEM));
+        tc::gemm_tc_ws<0, false><<<grid, tc::WS_THREADS, tc::WS_SMEM, st>>>(dxw, D, N, D, img, n_kb, n_tiles, dx, nullptr, lddx,
+                                                                          (int)K, nullptr, nullptr, nullptr, nullptr, 0);
+        g_launches += 2;
+        GNNFD_LAUNCH_CHECK();
+        return GNNFD_OK;
+    }
     const size_t smem = tc::gemm_smem_bytes<BN>();
     GNNFD_CUDA(cudaFuncSetAttribute(tc::gemm_tc<BN, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)(int64_t(n_tiles) * ((N + tc::BM - 1) / tc::BM)));

@@ -1,0 +1,234 @@
+// Persistent, warp-specialised tcgen05 GEMM:  C[M, NT*256] = A[M, Kd] * B^T  (3xTF32, fp32 accumulate in TMEM).
+//
+// One CTA per SM, 9 warps:
+//   warps 0-3  A producers: coalesced 128-byte row segments of x -> hi/lo split -> swizzled K-major smem stage
+//   warp  4    one lane: cp.async.bulk of the prebuilt B image of the NEXT k-block, then the tcgen05.mma's of the
+//              current one; tcgen05.commit releases the smem stage and, on a tile's last k-block, hands the TMEM
+//              accumulator to the epilogue
+//   warps 5-8  epilogue: tcgen05.ld of their TMEM lane quadrant, logit dot products, staged coalesced stores
+// Two smem stages (A 2x32 KB, B 2x64 KB) and two TMEM accumulators (2 x 256 columns) keep all three roles busy:
+// the epilogue of tile t overlaps the mainloop of tile t+1, the copies of k-block k+1 overlap the MMAs of k.
+#pragma once
+
+namespace gnnfd {
+namespace tc {
+
+constexpr int WS_THREADS = 288;
+constexpr int WS_BN = 256;
+constexpr uint32_t WS_A_PART = BM * 128;            // 16 KB: one part (hi or lo) of an A k-block
+constexpr uint32_t WS_B_PART = WS_BN * 128;         // 32 KB
+constexpr uint32_t WS_STAGE = 2 * WS_A_PART + 2 * WS_B_PART;   // 96 KB
+constexpr int WS_STG_LD = 36;
+constexpr size_t WS_SMEM = 2 * WS_STAGE + 4 * 32 * WS_STG_LD * 4 + 1024;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int EPI, bool OUT_BF16>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const float* __restrict__ b_img, int n_kb,
+           int n_col_tiles, float* __restrict__ Cf, __nv_bfloat16* __restrict__ Cb, int64_t ldc, int n_valid,
+           const float* __restrict__ att_src, const float* __restrict__ att_dst, float* __restrict__ a_src,
+           float* __restrict__ a_dst, int H)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full_a[2], full_b[2], empty[2], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t m_tiles = (M + BM - 1) / BM;
+    const int64_t n_tiles = m_tiles * n_col_tiles;           // tile id = m * n_col_tiles + nt  (nt fastest)
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&full_a[s], 128);
+            mbar_init(&full_b[s], 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], 128);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 4) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp < 4) {
+        // ---------------- A producers ----------------------------------------------------------------
+        // software-pipelined by one step: the global loads of step i+1 are in flight while step i is split and
+        // stored, so neither the DRAM/L2 latency nor the smem stores sit on the MMA critical path
+        const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t n_steps = my_tiles * n_kb;
+        auto load_step = [&](int64_t step, float (&xr)[32]) {
+            const int64_t t = blockIdx.x + (step / n_kb) * gridDim.x;
+            const int64_t m0 = (t / n_col_tiles) * BM;
+            const int gk = int(step % n_kb) * BK + lane;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int64_t gm = m0 + warp * 32 + i;
+                xr[i] = (gm < M && gk < Kd) ? __ldg(A + gm * lda + gk) : 0.f;
+            }
+        };
+        auto store_step = [&](int64_t step, const float (&xr)[32]) {
+            const int s = int(step & 1);
+            const int64_t u = step >> 1;
+            if (u > 0) mbar_wait(&empty[s], uint32_t((u - 1) & 1));   // MMAs that read this stage have retired
+            uint8_t* sA_hi = smem + s * WS_STAGE;
+            uint8_t* sA_lo = sA_hi + WS_A_PART;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float h, l;
+                split_tf32(xr[i], h, l);
+                const uint32_t off = kmajor_off(warp * 32 + i, lane);
+                *reinterpret_cast<float*>(sA_hi + off) = h;
+                *reinterpret_cast<float*>(sA_lo + off) = l;
+            }
+            fence_proxy_async();
+            mbar_arrive(&full_a[s]);
+        };
+        float xa[32], xb[32];
+        if (n_steps > 0) load_step(0, xa);
+        for (int64_t step = 0; step < n_steps; step += 2) {
+            if (step + 1 < n_steps) load_step(step + 1, xb);
+            store_step(step, xa);
+            if (step + 1 < n_steps) {
+                if (step + 2 < n_steps) load_step(step + 2, xa);
+                store_step(step + 1, xb);
+            }
+        }
+    } else if (warp == 4) {
+        // ---------------- B copies + MMA issue (one lane) -----------------------------------------------
+        if (lane == 0) {
+            constexpr uint32_t IDESC = make_idesc(BM, WS_BN, 0, 0);
+            const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            const int64_t n_steps = my_tiles * n_kb;
+            auto issue_b = [&](int64_t step) {
+                const int64_t t = blockIdx.x + (step / n_kb) * gridDim.x;
+                const int kb = int(step % n_kb), nt = int(t % n_col_tiles);
+                const int s = int(step & 1);
+                const int64_t u = step >> 1;
+                if (u > 0) mbar_wait(&empty[s], uint32_t((u - 1) & 1));
+                uint8_t* sB = smem + s * WS_STAGE + 2 * WS_A_PART;
+                const float* img = b_img + (size_t(nt) * n_kb + kb) * 2 * (size_t(WS_BN) * BK);
+                mbar_expect_tx(&full_b[s], 2 * WS_B_PART);
+                bulk_g2s(sB, img, 2 * WS_B_PART, &full_b[s]);
+            };
+            if (n_steps > 0) issue_b(0);
+            for (int64_t step = 0; step < n_steps; ++step) {
+                if (step + 1 < n_steps) issue_b(step + 1);          // overlaps the MMAs issued below
+                const int64_t j = step / n_kb;                        // CTA-local tile counter
+                const int kb = int(step % n_kb);
+                const int s = int(step & 1);
+                const uint32_t par = uint32_t((step >> 1) & 1);
+                const int buf = int(j & 1);
+                if (kb == 0 && (j >> 1) > 0) {                        // accumulator buffer drained by the epilogue?
+                    mbar_wait(&acc_empty[buf], uint32_t(((j >> 1) - 1) & 1));
+                    tc_fence_after();
+                }
+                mbar_wait(&full_a[s], par);
+                mbar_wait(&full_b[s], par);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * WS_STAGE), a_lo = a_hi + WS_A_PART;
+                const uint32_t b_hi = a_hi + 2 * WS_A_PART, b_lo = b_hi + WS_B_PART;
+                const uint32_t d = tmem_base + uint32_t(buf * WS_BN);
+                const int ksteps = min(BK / UK, (Kd - kb * BK + UK - 1) / UK);
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t ko = ks * UK * 4;
+                    const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                    const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                    umma_tf32(d, dah, dbh, IDESC, (kb | ks) ? 1u : 0u);
+                    umma_tf32(d, dal, dbh, IDESC, 1u);
+                    umma_tf32(d, dah, dbl, IDESC, 1u);
+                }
+                umma_commit(&empty[s]);                               // stage reusable once these MMAs retire
+                if (kb == n_kb - 1) umma_commit(&acc_full[buf]);      // ... and the tile is complete
+            }
+        }
+    } else {
+        // ---------------- epilogue (warps 5..8 -> TMEM lane quadrants 1,2,3,0) ---------------------------
+        const int quad = warp & 3;
+        float* stg = reinterpret_cast<float*>(smem + 2 * WS_STAGE) + (warp - 5) * (32 * WS_STG_LD);
+        int64_t j = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+            const int64_t m0 = (t / n_col_tiles) * BM;
+            const int nt = int(t % n_col_tiles);
+            const int buf = int(j & 1);
+            mbar_wait(&acc_full[buf], uint32_t((j >> 1) & 1));
+            tc_fence_after();
+            const int64_t row = m0 + quad * 32 + lane;
+            float ps = 0.f, pd = 0.f;
+#pragma unroll 1
+            for (int ch = 0; ch < WS_BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(buf * WS_BN + ch * 32), v);
+                const int col0 = nt * WS_BN + ch * 32;
+                if (EPI == 1) {
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 as4 = __ldg(reinterpret_cast<const float4*>(att_src + col0 + c));
+                        const float4 ad4 = __ldg(reinterpret_cast<const float4*>(att_dst + col0 + c));
+                        ps = fmaf(__uint_as_float(v[c]), as4.x, ps); pd = fmaf(__uint_as_float(v[c]), ad4.x, pd);
+                        ps = fmaf(__uint_as_float(v[c + 1]), as4.y, ps); pd = fmaf(__uint_as_float(v[c + 1]), ad4.y, pd);
+                        ps = fmaf(__uint_as_float(v[c + 2]), as4.z, ps); pd = fmaf(__uint_as_float(v[c + 2]), ad4.z, pd);
+                        ps = fmaf(__uint_as_float(v[c + 3]), as4.w, ps); pd = fmaf(__uint_as_float(v[c + 3]), ad4.w, pd);
+                    }
+                    if (ch & 1) {                                   // two 32-column chunks per 64-wide head
+                        if (row < M) {
+                            const int h = col0 / 64;
+                            a_src[row * H + h] = ps;
+                            a_dst[row * H + h] = pd;
+                        }
+                        ps = pd = 0.f;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 32; c += 4)
+                    *reinterpret_cast<float4*>(stg + lane * WS_STG_LD + c) =
+                        make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]),
+                                    __uint_as_float(v[c + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + (lane >> 3), cq = (lane & 7) * 4;
+                    const int64_t gm = m0 + quad * 32 + r;
+                    const float4 o = *reinterpret_cast<const float4*>(stg + r * WS_STG_LD + cq);
+                    if (gm < M) {
+                        if (EPI == 1) {
+                            if (OUT_BF16) {
+                                __nv_bfloat162 lo2 = __floats2bfloat162_rn(o.x, o.y), hi2 = __floats2bfloat162_rn(o.z, o.w);
+                                uint2 pk;
+                                pk.x = *reinterpret_cast<uint32_t*>(&lo2);
+                                pk.y = *reinterpret_cast<uint32_t*>(&hi2);
+                                *reinterpret_cast<uint2*>(Cb + gm * ldc + col0 + cq) = pk;
+                            } else {
+                                *reinterpret_cast<float4*>(Cf + gm * ldc + col0 + cq) = o;
+                            }
+                        } else {
+                            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                if (col0 + cq + k < n_valid) Cf[gm * ldc + col0 + cq + k] = ov[k];
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace tc
+}  // namespace gnnfd
