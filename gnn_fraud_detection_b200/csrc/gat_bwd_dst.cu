@@ -112,14 +112,14 @@ template <class GE>
 __device__ __forceinline__ void dst_sweep2(const RowStat<GE::H>& r, int beg, int end, const int32_t* __restrict__ col,
                                            const int32_t* __restrict__ csr2csc, const float* __restrict__ a_src,
                                            float slope, const float (&t)[GE::H], int lane, float* __restrict__ dz,
-                                           float (&dad)[GE::H])
+                                           int64_t eg_ld, float (&dad)[GE::H])
 {
     constexpr int H = GE::H;
     for (int e = beg + lane; e < end; e += 32) {
         float as[H], u[H], o[H];
         const int64_t pos = csr2csc[e];          // edge gradients live in source-major order
         load_vecH<H>(a_src + int64_t(col[e]) * H, as);
-        load_vecH<H>(dz + pos * H, u);
+        load_vecH<H>(dz + pos * eg_ld, u);
 #pragma unroll
         for (int h = 0; h < H; ++h) {
             const float z = as[h] + r.adst[h];
@@ -128,7 +128,7 @@ __device__ __forceinline__ void dst_sweep2(const RowStat<GE::H>& r, int beg, int
             o[h] = sl * (u[h] - al * t[h]);
             dad[h] += o[h];
         }
-        store_vecH<H>(dz + pos * H, o);
+        store_vecH<H>(dz + pos * eg_ld, o);
     }
 }
 
@@ -143,7 +143,7 @@ __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bw
                                                const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                                                const float* __restrict__ d_out, float slope,
                                                const uint8_t* __restrict__ keep, float keep_scale,
-                                               float* __restrict__ alpha_used, float* __restrict__ dz,
+                                               float* __restrict__ alpha_used, float* __restrict__ dz, int64_t eg_ld,
                                                float* __restrict__ da_dst, float* __restrict__ part_t, int chunk_id,
                                                int lane)
 {
@@ -233,14 +233,14 @@ __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bw
                     dad[h] = warp_sum(o[h]);
                 }
                 if (live) {
-                    store_vecH<H>(alpha_used + pos * H, au);
-                    store_vecH<H>(dz + pos * H, o);
+                    store_vecH<H>(alpha_used + pos * eg_ld, au);
+                    store_vecH<H>(dz + pos * eg_ld, o);
                 }
                 if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
             } else {
                 if (live) {
-                    store_vecH<H>(alpha_used + pos * H, au);
-                    store_vecH<H>(dz + pos * H, u);       // parked until t is known
+                    store_vecH<H>(alpha_used + pos * eg_ld, au);
+                    store_vecH<H>(dz + pos * eg_ld, u);       // parked until t is known
                 }
 #pragma unroll
                 for (int h = 0; h < H; ++h) trow[h] += warp_sum(u[h]);
@@ -254,7 +254,7 @@ __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bw
                         float dad[H];
 #pragma unroll
                         for (int h = 0; h < H; ++h) dad[h] = 0.f;
-                        dst_sweep2<GE>(r, row_beg, c0.beg + c0.n, col, csr2csc, a_src, slope, trow, lane, dz, dad);
+                        dst_sweep2<GE>(r, row_beg, c0.beg + c0.n, col, csr2csc, a_src, slope, trow, lane, dz, eg_ld, dad);
 #pragma unroll
                         for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
                         if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
@@ -283,7 +283,7 @@ gat_bwd_dst_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                   const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                   const float* __restrict__ d_out, gnnfd_item_plan_t items, int hub_threshold, float slope,
                   const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
-                  float* __restrict__ dz, float* __restrict__ da_dst)
+                  float* __restrict__ dz, int64_t eg_ld, float* __restrict__ da_dst)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -294,7 +294,7 @@ gat_bwd_dst_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
     ChunkCursor cur;
     cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
     bwd_dst_stream<GE, CONCAT, DROPOUT, false>(cur, ring, rowptr, col, perm, csr2csc, xw, a_src, a_dst, rowmax, rowsum, d_out, slope,
-                                               keep, keep_scale, alpha_used, dz, da_dst, nullptr, 0, lane);
+                                               keep, keep_scale, alpha_used, dz, eg_ld, da_dst, nullptr, 0, lane);
 }
 
 // hub rows, step 1: one warp per chunk -- first sweep, partial t
@@ -305,7 +305,7 @@ gat_bwd_dst_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
                  const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                  const float* __restrict__ d_out, gnnfd_hub_plan_t plan, float slope,
                  const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
-                 float* __restrict__ dz, float* __restrict__ part_t)
+                 float* __restrict__ dz, int64_t eg_ld, float* __restrict__ part_t)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -320,7 +320,7 @@ gat_bwd_dst_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     ChunkCursor cur;
     cur.start_segment(i, beg, end);
     bwd_dst_stream<GE, CONCAT, DROPOUT, true>(cur, ring, rowptr, col, perm, csr2csc, xw, a_src, a_dst, rowmax, rowsum, d_out, slope,
-                                              keep, keep_scale, alpha_used, dz, nullptr, part_t, c, lane);
+                                              keep, keep_scale, alpha_used, dz, eg_ld, nullptr, part_t, c, lane);
 }
 // hub rows, step 2: total t of the row (chunk order), second sweep, partial da_dst
 template <class GE>
@@ -329,7 +329,7 @@ gat_bwd_dst_hub2(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
                  const int32_t* __restrict__ csr2csc, const float* __restrict__ a_src,
                  const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                  gnnfd_hub_plan_t plan, float slope, const float* __restrict__ t_total, float* __restrict__ dz,
-                 float* __restrict__ part_dad)
+                 int64_t eg_ld, float* __restrict__ part_dad)
 {
     constexpr int H = GE::H;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -347,7 +347,7 @@ gat_bwd_dst_hub2(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
 #pragma unroll
     for (int h = 0; h < H; ++h) dad[h] = 0.f;
     (void)c1;
-    dst_sweep2<GE>(r, beg, end, col, csr2csc, a_src, slope, t, lane, dz, dad);
+    dst_sweep2<GE>(r, beg, end, col, csr2csc, a_src, slope, t, lane, dz, eg_ld, dad);
 #pragma unroll
     for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
     if (lane == 0) store_vecH<H>(part_dad + int64_t(c) * H, dad);
@@ -400,13 +400,15 @@ static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* 
     const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
     const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
     const unsigned grid = (unsigned)((g->items_dst.n_items + ST_WARPS - 1) / ST_WARPS);
+    // two dense [E',H] arrays, or the halves of one interleaved [E',2H] buffer (dz == alpha_used + H)
+    const int64_t eg_ld = (dz == alpha_used + GE::H) ? 2 * GE::H : GE::H;
     int rc = GNNFD_OK;
 #define GNNFD_BWD_ITEMS(CC, DD)                                                                                        \
     rc = set_smem_bwd(gat_bwd_dst_items<GE, CC, DD>, SMEM);                                                            \
     if (rc) return rc;                                                                                                 \
     gat_bwd_dst_items<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, xw, a_src, a_dst, rowmax,  \
                                                                   rowsum, d_out, g->items_dst, thr, slope, keep, ks,    \
-                                                                  alpha_used, dz, da_dst)
+                                                                  alpha_used, dz, eg_ld, da_dst)
     if (concat) { if (drop) { GNNFD_BWD_ITEMS(true, true); } else { GNNFD_BWD_ITEMS(true, false); } }
     else        { if (drop) { GNNFD_BWD_ITEMS(false, true); } else { GNNFD_BWD_ITEMS(false, false); } }
 #undef GNNFD_BWD_ITEMS
@@ -426,13 +428,13 @@ static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* 
     rc = set_smem_bwd(gat_bwd_dst_hub1<GE, CC, DD>, SMEM);                                                             \
     if (rc) return rc;                                                                                                 \
     gat_bwd_dst_hub1<GE, CC, DD><<<gc, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, xw, a_src, a_dst, rowmax,     \
-                                                               rowsum, d_out, pl, slope, keep, ks, alpha_used, dz, part_t)
+                                                               rowsum, d_out, pl, slope, keep, ks, alpha_used, dz, eg_ld, part_t)
         if (concat) { if (drop) { GNNFD_BWD_HUB1(true, true); } else { GNNFD_BWD_HUB1(true, false); } }
         else        { if (drop) { GNNFD_BWD_HUB1(false, true); } else { GNNFD_BWD_HUB1(false, false); } }
 #undef GNNFD_BWD_HUB1
         gat_hub_chunk_sum<GE::H, false><<<gh, ROW_THREADS, 0, st>>>(pl, part_t, t_total);
         gat_bwd_dst_hub2<GE><<<gc2, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->csr2csc, a_src, a_dst, rowmax, rowsum, pl, slope,
-                                                          t_total, dz, part_dad);
+                                                          t_total, dz, eg_ld, part_dad);
         gat_hub_chunk_sum<GE::H, true><<<gh, ROW_THREADS, 0, st>>>(pl, part_dad, da_dst);
         g_launches += 4;
     }

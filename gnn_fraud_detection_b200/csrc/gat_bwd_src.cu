@@ -23,7 +23,7 @@ constexpr int BWD_U = 4;
 template <class GE, bool CONCAT>
 __device__ __forceinline__ void src_range(int beg, int end, const int32_t* __restrict__ csc_row,
                                           const int32_t* __restrict__ csc_eid, const float* __restrict__ alpha_used,
-                                          const float* __restrict__ dz, const float* __restrict__ d_out,
+                                          const float* __restrict__ dz, int64_t eg_ld, const float* __restrict__ d_out,
                                           float (&acc)[GE::NS][4], float (&das)[GE::H], float* p_s, int* i_s, int lane)
 {
     constexpr int H = GE::H, NS = GE::NS, HP = GE::HP, D = GE::D, C = GE::C;
@@ -37,8 +37,8 @@ __device__ __forceinline__ void src_range(int beg, int end, const int32_t* __res
             const int64_t eid = csc_eid ? int64_t(csc_eid[base + lane]) : int64_t(base + lane);
             i = csc_row[base + lane];
             float al[H], dzv[H];
-            load_vecH<H>(alpha_used + eid * H, al);
-            load_vecH<H>(dz + eid * H, dzv);
+            load_vecH<H>(alpha_used + eid * eg_ld, al);
+            load_vecH<H>(dz + eid * eg_ld, dzv);
 #pragma unroll
             for (int h = 0; h < H; ++h) das[h] += dzv[h];
             store_vecH<H>(p_s + lane * H, al);
@@ -108,7 +108,7 @@ template <class GE, bool CONCAT>
 __global__ void __launch_bounds__(ROW_THREADS)
 gat_bwd_src_rows(const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_row,
                  const int32_t* __restrict__ csc_eid, const float* __restrict__ alpha_used,
-                 const float* __restrict__ dz, const float* __restrict__ d_out, const float* __restrict__ att_src,
+                 const float* __restrict__ dz, int64_t eg_ld, const float* __restrict__ d_out, const float* __restrict__ att_src,
                  const float* __restrict__ att_dst, const float* __restrict__ da_dst_full, gnnfd_item_plan_t items,
                  int hub_threshold, float* __restrict__ dxw, float* __restrict__ da_src)
 {
@@ -130,7 +130,7 @@ gat_bwd_src_rows(const int32_t* __restrict__ colptr, const int32_t* __restrict__
             for (int k = 0; k < 4; ++k) acc[q][k] = 0.f;
 #pragma unroll
         for (int h = 0; h < H; ++h) das[h] = 0.f;
-        src_range<GE, CONCAT>(beg, end, csc_row, csc_eid, alpha_used, dz, d_out, acc, das, p_sh[warp], i_sh[warp], lane);
+        src_range<GE, CONCAT>(beg, end, csc_row, csc_eid, alpha_used, dz, eg_ld, d_out, acc, das, p_sh[warp], i_sh[warp], lane);
 #pragma unroll
         for (int h = 0; h < H; ++h) das[h] = warp_sum(das[h]);
         src_epilogue<GE, CONCAT>(j, acc, das, att_src, att_dst, da_dst_full, dxw, da_src, lane);
@@ -141,7 +141,7 @@ template <class GE, bool CONCAT>
 __global__ void __launch_bounds__(ROW_THREADS)
 gat_bwd_src_hub_chunks(const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_row,
                        const int32_t* __restrict__ csc_eid, const float* __restrict__ alpha_used,
-                       const float* __restrict__ dz, const float* __restrict__ d_out, gnnfd_hub_plan_t plan,
+                       const float* __restrict__ dz, int64_t eg_ld, const float* __restrict__ d_out, gnnfd_hub_plan_t plan,
                        float* __restrict__ part_acc, float* __restrict__ part_das)
 {
     constexpr int H = GE::H, NS = GE::NS, D = GE::D;
@@ -161,7 +161,7 @@ gat_bwd_src_hub_chunks(const int32_t* __restrict__ colptr, const int32_t* __rest
         for (int k = 0; k < 4; ++k) acc[q][k] = 0.f;
 #pragma unroll
     for (int h = 0; h < H; ++h) das[h] = 0.f;
-    src_range<GE, CONCAT>(beg, end, csc_row, csc_eid, alpha_used, dz, d_out, acc, das, p_sh[warp], i_sh[warp], lane);
+    src_range<GE, CONCAT>(beg, end, csc_row, csc_eid, alpha_used, dz, eg_ld, d_out, acc, das, p_sh[warp], i_sh[warp], lane);
 #pragma unroll
     for (int h = 0; h < H; ++h) das[h] = warp_sum(das[h]);
     if (lane == 0) store_vecH<H>(part_das + int64_t(c) * H, das);
@@ -211,15 +211,17 @@ static int launch_bwd_src(const gnnfd_graph_t* g, const float* alpha_used, const
     const int64_t n = g->n_src;
     if (n == 0) return GNNFD_OK;
     const int32_t* eid_ptr = g->edge_grads_indirect ? g->csc_eid : nullptr;
+    // two dense [E',H] arrays, or the halves of one interleaved [E',2H] buffer (dz == alpha_used + H)
+    const int64_t eg_ld = (dz == alpha_used + GE::H) ? 2 * GE::H : GE::H;
     const int thr = g->hub_src.n_hub > 0 ? g->hub_src.threshold : INT_MAX;
     GNNFD_REQUIRE(g->items_src.n_items > 0 && g->items_src.item_start, GNNFD_ERR_ARG,
                   "gat_bwd_src: the graph has no work-item plan over colptr (gnnfd_item_plan)");
     const unsigned grid = (unsigned)((g->items_src.n_items + ROW_WARPS - 1) / ROW_WARPS);
     if (concat)
-        gat_bwd_src_rows<GE, true><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, d_out,
+        gat_bwd_src_rows<GE, true><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, eg_ld, d_out,
                                                                  att_src, att_dst, da_dst_full, g->items_src, thr, dxw, da_src);
     else
-        gat_bwd_src_rows<GE, false><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, d_out,
+        gat_bwd_src_rows<GE, false><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, eg_ld, d_out,
                                                                   att_src, att_dst, da_dst_full, g->items_src, thr, dxw, da_src);
     g_launches += 1;
     if (g->hub_src.n_hub > 0) {
@@ -232,12 +234,12 @@ static int launch_bwd_src(const gnnfd_graph_t* g, const float* alpha_used, const
         const unsigned gc = (unsigned)((pl.n_chunk + ROW_WARPS - 1) / ROW_WARPS);
         const unsigned gh = (unsigned)((pl.n_hub + ROW_WARPS - 1) / ROW_WARPS);
         if (concat) {
-            gat_bwd_src_hub_chunks<GE, true><<<gc, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz,
+            gat_bwd_src_hub_chunks<GE, true><<<gc, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, eg_ld,
                                                                          d_out, pl, part_acc, part_das);
             gat_bwd_src_hub_merge<GE, true><<<gh, ROW_THREADS, 0, st>>>(pl, part_acc, part_das, att_src, att_dst,
                                                                         da_dst_full, dxw, da_src);
         } else {
-            gat_bwd_src_hub_chunks<GE, false><<<gc, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz,
+            gat_bwd_src_hub_chunks<GE, false><<<gc, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, eg_ld,
                                                                           d_out, pl, part_acc, part_das);
             gat_bwd_src_hub_merge<GE, false><<<gh, ROW_THREADS, 0, st>>>(pl, part_acc, part_das, att_src, att_dst,
                                                                          da_dst_full, dxw, da_src);

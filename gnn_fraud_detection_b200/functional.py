@@ -98,11 +98,14 @@ def gat_bwd(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, att_src, att_d
 
 def gat_bwd_dst(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, H, C_, negative_slope, concat, keep_mask=None,
                 p_drop=0.0):
-    """dst-major pass: alpha_used [E',H], dz [E',H] (both in source-major order) and da_dst [n_dst,H]."""
+    """dst-major pass: alpha_used [E',H], dz [E',H] (views of one interleaved [E',2H] buffer, rows in source-major
+    order) and da_dst [n_dst,H]."""
     L = _abi.lib()
     dev = xw.device
-    alpha_used = torch.empty(g.n_edges, H, dtype=torch.float32, device=dev)
-    dz = torch.empty(g.n_edges, H, dtype=torch.float32, device=dev)
+    # one interleaved [E', 2H] buffer: row = (alpha_used[0..H), dz[0..H)) of an edge, 64 contiguous bytes; the
+    # library recognises the layout from dz == alpha_used + H
+    eg = torch.empty(g.n_edges, 2 * H, dtype=torch.float32, device=dev)
+    alpha_used, dz = eg[:, :H], eg[:, H:]
     da_dst = torch.empty(g.n_dst, H, dtype=torch.float32, device=dev)
     nb = C.c_size_t()
     _abi.check(L.gnnfd_gat_bwd_workspace_bytes(g.ref(), H, C_, C.byref(nb)))

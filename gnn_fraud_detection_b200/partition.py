@@ -318,10 +318,11 @@ class ReplicatedInputPartition(DstRangePartition):
             dO_full[lo:lo + n] = d_out
         alpha_used, dz, da_dst = Fn.gat_bwd_dst(g, xw_full, asrc_full, a_dst, rowmax, rowsum, d_out, H, C, 0.2, False)
         if self.world > 1:
-            r_alpha = torch.empty(self.n_recv, H, dtype=torch.float32, device=dev)
-            r_dz = torch.empty(self.n_recv, H, dtype=torch.float32, device=dev)
-            dist.all_to_all_single(r_alpha, alpha_used, self.recv_splits, self.send_splits)
-            dist.all_to_all_single(r_dz, dz, self.recv_splits, self.send_splits)
+            # alpha_used / dz are the halves of one interleaved [E',2H] buffer: one all-to-all of 64-byte rows
+            eg = alpha_used._base if alpha_used._base is not None else torch.cat([alpha_used, dz], 1)
+            r_eg = torch.empty(self.n_recv, 2 * H, dtype=torch.float32, device=dev)
+            dist.all_to_all_single(r_eg, eg, self.recv_splits, self.send_splits)
+            r_alpha, r_dz = r_eg[:, :H], r_eg[:, H:]
             ag_work.wait()
         else:
             r_alpha, r_dz = alpha_used, dz

@@ -174,7 +174,9 @@ int gnnfd_gat_alpha(const gnnfd_graph_t* g, const float* a_src, const float* a_d
  *   writes alpha_used [E',H] (alpha after dropout scaling) and dz [E',H] -- both in SOURCE-MAJOR (CSC)
  *   order, i.e. the value of dst-sorted edge e lands at row csr2csc[e], so that the src-major pass (and,
  *   across GPUs, the exchange to the source owners) reads them contiguously -- and da_dst [n_dst,H].
- *   Needs the CSC twin and csr2csc.
+ *   alpha_used and dz are either two dense [E',H] arrays or the two halves of ONE interleaved [E',2H]
+ *   buffer (dz == alpha_used + H: 64 contiguous bytes per edge) -- the library recognises the latter from
+ *   the pointers.  Needs the CSC twin and csr2csc.
  * src-major pass (needs the CSC twin): dxw[j] = sum_e alpha_used*dO_h[i] + da_src[j]*att_src
  *   + da_dst_full[j]*att_dst, da_src[j] = sum_e dz.  da_dst_full is indexed by SOURCE id (for a single
  *   GPU it is the da_dst the dst pass produced; NULL => the att_dst term is skipped).
