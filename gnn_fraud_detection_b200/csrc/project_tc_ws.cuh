@@ -21,6 +21,16 @@ constexpr uint32_t WS_STAGE = 2 * WS_A_PART + 2 * WS_B_PART;   // 96 KB
 constexpr int WS_STG_LD = 36;
 constexpr size_t WS_SMEM = 2 * WS_STAGE + 4 * 32 * WS_STG_LD * 4 + 1024;
 
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -38,7 +48,8 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
     __shared__ uint64_t full_a[2], full_b[2], empty[2], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler (uniform datapath)
     const int64_t m_tiles = (M + BM - 1) / BM;
     const int64_t n_tiles = m_tiles * n_col_tiles;           // tile id = m * n_col_tiles + nt  (nt fastest)
 
@@ -103,7 +114,9 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
         }
     } else if (warp == 4) {
         // ---------------- B copies + MMA issue (one lane) -----------------------------------------------
-        if (lane == 0) {
+        {
+            // the whole warp walks the loop with warp-uniform operands (descriptors live in uniform registers);
+            // one elected lane issues the asynchronous instructions
             constexpr uint32_t IDESC = make_idesc(BM, WS_BN, 0, 0);
             const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
             const int64_t n_steps = my_tiles * n_kb;
@@ -115,8 +128,11 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                 if (u > 0) mbar_wait(&empty[s], uint32_t((u - 1) & 1));
                 uint8_t* sB = smem + s * WS_STAGE + 2 * WS_A_PART;
                 const float* img = b_img + (size_t(nt) * n_kb + kb) * 2 * (size_t(WS_BN) * BK);
-                mbar_expect_tx(&full_b[s], 2 * WS_B_PART);
-                bulk_g2s(sB, img, 2 * WS_B_PART, &full_b[s]);
+                if (elect_one()) {
+                    mbar_expect_tx(&full_b[s], 2 * WS_B_PART);
+                    bulk_g2s(sB, img, 2 * WS_B_PART, &full_b[s]);
+                }
+                __syncwarp();
             };
             if (n_steps > 0) issue_b(0);
             for (int64_t step = 0; step < n_steps; ++step) {
@@ -137,16 +153,19 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                 const uint32_t b_hi = a_hi + 2 * WS_A_PART, b_lo = b_hi + WS_B_PART;
                 const uint32_t d = tmem_base + uint32_t(buf * WS_BN);
                 const int ksteps = min(BK / UK, (Kd - kb * BK + UK - 1) / UK);
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint32_t ko = ks * UK * 4;
-                    const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
-                    const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
-                    umma_tf32(d, dah, dbh, IDESC, (kb | ks) ? 1u : 0u);
-                    umma_tf32(d, dal, dbh, IDESC, 1u);
-                    umma_tf32(d, dah, dbl, IDESC, 1u);
+                if (elect_one()) {
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint32_t ko = ks * UK * 4;
+                        const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                        const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                        umma_tf32(d, dah, dbh, IDESC, (kb | ks) ? 1u : 0u);
+                        umma_tf32(d, dal, dbh, IDESC, 1u);
+                        umma_tf32(d, dah, dbl, IDESC, 1u);
+                    }
+                    umma_commit(&empty[s]);                           // stage reusable once these MMAs retire
+                    if (kb == n_kb - 1) umma_commit(&acc_full[buf]);  // ... and the tile is complete
                 }
-                umma_commit(&empty[s]);                               // stage reusable once these MMAs retire
-                if (kb == n_kb - 1) umma_commit(&acc_full[buf]);      // ... and the tile is complete
+                __syncwarp();
             }
         }
     } else {
