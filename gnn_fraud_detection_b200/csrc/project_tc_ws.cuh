@@ -36,7 +36,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int EPI, bool OUT_BF16>
+template <int EPI, bool OUT_BF16, bool FAST = false>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const float* __restrict__ b_img, int n_kb,
            int n_col_tiles, float* __restrict__ Cf, __nv_bfloat16* __restrict__ Cb, int64_t ldc, int n_valid,
@@ -128,9 +128,9 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                 if (u > 0) mbar_wait(&empty[s], uint32_t((u - 1) & 1));
                 uint8_t* sB = smem + s * WS_STAGE + 2 * WS_A_PART;
                 const float* img = b_img + (size_t(nt) * n_kb + kb) * 2 * (size_t(WS_BN) * BK);
-                if (elect_one()) {
-                    mbar_expect_tx(&full_b[s], 2 * WS_B_PART);
-                    bulk_g2s(sB, img, 2 * WS_B_PART, &full_b[s]);
+                if (elect_one()) {     // FAST needs only the hi half of the image
+                    mbar_expect_tx(&full_b[s], (FAST ? 1 : 2) * WS_B_PART);
+                    bulk_g2s(sB, img, (FAST ? 1 : 2) * WS_B_PART, &full_b[s]);
                 }
                 __syncwarp();
             };
@@ -159,8 +159,10 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                         const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
                         const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
                         umma_tf32(d, dah, dbh, IDESC, (kb | ks) ? 1u : 0u);
-                        umma_tf32(d, dal, dbh, IDESC, 1u);
-                        umma_tf32(d, dah, dbl, IDESC, 1u);
+                        if (!FAST) {
+                            umma_tf32(d, dal, dbh, IDESC, 1u);
+                            umma_tf32(d, dah, dbl, IDESC, 1u);
+                        }
                     }
                     umma_commit(&empty[s]);                           // stage reusable once these MMAs retire
                     if (kb == n_kb - 1) umma_commit(&acc_full[buf]);  // ... and the tile is complete

@@ -212,8 +212,12 @@ def test_projection_tensor_core_3xtf32(N, K, dtype):
         assert relerr(xw_t, ref) <= 2e-6
     else:
         assert relerr(xw_t.float(), ref) <= 4e-3
-    assert maxabs(as_t, ra) <= TOL32 and maxabs(ad_t, rd) <= TOL32
-    assert maxabs(as_t, as_s) <= TOL32
+    if dtype == torch.float32:
+        assert maxabs(as_t, ra) <= TOL32 and maxabs(ad_t, rd) <= TOL32
+        assert maxabs(as_t, as_s) <= TOL32
+    else:   # bf16 feature storage runs ONE TF32 pass (2e-2 relative bar): logits carry ~1e-3 relative error
+        assert relerr(as_t, ra) <= 4e-3 and relerr(ad_t, rd) <= 4e-3
+        assert maxabs(as_s, ra) <= TOL32      # the fp32 SIMT path stays exact
 
 
 @pytest.mark.parametrize("N,K", [(1, 7), (1000, 166), (3000, 64), (500, 300), (10000, 166), (9000, 165), (33, 256)])
