@@ -188,14 +188,32 @@ __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bw
             float v[NS][VW];
 #pragma unroll
             for (int q = 0; q < NS; ++q) lds_slot(row, q, lane, v[q]);
+            float d[NS];
 #pragma unroll
             for (int q = 0; q < NS; ++q) {
-                float d = 0.f;
+                d[q] = 0.f;
 #pragma unroll
-                for (int k = 0; k < VW; ++k) d = fmaf(g0[q][k], v[q][k], d);
+                for (int k = 0; k < VW; ++k) d[q] = fmaf(g0[q][k], v[q][k], d[q]);
+            }
+            if constexpr (NS == 4 && G == 16) {
+                // reduce-scatter butterfly over the 16-lane head group: 5 shuffles instead of 4 x 4.  After the
+                // xor-8 / xor-4 steps a lane keeps only slot q = 2*bit3 + bit2; xor-2 / xor-1 finish its sum.
+                const bool b3 = lane & 8, b2 = lane & 4;
+                const float k0 = b3 ? d[2] : d[0], k1 = b3 ? d[3] : d[1];
+                const float s0 = b3 ? d[0] : d[2], s1 = b3 ? d[1] : d[3];
+                const float a0 = k0 + __shfl_xor_sync(FULL, s0, 8), a1 = k1 + __shfl_xor_sync(FULL, s1, 8);
+                float b = (b2 ? a1 : a0) + __shfl_xor_sync(FULL, b2 ? a0 : a1, 4);
+                b += __shfl_xor_sync(FULL, b, 2);
+                b += __shfl_xor_sync(FULL, b, 1);
+                if ((lane & 3) == 0) dal_s[t * H + ((lane >> 2) & 3) * HP + sub] = b;
+            } else {
 #pragma unroll
-                for (int o = G / 2; o > 0; o >>= 1) d += __shfl_xor_sync(FULL, d, o);
-                if ((lane & (G - 1)) == 0) dal_s[t * H + q * HP + sub] = d;
+                for (int q = 0; q < NS; ++q) {
+                    float dq = d[q];
+#pragma unroll
+                    for (int o = G / 2; o > 0; o >>= 1) dq += __shfl_xor_sync(FULL, dq, o);
+                    if ((lane & (G - 1)) == 0) dal_s[t * H + q * HP + sub] = dq;
+                }
             }
             ring.pop();
             if (issued0 < c0.n) ring.issue(xw, j0[issued0++], lane);
