@@ -174,9 +174,17 @@ dw_partial(const float* __restrict__ dxw, int64_t D, const float* __restrict__ x
 __global__ void reduce_slices(const float* __restrict__ P, int64_t n, int S, float* __restrict__ out)
 {
     for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < S; ++k) s += P[int64_t(k) * n + i];
-        out[i] = s;
+        // eight independent partial sums keep eight loads in flight; the combine order is fixed => deterministic
+        float s[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] = 0.f;
+        int k = 0;
+        for (; k + 8 <= S; k += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] += P[int64_t(k + u) * n + i];
+        }
+        for (; k < S; ++k) s[0] += P[int64_t(k) * n + i];
+        out[i] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
     }
 }
 
