@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -61,6 +61,8 @@ SIGNATURES = {
     "gnnfd_project_fwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gnnfd_gat_fwd_workspace_bytes": (_i, [_gp, _i, _i, _szp]),
     "gnnfd_gat_fwd": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gnnfd_gat_fwd_fused": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _sz, _vp]),
     "gnnfd_gat_alpha": (_i, [_gp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
     "gnnfd_gat_bwd_workspace_bytes": (_i, [_gp, _i, _i, _szp]),
     "gnnfd_gat_bwd_dst": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _f, _vp, _vp, _vp, _vp,

@@ -20,6 +20,16 @@
 namespace gnnfd {
 extern std::atomic<long long> g_launches;
 
+// Fused row epilogue:  v = mean/concat + bias;  v = v*scale + shift (folded eval-mode BatchNorm, optional);
+// v = act(v);  v += residual[row] (optional).  Mirrors gat.py:80-91 in eval mode (BatchNorm -> ReLU -> residual).
+struct EpiParams {
+    const float* bias;
+    const float* scale;
+    const float* shift;
+    const float* residual;
+    int act;
+};
+
 __device__ __forceinline__ float apply_act(float v, int act)
 {
     if (act == GNNFD_ACT_RELU) return fmaxf(v, 0.f);
@@ -30,7 +40,7 @@ __device__ __forceinline__ float apply_act(float v, int act)
 // normalise by the softmax denominator, save the row statistics, head mean/concat + bias + activation
 template <class GE, bool CONCAT>
 __device__ __forceinline__ void fwd_epilogue(int64_t i, const float (&m)[GE::H], const float (&s)[GE::H],
-                                             float (&acc)[GE::NS][GE::VW], const float* __restrict__ bias, int act,
+                                             float (&acc)[GE::NS][GE::VW], const EpiParams& ep,
                                              float* __restrict__ out, float* __restrict__ rowmax,
                                              float* __restrict__ rowsum, int lane)
 {
@@ -58,7 +68,13 @@ __device__ __forceinline__ void fwd_epilogue(int64_t i, const float (&m)[GE::H],
             const int c0 = VW * (lane + 32 * q);
             float r[VW];
 #pragma unroll
-            for (int k = 0; k < VW; ++k) r[k] = apply_act(acc[q][k] + (bias ? bias[c0 + k] : 0.f), act);
+            for (int k = 0; k < VW; ++k) {
+                float v = acc[q][k] + (ep.bias ? ep.bias[c0 + k] : 0.f);
+                if (ep.scale) v = fmaf(v, ep.scale[c0 + k], ep.shift[c0 + k]);
+                v = apply_act(v, ep.act);
+                if (ep.residual) v += ep.residual[i * D + c0 + k];
+                r[k] = v;
+            }
 #pragma unroll
             for (int k = 0; k < VW; k += 4)
                 stg_stream(reinterpret_cast<float4*>(out + i * D + c0 + k), make_float4(r[k], r[k + 1], r[k + 2], r[k + 3]));
@@ -76,7 +92,13 @@ __device__ __forceinline__ void fwd_epilogue(int64_t i, const float (&m)[GE::H],
         if (sub == 0) {
             const int c0 = VW * lane;  // lane < G here
 #pragma unroll
-            for (int k = 0; k < VW; ++k) r[k] = apply_act(r[k] * (1.f / H) + (bias ? bias[c0 + k] : 0.f), act);
+            for (int k = 0; k < VW; ++k) {
+                float v = r[k] * (1.f / H) + (ep.bias ? ep.bias[c0 + k] : 0.f);
+                if (ep.scale) v = fmaf(v, ep.scale[c0 + k], ep.shift[c0 + k]);
+                v = apply_act(v, ep.act);
+                if (ep.residual) v += ep.residual[i * C + c0 + k];
+                r[k] = v;
+            }
 #pragma unroll
             for (int k = 0; k < VW; k += 4)
                 stg_stream(reinterpret_cast<float4*>(out + i * C + c0 + k), make_float4(r[k], r[k + 1], r[k + 2], r[k + 3]));
@@ -136,11 +158,11 @@ __device__ __forceinline__ void fwd_phase_a(ChunkStat<GE::H>& c, int beg, const 
 // What happens when a row (or a hub chunk) is complete.
 template <class GE, bool CONCAT>
 struct RowEpilogue {
-    const float* bias; int act; float* out; float* rowmax; float* rowsum;
+    EpiParams ep; float* out; float* rowmax; float* rowsum;
     __device__ __forceinline__ void finish(int row, const float (&m)[GE::H], const float (&s)[GE::H],
                                            float (&acc)[GE::NS][GE::VW], int lane) const
     {
-        fwd_epilogue<GE, CONCAT>(row, m, s, acc, bias, act, out, rowmax, rowsum, lane);
+        fwd_epilogue<GE, CONCAT>(row, m, s, acc, ep, out, rowmax, rowsum, lane);
     }
     __device__ __forceinline__ void empty(int row, int lane) const
     {
@@ -151,7 +173,7 @@ struct RowEpilogue {
         for (int q = 0; q < GE::NS; ++q)
 #pragma unroll
             for (int k = 0; k < GE::VW; ++k) acc[q][k] = 0.f;
-        fwd_epilogue<GE, CONCAT>(row, m, s, acc, bias, act, out, rowmax, rowsum, lane);
+        fwd_epilogue<GE, CONCAT>(row, m, s, acc, ep, out, rowmax, rowsum, lane);
     }
 };
 template <class GE>
@@ -266,8 +288,8 @@ template <class GE, bool CONCAT, bool DROPOUT>
 __global__ void __launch_bounds__(ST_THREADS, 4)
 gat_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
               const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
-              const float* __restrict__ a_dst, const float* __restrict__ bias, gnnfd_item_plan_t items,
-              int hub_threshold, float slope, int act, const uint8_t* __restrict__ keep, float keep_scale,
+              const float* __restrict__ a_dst, EpiParams ep, gnnfd_item_plan_t items,
+              int hub_threshold, float slope, const uint8_t* __restrict__ keep, float keep_scale,
               float* __restrict__ out, float* __restrict__ rowmax, float* __restrict__ rowsum)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -278,7 +300,7 @@ gat_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     ring.init(smem + warp * StreamGeo<GE>::WARP_BYTES, lane);
     ChunkCursor cur;
     cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
-    RowEpilogue<GE, CONCAT> sink{bias, act, out, rowmax, rowsum};
+    RowEpilogue<GE, CONCAT> sink{ep, out, rowmax, rowsum};
     fwd_stream<GE, DROPOUT>(cur, ring, sink, rowptr, col, perm, xw, a_src, a_dst, slope, keep, keep_scale, lane);
 }
 
@@ -312,8 +334,7 @@ gat_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict
 template <class GE, bool CONCAT>
 __global__ void __launch_bounds__(ROW_THREADS)
 gat_fwd_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_ms, const float* __restrict__ part_acc,
-                  const float* __restrict__ bias, int act, float* __restrict__ out, float* __restrict__ rowmax,
-                  float* __restrict__ rowsum)
+                  EpiParams ep, float* __restrict__ out, float* __restrict__ rowmax, float* __restrict__ rowsum)
 {
     constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP, D = GE::D;
     __shared__ __align__(16) float st_ms[ROW_WARPS][2 * H];
@@ -377,7 +398,7 @@ gat_fwd_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_ms, cons
         for (int h = 0; h < H; ++h) { mc[h] = st_ms[w][h]; sc[h] = st_ms[w][H + h]; }
         fold(mc, sc, &st_acc[w][0]);
     }
-    fwd_epilogue<GE, CONCAT>(i, M, s, acc, bias, act, out, rowmax, rowsum, lane);
+    fwd_epilogue<GE, CONCAT>(i, M, s, acc, ep, out, rowmax, rowsum, lane);
 }
 
 // alpha[e,h] in CSR order from the saved row statistics; warp per row, lane = edge
@@ -413,7 +434,7 @@ static int set_smem(K kernel, int bytes)
 
 template <class GE>
 static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_src, const float* a_dst,
-                      const float* bias, float slope, int concat, int act, const uint8_t* keep, float p_drop,
+                      EpiParams ep, float slope, int concat, const uint8_t* keep, float p_drop,
                       float* out, float* rowmax, float* rowsum, void* ws, size_t ws_bytes, cudaStream_t st)
 {
     using XT = typename GE::XT;
@@ -431,9 +452,8 @@ static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_sr
 #define GNNFD_FWD_ITEMS(CC, DD)                                                                                       \
     rc = set_smem(gat_fwd_items<GE, CC, DD>, SMEM);                                                                   \
     if (rc) return rc;                                                                                                \
-    gat_fwd_items<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, bias,       \
-                                                              g->items_dst, thr, slope, act, keep, ks, out, rowmax,    \
-                                                              rowsum)
+    gat_fwd_items<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, ep,         \
+                                                              g->items_dst, thr, slope, keep, ks, out, rowmax, rowsum)
     if (concat) { if (drop) { GNNFD_FWD_ITEMS(true, true); } else { GNNFD_FWD_ITEMS(true, false); } }
     else        { if (drop) { GNNFD_FWD_ITEMS(false, true); } else { GNNFD_FWD_ITEMS(false, false); } }
 #undef GNNFD_FWD_ITEMS
@@ -459,9 +479,9 @@ static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_sr
                                                                         slope, keep, ks, part_ms, part_acc);
         }
         if (concat)
-            gat_fwd_hub_merge<GE, true><<<gh, ROW_THREADS, 0, st>>>(pl, part_ms, part_acc, bias, act, out, rowmax, rowsum);
+            gat_fwd_hub_merge<GE, true><<<gh, ROW_THREADS, 0, st>>>(pl, part_ms, part_acc, ep, out, rowmax, rowsum);
         else
-            gat_fwd_hub_merge<GE, false><<<gh, ROW_THREADS, 0, st>>>(pl, part_ms, part_acc, bias, act, out, rowmax, rowsum);
+            gat_fwd_hub_merge<GE, false><<<gh, ROW_THREADS, 0, st>>>(pl, part_ms, part_acc, ep, out, rowmax, rowsum);
         g_launches += 2;
     }
     GNNFD_LAUNCH_CHECK();
@@ -494,10 +514,11 @@ int gnnfd_gat_fwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* 
     return GNNFD_OK;
 }
 
-int gnnfd_gat_fwd(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src, const float* a_dst,
-                  const float* bias, int H, int C, float negative_slope, int concat, int act,
-                  const uint8_t* keep_mask, float p_drop, float* out, float* rowmax, float* rowsum, void* ws,
-                  size_t ws_bytes, gnnfd_stream_t stream)
+int gnnfd_gat_fwd_fused(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src, const float* a_dst,
+                        const float* bias, int H, int C, float negative_slope, int concat, int act,
+                        const uint8_t* keep_mask, float p_drop, const float* post_scale, const float* post_shift,
+                        const float* residual, float* out, float* rowmax, float* rowsum, void* ws, size_t ws_bytes,
+                        gnnfd_stream_t stream)
 {
     int rc = check_graph(g, false, "gat_fwd");
     if (rc) return rc;
@@ -506,19 +527,31 @@ int gnnfd_gat_fwd(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const fl
     GNNFD_REQUIRE(p_drop >= 0.f && p_drop < 1.f, GNNFD_ERR_ARG, "gat_fwd: dropout p must be in [0,1)");
     GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(xw) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                   GNNFD_ERR_ARG, "gat_fwd: xw/out must be 16-byte aligned");
+    GNNFD_REQUIRE((post_scale == nullptr) == (post_shift == nullptr), GNNFD_ERR_ARG,
+                  "gat_fwd: post_scale and post_shift must be given together");
     cudaStream_t st = (cudaStream_t)stream;
+    const EpiParams ep{bias, post_scale, post_shift, residual, act};
     if (H == 8 && C == 64 && xw_dtype == GNNFD_F32)
-        return launch_fwd<Geo<8, 64, float>>(g, xw, a_src, a_dst, bias, negative_slope, concat, act, keep_mask, p_drop,
-                                             out, rowmax, rowsum, ws, ws_bytes, st);
+        return launch_fwd<Geo<8, 64, float>>(g, xw, a_src, a_dst, ep, negative_slope, concat, keep_mask, p_drop, out, rowmax,
+                                             rowsum, ws, ws_bytes, st);
     if (H == 8 && C == 64 && xw_dtype == GNNFD_BF16)
-        return launch_fwd<Geo<8, 64, __nv_bfloat16>>(g, xw, a_src, a_dst, bias, negative_slope, concat, act, keep_mask,
-                                                     p_drop, out, rowmax, rowsum, ws, ws_bytes, st);
+        return launch_fwd<Geo<8, 64, __nv_bfloat16>>(g, xw, a_src, a_dst, ep, negative_slope, concat, keep_mask, p_drop, out,
+                                                     rowmax, rowsum, ws, ws_bytes, st);
     if (H == 4 && C == 32 && xw_dtype == GNNFD_F32)
-        return launch_fwd<Geo<4, 32, float>>(g, xw, a_src, a_dst, bias, negative_slope, concat, act, keep_mask, p_drop,
-                                             out, rowmax, rowsum, ws, ws_bytes, st);
+        return launch_fwd<Geo<4, 32, float>>(g, xw, a_src, a_dst, ep, negative_slope, concat, keep_mask, p_drop, out, rowmax,
+                                             rowsum, ws, ws_bytes, st);
     GNNFD_REQUIRE(false, GNNFD_ERR_UNSUPPORTED, "gat_fwd: (heads=%d, out_channels=%d, dtype=%d) is not built; "
                   "available: (8,64,f32), (8,64,bf16), (4,32,f32)", H, C, xw_dtype);
     return GNNFD_ERR_UNSUPPORTED;
+}
+
+int gnnfd_gat_fwd(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src, const float* a_dst,
+                  const float* bias, int H, int C, float negative_slope, int concat, int act,
+                  const uint8_t* keep_mask, float p_drop, float* out, float* rowmax, float* rowsum, void* ws,
+                  size_t ws_bytes, gnnfd_stream_t stream)
+{
+    return gnnfd_gat_fwd_fused(g, xw, xw_dtype, a_src, a_dst, bias, H, C, negative_slope, concat, act, keep_mask, p_drop,
+                               nullptr, nullptr, nullptr, out, rowmax, rowsum, ws, ws_bytes, stream);
 }
 
 int gnnfd_gat_alpha(const gnnfd_graph_t* g, const float* a_src, const float* a_dst, const float* rowmax,

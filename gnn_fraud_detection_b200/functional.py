@@ -54,7 +54,9 @@ def project_fwd(x, W, att_src, att_dst, H, C_, xw_dtype=torch.float32, algo=_abi
 
 
 def gat_fwd(g: GraphCSR, xw, a_src, a_dst, bias, H, C_, negative_slope, concat, act=_abi.ACT_NONE, keep_mask=None,
-            p_drop=0.0):
+            p_drop=0.0, post_scale=None, post_shift=None, residual=None):
+    """Fused softmax/aggregation.  ``post_scale``/``post_shift`` [Co] (folded eval-mode BatchNorm), ``act`` and
+    ``residual`` [n_dst,Co] are applied in the row epilogue: ``act((mean+bias)*scale+shift) + residual``."""
     L = _abi.lib()
     dev = xw.device
     Co = H * C_ if concat else C_
@@ -64,10 +66,11 @@ def gat_fwd(g: GraphCSR, xw, a_src, a_dst, bias, H, C_, negative_slope, concat, 
     nb = C.c_size_t()
     _abi.check(L.gnnfd_gat_fwd_workspace_bytes(g.ref(), H, C_, C.byref(nb)))
     ws = _ws(nb.value, dev)
-    _abi.check(L.gnnfd_gat_fwd(g.ref(), xw.data_ptr(), _DT[xw.dtype], a_src.data_ptr(), a_dst.data_ptr(),
-                               _abi.ptr(bias), H, C_, float(negative_slope), int(concat), int(act),
-                               _abi.ptr(keep_mask), float(p_drop), out.data_ptr(), rowmax.data_ptr(),
-                               rowsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    _abi.check(L.gnnfd_gat_fwd_fused(g.ref(), xw.data_ptr(), _DT[xw.dtype], a_src.data_ptr(), a_dst.data_ptr(),
+                                     _abi.ptr(bias), H, C_, float(negative_slope), int(concat), int(act),
+                                     _abi.ptr(keep_mask), float(p_drop), _abi.ptr(post_scale), _abi.ptr(post_shift),
+                                     _abi.ptr(residual), out.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(),
+                                     ws.data_ptr(), ws.numel(), _stream()))
     return out, rowmax, rowsum
 
 

@@ -39,6 +39,13 @@ class _GATStack(nn.Module):
 
     def _encode(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
         h = x
+        if not self.training and not torch.is_grad_enabled():
+            # inference: BatchNorm (running stats) + ReLU + residual are fused into each layer's kernel epilogue
+            for i, conv in enumerate(self.gat_layers):
+                res = h if (self.residual and h.size(-1) == conv.out_channels) else None
+                h = conv.forward_fused_eval(h, edge_index, self.batch_norms[i] if self.use_batch_norm else None,
+                                            relu=True, residual=res)
+            return h
         for i, conv in enumerate(self.gat_layers):
             z = conv(h, edge_index)
             if self.use_batch_norm:

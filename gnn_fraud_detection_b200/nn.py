@@ -121,5 +121,32 @@ class GATConv(nn.Module):
         ei[1, perm] = dst_sorted
         return out, (ei, alpha)
 
+    @torch.no_grad()
+    def forward_fused_eval(self, x: torch.Tensor, edge_index, batch_norm: Optional[nn.BatchNorm1d] = None,
+                           relu: bool = True, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Inference-only fast path for the reference's layer loop (``src/models/gat.py:80-91``):
+        ``residual + relu(batch_norm_eval(gat(x, edge_index)))`` with the BatchNorm (running statistics folded to
+        a per-channel affine), the ReLU and the residual add fused into the aggregation kernel's row epilogue."""
+        from . import functional as Fn
+        if not x.is_cuda:
+            raise RuntimeError("gnn_fraud_detection_b200.GATConv runs on CUDA only (no CPU fallback)")
+        g = self._graph(edge_index, x.size(0))
+        H, C = self.heads, self.out_channels
+        scale = shift = None
+        if batch_norm is not None:
+            inv = torch.rsqrt(batch_norm.running_var + batch_norm.eps)
+            w = batch_norm.weight if batch_norm.weight is not None else torch.ones_like(inv)
+            b = batch_norm.bias if batch_norm.bias is not None else torch.zeros_like(inv)
+            scale = (w * inv).contiguous()
+            shift = (b - batch_norm.running_mean * w * inv).contiguous()
+        x = x if x.stride(1) == 1 else x.contiguous()
+        with torch.cuda.device(x.device):
+            xw, a_src, a_dst = Fn.project_fwd(x, self.lin_src.weight.contiguous(), self.att_src.reshape(-1),
+                                              self.att_dst.reshape(-1), H, C, self.feature_dtype, self.gemm_algo)
+            out, _, _ = Fn.gat_fwd(g, xw, a_src, a_dst, self.bias, H, C, self.negative_slope, self.concat,
+                                   _abi.ACT_RELU if relu else _abi.ACT_NONE, None, 0.0, scale, shift,
+                                   None if residual is None else residual.contiguous())
+        return out
+
     def extra_repr(self):
         return f"{self.in_channels}, {self.out_channels}, heads={self.heads}, concat={self.concat}"

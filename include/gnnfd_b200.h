@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 5
+#define GNNFD_ABI_VERSION 6
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -163,6 +163,15 @@ int gnnfd_gat_fwd(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const fl
                   const float* a_dst, const float* bias, int H, int C, float negative_slope, int concat,
                   int act, const uint8_t* keep_mask, float p_drop, float* out, float* rowmax,
                   float* rowsum, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+/* Same with the layer loop's eval-mode tail fused into the row epilogue (src/models/gat.py:80-91, tgn.py:94-105):
+ *   v = mean/concat + bias;  v = v*post_scale[c] + post_shift[c] (BatchNorm1d with running statistics, folded);
+ *   v = act(v);  v += residual[row,c].   post_scale/post_shift [Co] come together or both NULL; residual
+ *   [n_dst,Co] or NULL. */
+int gnnfd_gat_fwd_fused(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src,
+                        const float* a_dst, const float* bias, int H, int C, float negative_slope, int concat,
+                        int act, const uint8_t* keep_mask, float p_drop, const float* post_scale,
+                        const float* post_shift, const float* residual, float* out, float* rowmax,
+                        float* rowsum, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 /* alpha [E',H] in dst-sorted (CSR) order, recomputed from the saved row statistics
  * (return_attention_weights=True; un-permute through perm to get PyG order). */
 int gnnfd_gat_alpha(const gnnfd_graph_t* g, const float* a_src, const float* a_dst, const float* rowmax,

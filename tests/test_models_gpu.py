@@ -66,3 +66,29 @@ def test_tgn_snapshots_independent():
             xt, et, idx = O.temporal_subgraph_oracle(x, ei, ts, t)
             lt, ht = m(xt.cuda(), et.cuda())
             assert maxabs(lt, full[idx.cuda()]) <= 1e-5 and maxabs(ht, hid[idx.cuda()]) <= 1e-5
+
+
+def test_fused_eval_epilogue_matches_unfused_and_oracle(golden_dir):
+    """BatchNorm(eval) + ReLU + residual fused into the aggregation epilogue (the no_grad
+    inference path) must equal the un-fused layer loop and the oracle."""
+    gold = np.load(os.path.join(golden_dir, "golden_small.npz"))
+    x, ei = torch.from_numpy(gold["x"]).cuda(), torch.from_numpy(gold["edge_index"]).cuda()
+    gat = load_ckpt(GAT(x.size(1), 64, 1, num_layers=3), os.path.join(golden_dir, "gat_ckpt.npz")).cuda().eval()
+    with torch.no_grad():
+        fused = gat(x, ei)                              # fused path (eval + no_grad)
+    with torch.enable_grad():
+        unfused = gat(x, ei).detach()                   # grad enabled => plain torch BatchNorm/ReLU/residual ops
+    assert maxabs(fused, unfused) <= 1e-5
+    assert np.abs(fused.cpu().numpy() - gold["gat_logits"]).max() <= 1e-4
+    # layer-level: every epilogue option against torch ops
+    from gnn_fraud_detection_b200 import GATConv
+    torch.manual_seed(3)
+    conv = GATConv(64, 64, heads=8, concat=False).cuda().eval()
+    bn = torch.nn.BatchNorm1d(64).cuda().eval()
+    with torch.no_grad():
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0); bn.weight.normal_(); bn.bias.normal_()
+        h = torch.randn(x.size(0), 64, device="cuda")
+        ref = h + torch.relu(bn(conv(h, ei)))
+        got = conv.forward_fused_eval(h, ei, bn, relu=True, residual=h)
+        assert maxabs(got, ref) <= 1e-5
+        assert maxabs(conv.forward_fused_eval(h, ei, None, relu=False), conv(h, ei)) <= 1e-6
