@@ -93,6 +93,11 @@ __device__ __forceinline__ float4 ldg_stream(const float4* p)
                  : "l"(p));
     return r;
 }
+// software prefetch of one 128-byte line into L2 (no register, no scoreboard)
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 __device__ __forceinline__ uint4 ldg_stream_u4(const uint4* p)
 {
     uint4 r;

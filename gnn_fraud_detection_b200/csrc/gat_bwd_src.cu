@@ -120,9 +120,32 @@ gat_bwd_src_rows(const int32_t* __restrict__ colptr, const int32_t* __restrict__
     const int item = blockIdx.x * ROW_WARPS + warp;
     if (item >= items.n_items) return;
     const int j_end = items.item_start[item + 1];
+    // L2 look-ahead: the item's edges are one contiguous CSC range, so the warp prefetches the dOut rows (and the
+    // alpha/dz lines) of the edges 32-64 positions ahead of the row it is working on.  The gathers below then hit
+    // L2 instead of paying a DRAM round trip per dependent step, without holding any registers for the data.
+    constexpr int LOOK = 64;
+    const int e_item_end = colptr[j_end];
+    int pf = colptr[items.item_start[item]];
+    int pf_i = (pf + lane < e_item_end) ? csc_row[pf + lane] : -1;
     for (int64_t j = items.item_start[item]; j < j_end; ++j) {
         const int beg = colptr[j], end = colptr[j + 1];
-        if (end - beg > hub_threshold) continue;        // split rows are produced by the hub kernels
+        if (end - beg > hub_threshold) {                // split rows are produced by the hub kernels
+            if (pf < end) {
+                pf = end;
+                pf_i = (pf + lane < e_item_end) ? csc_row[pf + lane] : -1;
+            }
+            continue;
+        }
+        while (pf < e_item_end && pf < beg + LOOK) {
+            if (pf_i >= 0) {
+                const float* pr = d_out + int64_t(pf_i) * (CONCAT ? GE::D : GE::C);
+#pragma unroll
+                for (int b = 0; b < (CONCAT ? GE::D : GE::C) * 4; b += 128) prefetch_l2(reinterpret_cast<const char*>(pr) + b);
+                if (!csc_eid) prefetch_l2(alpha_used + int64_t(pf + lane) * eg_ld);
+            }
+            pf += 32;
+            pf_i = (pf + lane < e_item_end) ? csc_row[pf + lane] : -1;
+        }
         float acc[NS][4], das[H];
 #pragma unroll
         for (int q = 0; q < NS; ++q)

@@ -264,35 +264,72 @@ __global__ void __launch_bounds__(256)
 dax_partial(const float* __restrict__ x, int64_t ldx, const float* __restrict__ da_src, const float* __restrict__ da_dst,
             int64_t N, int K, int64_t rows_per_slice, float* __restrict__ Pg)
 {
-    // thread = one feature column k (x rows are read as coalesced segments across the CTA), 2H accumulators,
-    // sixteen independent row loads in flight per thread; the 64-byte da rows are CTA-wide broadcasts (L1).
-    constexpr int U = 16;
+    // thread = one feature column k (x rows are read as coalesced segments across the CTA), 2H accumulators.
+    // The [da_src | da_dst] rows of RB nodes are staged through shared memory with cp.async, one block ahead, and
+    // read back as broadcasts; the x loads of the next block are in flight while the current one is multiplied.
+    constexpr int RB = 16, V = 2 * H / 4;                 // V float4 per staged node row
+    __shared__ __align__(16) float da_s[2][RB][2 * H];
     const int64_t nb = int64_t(blockIdx.x) * rows_per_slice;
     const int64_t ne = (nb + rows_per_slice < N) ? nb + rows_per_slice : N;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const int64_t n_blk = (ne > nb) ? (ne - nb + RB - 1) / RB : 0;
+    auto stage = [&](int buf, int64_t n0) {
+        for (int i = threadIdx.x; i < RB * V; i += blockDim.x) {
+            const int r = i / V, part = i % V;
+            const int64_t n = n0 + r;
+            const float* src = (part < V / 2) ? da_src + n * H + 4 * part : da_dst + n * H + 4 * (part - V / 2);
+            const uint32_t dst = uint32_t(__cvta_generic_to_shared(&da_s[buf][r][4 * part]));
+            const int sz = (n < ne) ? 16 : 0;             // rows past the slab are zero-filled
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(n < ne ? src : da_src), "r"(sz) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int k0 = 0; k0 < K; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        const bool act = k < K;
         float acc[2 * H];
 #pragma unroll
         for (int h = 0; h < 2 * H; ++h) acc[h] = 0.f;
-        for (int64_t n = nb; n < ne; n += U) {
-            float xv[U];
+        float xv[RB], xn[RB];
+        auto load_x = [&](int64_t n0, float (&v)[RB]) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = (n + u < ne) ? __ldg(x + (n + u) * ldx + k) : 0.f;
+            for (int u = 0; u < RB; ++u) v[u] = (act && n0 + u < ne) ? __ldg(x + (n0 + u) * ldx + k) : 0.f;
+        };
+        auto fma_blk = [&](int buf, const float (&v)[RB]) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int64_t r = (n + u < ne) ? n + u : nb;     // clamped: xv is 0 there
+            for (int u = 0; u < RB; ++u) {
 #pragma unroll
-                for (int q = 0; q < H / 4; ++q) {
-                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(da_src + r * H) + q);
-                    const float4 d4 = __ldg(reinterpret_cast<const float4*>(da_dst + r * H) + q);
-                    acc[4 * q + 0] = fmaf(s4.x, xv[u], acc[4 * q + 0]); acc[4 * q + 1] = fmaf(s4.y, xv[u], acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(s4.z, xv[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(s4.w, xv[u], acc[4 * q + 3]);
-                    acc[H + 4 * q + 0] = fmaf(d4.x, xv[u], acc[H + 4 * q + 0]); acc[H + 4 * q + 1] = fmaf(d4.y, xv[u], acc[H + 4 * q + 1]);
-                    acc[H + 4 * q + 2] = fmaf(d4.z, xv[u], acc[H + 4 * q + 2]); acc[H + 4 * q + 3] = fmaf(d4.w, xv[u], acc[H + 4 * q + 3]);
+                for (int q = 0; q < V; ++q) {
+                    const float4 d4 = *reinterpret_cast<const float4*>(&da_s[buf][u][4 * q]);
+                    acc[4 * q + 0] = fmaf(d4.x, v[u], acc[4 * q + 0]); acc[4 * q + 1] = fmaf(d4.y, v[u], acc[4 * q + 1]);
+                    acc[4 * q + 2] = fmaf(d4.z, v[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(d4.w, v[u], acc[4 * q + 3]);
                 }
             }
+        };
+        if (n_blk > 0) {
+            stage(0, nb);
+            load_x(nb, xv);
         }
+        for (int64_t b = 0; b < n_blk; b += 2) {
+            // even block: data in xv / da_s[0]; odd block: xn / da_s[1]
+            stage(1, nb + (b + 1) * RB);
+            load_x(nb + (b + 1) * RB, xn);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncthreads();
+            fma_blk(0, xv);
+            __syncthreads();
+            stage(0, nb + (b + 2) * RB);
+            load_x(nb + (b + 2) * RB, xv);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncthreads();
+            fma_blk(1, xn);                                // past-the-end blocks are all zeros
+            __syncthreads();
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        if (act) {
 #pragma unroll
-        for (int h = 0; h < 2 * H; ++h) Pg[(int64_t(blockIdx.x) * 2 * H + h) * K + k] = acc[h];
+            for (int h = 0; h < 2 * H; ++h) Pg[(int64_t(blockIdx.x) * 2 * H + h) * K + k] = acc[h];
+        }
     }
 }
 // datt_src[o] = sum_k W[o,k] * G[h(o),k],  datt_dst[o] = sum_k W[o,k] * G[H + h(o),k];  one warp per o

@@ -79,6 +79,16 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
             const int64_t t = blockIdx.x + (step / n_kb) * gridDim.x;
             const int64_t m0 = (t / n_col_tiles) * BM;
             const int gk = int(step % n_kb) * BK + lane;
+            if (step % n_kb == 0 && t + gridDim.x < n_tiles) {
+                // pull the NEXT tile's rows (one contiguous block of A) into L2 while this tile is processed:
+                // the 32 scalar loads per thread below then see L2 latency instead of DRAM latency
+                const int64_t m1 = ((t + gridDim.x) / n_col_tiles) * BM;
+                const int64_t m2 = (m1 + BM < M) ? m1 + BM : M;
+                const char* pb = reinterpret_cast<const char*>(A + m1 * lda);
+                const int64_t nbytes = (m2 - m1) * lda * int64_t(sizeof(float));
+                for (int64_t off = int64_t(warp * 32 + lane) * 128; off < nbytes; off += 128 * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
+            }
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int64_t gm = m0 + warp * 32 + i;
