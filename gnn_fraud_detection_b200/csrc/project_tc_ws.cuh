@@ -19,6 +19,10 @@ constexpr uint32_t WS_A_PART = BM * 128;            // 16 KB: one part (hi or lo
 constexpr uint32_t WS_B_PART = WS_BN * 128;         // 32 KB
 constexpr uint32_t WS_STAGE = 2 * WS_A_PART + 2 * WS_B_PART;   // 96 KB
 constexpr int WS_STG_LD = 36;
+#ifndef GNNFD_WS_DIRECT_STORE
+#define GNNFD_WS_DIRECT_STORE 1
+#endif
+constexpr bool WS_DIRECT_STORE = GNNFD_WS_DIRECT_STORE != 0;
 constexpr size_t WS_SMEM = 2 * WS_STAGE + 4 * 32 * WS_STG_LD * 4 + 1024;
 
 __device__ __forceinline__ bool elect_one()
@@ -75,11 +79,13 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
         // stored, so neither the DRAM/L2 latency nor the smem stores sit on the MMA critical path
         const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
         const int64_t n_steps = my_tiles * n_kb;
+        const uint32_t lda32 = uint32_t(lda);
         auto load_step = [&](int64_t step, float (&xr)[32]) {
             const int64_t t = blockIdx.x + (step / n_kb) * gridDim.x;
             const int64_t m0 = (t / n_col_tiles) * BM;
-            const int gk = int(step % n_kb) * BK + lane;
-            if (step % n_kb == 0 && t + gridDim.x < n_tiles) {
+            const int kb = int(step % n_kb);
+            const int gk = kb * BK + lane;
+            if (kb == 0 && t + gridDim.x < n_tiles) {
                 // pull the NEXT tile's rows (one contiguous block of A) into L2 while this tile is processed:
                 // the 32 scalar loads per thread below then see L2 latency instead of DRAM latency
                 const int64_t m1 = ((t + gridDim.x) / n_col_tiles) * BM;
@@ -89,37 +95,60 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                 for (int64_t off = int64_t(warp * 32 + lane) * 128; off < nbytes; off += 128 * 128)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + off));
             }
+            // one producer warp per scheduler cannot hide instruction latency, so the interior path carries no
+            // predicates and one address instruction per element (uniform 64-bit base + 32-bit offset)
+            const float* base = A + (m0 + warp * 32) * lda;
+            if (m0 + BM <= M && (kb + 1) * BK <= Kd) {
+                uint32_t off = uint32_t(gk);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int64_t gm = m0 + warp * 32 + i;
-                xr[i] = (gm < M && gk < Kd) ? __ldg(A + gm * lda + gk) : 0.f;
+                for (int i = 0; i < 32; ++i) {
+                    xr[i] = __ldg(base + off);
+                    off += lda32;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int64_t gm = m0 + warp * 32 + i;
+                    xr[i] = (gm < M && gk < Kd) ? __ldg(base + uint32_t(i) * lda32 + uint32_t(gk)) : 0.f;
+                }
             }
         };
+        // swizzled K-major position of (row warp*32+i, k = lane): the lane-dependent part takes 8 values (i % 8)
+        const uint32_t smem_a = smem_u32(smem) + uint32_t(warp) * 4096u;
         auto store_step = [&](int64_t step, const float (&xr)[32]) {
             const int s = int(step & 1);
             const int64_t u = step >> 1;
             if (u > 0) mbar_wait(&empty[s], uint32_t((u - 1) & 1));   // MMAs that read this stage have retired
-            uint8_t* sA_hi = smem + s * WS_STAGE;
-            uint8_t* sA_lo = sA_hi + WS_A_PART;
+            const uint32_t a_hi = smem_a + uint32_t(s) * WS_STAGE;
+            uint32_t lp[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) lp[j] = a_hi + ((uint32_t((lane >> 2) ^ j)) << 4) + (uint32_t(lane & 3) << 2);
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 float h, l;
                 split_tf32(xr[i], h, l);
-                const uint32_t off = kmajor_off(warp * 32 + i, lane);
-                *reinterpret_cast<float*>(sA_hi + off) = h;
-                *reinterpret_cast<float*>(sA_lo + off) = l;
+                const uint32_t a = lp[i & 7] + uint32_t((i >> 3) * 1024 + (i & 7) * 128);   // folded into the STS immediate
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(h) : "memory");
+                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + WS_A_PART), "f"(l) : "memory");
             }
             fence_proxy_async();
             mbar_arrive(&full_a[s]);
         };
-        float xa[32], xb[32];
+        // register ring of three steps: the loads of step i+2 are issued before step i is split and stored, so an
+        // L2 (or DRAM) round trip is covered by a whole store phase plus the wait for the stage to drain
+        float xa[32], xb[32], xc[32];
         if (n_steps > 0) load_step(0, xa);
-        for (int64_t step = 0; step < n_steps; step += 2) {
-            if (step + 1 < n_steps) load_step(step + 1, xb);
+        if (n_steps > 1) load_step(1, xb);
+        for (int64_t step = 0; step < n_steps; step += 3) {
+            if (step + 2 < n_steps) load_step(step + 2, xc);
             store_step(step, xa);
             if (step + 1 < n_steps) {
-                if (step + 2 < n_steps) load_step(step + 2, xa);
+                if (step + 3 < n_steps) load_step(step + 3, xa);
                 store_step(step + 1, xb);
+            }
+            if (step + 2 < n_steps) {
+                if (step + 4 < n_steps) load_step(step + 4, xb);
+                store_step(step + 2, xc);
             }
         }
     } else if (warp == 4) {
@@ -216,6 +245,18 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                         }
                         ps = pd = 0.f;
                     }
+                }
+                if (WS_DIRECT_STORE && EPI == 1 && !OUT_BF16) {
+                    // every thread owns one full 128-byte line of its row: eight back-to-back 16-byte stores merge
+                    // in L2, and the smem round trip (a quarter of this kernel's LSU shared traffic) disappears
+                    if (row < M) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4)
+                            *reinterpret_cast<float4*>(Cf + row * ldc + col0 + c) =
+                                make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]),
+                                            __uint_as_float(v[c + 3]));
+                    }
+                    continue;
                 }
                 __syncwarp();
 #pragma unroll
