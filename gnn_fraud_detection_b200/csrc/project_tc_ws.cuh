@@ -19,10 +19,6 @@ constexpr uint32_t WS_A_PART = BM * 128;            // 16 KB: one part (hi or lo
 constexpr uint32_t WS_B_PART = WS_BN * 128;         // 32 KB
 constexpr uint32_t WS_STAGE = 2 * WS_A_PART + 2 * WS_B_PART;   // 96 KB
 constexpr int WS_STG_LD = 36;
-#ifndef GNNFD_WS_DIRECT_STORE
-#define GNNFD_WS_DIRECT_STORE 1
-#endif
-constexpr bool WS_DIRECT_STORE = GNNFD_WS_DIRECT_STORE != 0;
 constexpr size_t WS_SMEM = 2 * WS_STAGE + 4 * 32 * WS_STG_LD * 4 + 1024;
 
 __device__ __forceinline__ bool elect_one()
@@ -246,18 +242,8 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                         ps = pd = 0.f;
                     }
                 }
-                if (WS_DIRECT_STORE && EPI == 1 && !OUT_BF16) {
-                    // every thread owns one full 128-byte line of its row: eight back-to-back 16-byte stores merge
-                    // in L2, and the smem round trip (a quarter of this kernel's LSU shared traffic) disappears
-                    if (row < M) {
-#pragma unroll
-                        for (int c = 0; c < 32; c += 4)
-                            *reinterpret_cast<float4*>(Cf + row * ldc + col0 + c) =
-                                make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]),
-                                            __uint_as_float(v[c + 3]));
-                    }
-                    continue;
-                }
+                // staged through smem so that every store instruction writes four full 128-byte lines (writing each
+                // thread's own row directly was measured 40 % slower: 16-byte fragments of 32 different lines)
                 __syncwarp();
 #pragma unroll
                 for (int c = 0; c < 32; c += 4)
