@@ -392,13 +392,23 @@ def run_e2e(args, conv, x_host, ei_host, N, E_total, dev):
     steps = max(1, min(args.steps, args.e2e_steps))
     w_scale = 1.0 / N
 
+    copy_stream = torch.cuda.Stream(device=dev)
+
     def one():
         GLOBAL_CSR_CACHE.clear()
-        xd = x_host.to(dev, non_blocking=True)
+        main = torch.cuda.current_stream()
         ed = ei_host.to(dev, non_blocking=True)
+        # the feature copy (13 GB on the headline workload) rides the copy engine on its own stream while the
+        # CSR/CSC build of the freshly arrived edge list runs on the SMs; GATConv accepts the prebuilt GraphCSR
+        copy_stream.wait_stream(main)
+        with torch.cuda.stream(copy_stream):
+            xd = x_host.to(dev, non_blocking=True)
+        g = GLOBAL_CSR_CACHE.get(ed, N, True, True)
+        main.wait_stream(copy_stream)
+        xd.record_stream(main)
         for p in conv.parameters():
             p.grad = None
-        out = conv(xd, ed)
+        out = conv(xd, g)
         loss = out.sum() * w_scale
         loss.backward()
         res = [loss.detach().cpu()] + [p.grad.cpu() for p in conv.parameters()]
@@ -415,7 +425,7 @@ def run_e2e(args, conv, x_host, ei_host, N, E_total, dev):
     h2d = x_host.numel() * x_host.element_size() + ei_host.numel() * ei_host.element_size()
     d2h = sum(t.numel() * t.element_size() for t in res)
     return {"value": E_total / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
-            "ms_per_step": dt * 1e3, "includes": "H2D of x+edge_index, CSR/CSC rebuild, fwd+bwd, D2H of loss+grads"}
+            "ms_per_step": dt * 1e3, "includes": "H2D of x+edge_index (x copy overlapped with the CSR/CSC rebuild), fwd+bwd, D2H of loss+grads"}
 
 
 def main():

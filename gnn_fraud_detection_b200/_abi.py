@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgnnfd_b200.so")
+LIB_PATH = os.environ.get("GNNFD_B200_LIB") or os.path.join(_HERE, "libgnnfd_b200.so")   # override: A/B runs of two builds
 
 # enums (mirror include/gnnfd_b200.h)
 ADD_SELF_LOOPS, BUILD_CSC = 1, 2

@@ -10,12 +10,19 @@
 
 #include <atomic>
 #include <climits>
+#include <cstdlib>
 
 namespace gnnfd {
 extern std::atomic<long long> g_launches;
 int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who);
 
-constexpr int BWD_U = 4;
+#ifndef GNNFD_SRC_MINB
+#define GNNFD_SRC_MINB 4
+#endif
+#ifndef GNNFD_SRC_U
+#define GNNFD_SRC_U 4
+#endif
+constexpr int BWD_U = GNNFD_SRC_U;
 
 // ---------------------------------------------------------------------------------------------------------
 // src-major pass
@@ -105,12 +112,12 @@ __device__ __forceinline__ void src_epilogue(int64_t j, float (&acc)[GE::NS][4],
 }
 
 template <class GE, bool CONCAT>
-__global__ void __launch_bounds__(ROW_THREADS)
+__global__ void __launch_bounds__(ROW_THREADS, GNNFD_SRC_MINB)
 gat_bwd_src_rows(const int32_t* __restrict__ colptr, const int32_t* __restrict__ csc_row,
                  const int32_t* __restrict__ csc_eid, const float* __restrict__ alpha_used,
                  const float* __restrict__ dz, int64_t eg_ld, const float* __restrict__ d_out, const float* __restrict__ att_src,
                  const float* __restrict__ att_dst, const float* __restrict__ da_dst_full, gnnfd_item_plan_t items,
-                 int hub_threshold, float* __restrict__ dxw, float* __restrict__ da_src)
+                 int hub_threshold, int look, float* __restrict__ dxw, float* __restrict__ da_src)
 {
     constexpr int H = GE::H, NS = GE::NS;
     __shared__ __align__(16) float p_sh[ROW_WARPS][32 * H];
@@ -121,9 +128,9 @@ gat_bwd_src_rows(const int32_t* __restrict__ colptr, const int32_t* __restrict__
     if (item >= items.n_items) return;
     const int j_end = items.item_start[item + 1];
     // L2 look-ahead: the item's edges are one contiguous CSC range, so the warp prefetches the dOut rows (and the
-    // alpha/dz lines) of the edges 32-64 positions ahead of the row it is working on.  The gathers below then hit
-    // L2 instead of paying a DRAM round trip per dependent step, without holding any registers for the data.
-    constexpr int LOOK = 64;
+    // alpha/dz lines) of the edges up to `look` positions ahead of the row it is working on (in batches of 32).
+    // The gathers below then hit L2 instead of paying a DRAM round trip per dependent step, without holding any
+    // registers for the data.  look = 0 disables it.
     const int e_item_end = colptr[j_end];
     int pf = colptr[items.item_start[item]];
     int pf_i = (pf + lane < e_item_end) ? csc_row[pf + lane] : -1;
@@ -136,7 +143,7 @@ gat_bwd_src_rows(const int32_t* __restrict__ colptr, const int32_t* __restrict__
             }
             continue;
         }
-        while (pf < e_item_end && pf < beg + LOOK) {
+        while (pf < e_item_end && pf < beg + look) {
             if (pf_i >= 0) {
                 const float* pr = d_out + int64_t(pf_i) * (CONCAT ? GE::D : GE::C);
 #pragma unroll
@@ -240,12 +247,16 @@ static int launch_bwd_src(const gnnfd_graph_t* g, const float* alpha_used, const
     GNNFD_REQUIRE(g->items_src.n_items > 0 && g->items_src.item_start, GNNFD_ERR_ARG,
                   "gat_bwd_src: the graph has no work-item plan over colptr (gnnfd_item_plan)");
     const unsigned grid = (unsigned)((g->items_src.n_items + ROW_WARPS - 1) / ROW_WARPS);
+    static const int look = [] {
+        const char* e = getenv("GNNFD_SRC_LOOKAHEAD");     // edges of L2 look-ahead per warp (tuning knob)
+        return e ? atoi(e) : 0;      // measured on the 200M-edge graph: every distance > 0 is slower (L2 thrash)
+    }();
     if (concat)
         gat_bwd_src_rows<GE, true><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, eg_ld, d_out,
-                                                                 att_src, att_dst, da_dst_full, g->items_src, thr, dxw, da_src);
+                                                                 att_src, att_dst, da_dst_full, g->items_src, thr, look, dxw, da_src);
     else
         gat_bwd_src_rows<GE, false><<<grid, ROW_THREADS, 0, st>>>(g->colptr, g->csc_row, eid_ptr, alpha_used, dz, eg_ld, d_out,
-                                                                  att_src, att_dst, da_dst_full, g->items_src, thr, dxw, da_src);
+                                                                  att_src, att_dst, da_dst_full, g->items_src, thr, look, dxw, da_src);
     g_launches += 1;
     if (g->hub_src.n_hub > 0) {
         const gnnfd_hub_plan_t& pl = g->hub_src;

@@ -113,6 +113,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// split form: issue the load, later wait with the destination registers threaded through the wait (so the compiler
+// cannot touch them while the asynchronous load may still be writing them)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
 // ---- descriptors ------------------------------------------------------------------------------------
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout type [61,64) (2 = SWIZZLE_128B)
@@ -499,20 +525,27 @@ inline int kblocks(int64_t Kd) { return int((Kd + BK - 1) / BK); }
 
 }  // namespace gnnfd
 #include "project_tc_ws.cuh"
+#include "project_tc_ws2.cuh"
 namespace gnnfd {
 
 // ------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------
 // GNNFD_GEMM_WS=0 selects the simpler one-tile-per-CTA kernel (kept for A/B measurements)
-static bool use_ws()
+// GNNFD_GEMM_WS: 0 = simple one-tile-per-CTA kernel, 1 = persistent warp-specialised 1-SM kernel,
+// 2 = 2-SM (cta_group::2) kernel
+static int ws_mode()
 {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GNNFD_GEMM_WS");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = e ? atoi(e) : 2;
     }
-    return v == 1;
+    return v;
+}
+static bool use_ws()
+{
+    return ws_mode() >= 1;
 }
 static int g_tc_state = 0;   // 0 unknown, 1 usable, -1 not an sm_100 device
 static bool tc_device_ok()
@@ -556,6 +589,24 @@ int project_fwd_tc(const float* x, int64_t ldx, const float* W, const float* att
     const int n_kb = tc::kblocks(K), n_tiles = D / BN;
     float* img = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     tc::build_b_images<<<dim3(8, n_kb, n_tiles), 256, 0, st>>>(W, K, 1, D, (int)K, BN, n_kb, img);
+    if (ws_mode() == 2) {
+        const int64_t tiles = int64_t(n_tiles) * ((N + 2 * tc::BM - 1) / (2 * tc::BM));
+        int64_t clusters = sm_count() / 2;
+        if (tiles < clusters) clusters = tiles;
+        const unsigned grid = (unsigned)(2 * clusters);
+        if (xw_dtype == GNNFD_BF16) {
+            GNNFD_CUDA(cudaFuncSetAttribute(tc::gemm_tc_ws2<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS2_SMEM));
+            tc::gemm_tc_ws2<1, true, true><<<grid, tc::WS2_THREADS, tc::WS2_SMEM, st>>>(x, ldx, N, (int)K, img, n_kb, n_tiles, nullptr,
+                                                                                (__nv_bfloat16*)xw, D, D, att_src, att_dst, a_src, a_dst, H);
+        } else {
+            GNNFD_CUDA(cudaFuncSetAttribute(tc::gemm_tc_ws2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS2_SMEM));
+            tc::gemm_tc_ws2<1, false><<<grid, tc::WS2_THREADS, tc::WS2_SMEM, st>>>(x, ldx, N, (int)K, img, n_kb, n_tiles, (float*)xw,
+                                                                                 nullptr, D, D, att_src, att_dst, a_src, a_dst, H);
+        }
+        g_launches += 2;
+        GNNFD_LAUNCH_CHECK();
+        return GNNFD_OK;
+    }
     if (use_ws()) {
         const int64_t tiles = int64_t(n_tiles) * ((N + tc::BM - 1) / tc::BM);
         const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());

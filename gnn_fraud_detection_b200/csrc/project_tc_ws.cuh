@@ -1,19 +1,21 @@
 // Persistent, warp-specialised tcgen05 GEMM:  C[M, NT*256] = A[M, Kd] * B^T  (3xTF32, fp32 accumulate in TMEM).
 //
-// One CTA per SM, 9 warps:
+// One CTA per SM, 10 warps:
 //   warps 0-3  A producers: coalesced 128-byte row segments of x -> hi/lo split -> swizzled K-major smem stage
-//   warp  4    one lane: cp.async.bulk of the prebuilt B image of the NEXT k-block, then the tcgen05.mma's of the
-//              current one; tcgen05.commit releases the smem stage and, on a tile's last k-block, hands the TMEM
-//              accumulator to the epilogue
+//              (three-step register ring, next tile's rows prefetched into L2)
+//   warp  4    MMA issuer (one elected lane): waits only for FULL barriers, so the tcgen05.mma's of consecutive
+//              k-blocks queue back to back; tcgen05.commit releases the smem stage and, on a tile's last
+//              k-block, hands the TMEM accumulator to the epilogue
 //   warps 5-8  epilogue: tcgen05.ld of their TMEM lane quadrant, logit dot products, staged coalesced stores
-// Two smem stages (A 2x32 KB, B 2x64 KB) and two TMEM accumulators (2 x 256 columns) keep all three roles busy:
+//   warp  9    B producer: cp.async.bulk of the prebuilt weight image of each k-block as soon as its stage drains
+// Two smem stages (A 2x32 KB, B 2x64 KB) and two TMEM accumulators (2 x 256 columns) keep all roles busy:
 // the epilogue of tile t overlaps the mainloop of tile t+1, the copies of k-block k+1 overlap the MMAs of k.
 #pragma once
 
 namespace gnnfd {
 namespace tc {
 
-constexpr int WS_THREADS = 288;
+constexpr int WS_THREADS = 320;
 constexpr int WS_BN = 256;
 constexpr uint32_t WS_A_PART = BM * 128;            // 16 KB: one part (hi or lo) of an A k-block
 constexpr uint32_t WS_B_PART = WS_BN * 128;         // 32 KB
@@ -55,11 +57,11 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
 
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&full_a[s], 128);
+            mbar_init(&full_a[s], 4);                 // one arrive per producer warp
             mbar_init(&full_b[s], 1);
             mbar_init(&empty[s], 1);
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], 128);
+            mbar_init(&acc_empty[s], 4);              // one arrive per epilogue warp
         }
         fence_mbar_init();
     }
@@ -128,7 +130,8 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                 asm volatile("st.shared.f32 [%0], %1;" ::"r"(a + WS_A_PART), "f"(l) : "memory");
             }
             fence_proxy_async();
-            mbar_arrive(&full_a[s]);
+            __syncwarp();                                  // every lane's stores + proxy fence precede the arrive
+            if (lane == 0) mbar_arrive(&full_a[s]);
         };
         // register ring of three steps: the loads of step i+2 are issued before step i is split and stored, so an
         // L2 (or DRAM) round trip is covered by a whole store phase plus the wait for the stage to drain
@@ -148,30 +151,14 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
             }
         }
     } else if (warp == 4) {
-        // ---------------- B copies + MMA issue (one lane) -----------------------------------------------
+        // ---------------- MMA issue (one elected lane) ---------------------------------------------------
         {
             // the whole warp walks the loop with warp-uniform operands (descriptors live in uniform registers);
             // one elected lane issues the asynchronous instructions
             constexpr uint32_t IDESC = make_idesc(BM, WS_BN, 0, 0);
             const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
             const int64_t n_steps = my_tiles * n_kb;
-            auto issue_b = [&](int64_t step) {
-                const int64_t t = blockIdx.x + (step / n_kb) * gridDim.x;
-                const int kb = int(step % n_kb), nt = int(t % n_col_tiles);
-                const int s = int(step & 1);
-                const int64_t u = step >> 1;
-                if (u > 0) mbar_wait(&empty[s], uint32_t((u - 1) & 1));
-                uint8_t* sB = smem + s * WS_STAGE + 2 * WS_A_PART;
-                const float* img = b_img + (size_t(nt) * n_kb + kb) * 2 * (size_t(WS_BN) * BK);
-                if (elect_one()) {     // FAST needs only the hi half of the image
-                    mbar_expect_tx(&full_b[s], (FAST ? 1 : 2) * WS_B_PART);
-                    bulk_g2s(sB, img, (FAST ? 1 : 2) * WS_B_PART, &full_b[s]);
-                }
-                __syncwarp();
-            };
-            if (n_steps > 0) issue_b(0);
             for (int64_t step = 0; step < n_steps; ++step) {
-                if (step + 1 < n_steps) issue_b(step + 1);          // overlaps the MMAs issued below
                 const int64_t j = step / n_kb;                        // CTA-local tile counter
                 const int kb = int(step % n_kb);
                 const int s = int(step & 1);
@@ -205,6 +192,27 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                 __syncwarp();
             }
         }
+    } else if (warp == 9) {
+        // ---------------- B producer: cp.async.bulk of the prebuilt weight images -------------------------
+        // Its own warp, so that the MMA issuer never waits for a stage to drain: the issuer only waits for FULL
+        // barriers and keeps the tensor pipe queued across k-blocks.
+        const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        const int64_t n_steps = my_tiles * n_kb;
+        auto issue_b = [&](int64_t step) {
+            const int64_t t = blockIdx.x + (step / n_kb) * gridDim.x;
+            const int kb = int(step % n_kb), nt = int(t % n_col_tiles);
+            const int s = int(step & 1);
+            const int64_t u = step >> 1;
+            if (u > 0) mbar_wait(&empty[s], uint32_t((u - 1) & 1));
+            uint8_t* sB = smem + s * WS_STAGE + 2 * WS_A_PART;
+            const float* img = b_img + (size_t(nt) * n_kb + kb) * 2 * (size_t(WS_BN) * BK);
+            if (elect_one()) {     // FAST needs only the hi half of the image
+                mbar_expect_tx(&full_b[s], (FAST ? 1 : 2) * WS_B_PART);
+                bulk_g2s(sB, img, (FAST ? 1 : 2) * WS_B_PART, &full_b[s]);
+            }
+            __syncwarp();
+        };
+        for (int64_t step = 0; step < n_steps; ++step) issue_b(step);
     } else {
         // ---------------- epilogue (warps 5..8 -> TMEM lane quadrants 1,2,3,0) ---------------------------
         const int quad = warp & 3;
@@ -277,7 +285,8 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                 }
             }
             tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
     tc_fence_before();

@@ -356,11 +356,18 @@ class ReplicatedInputPartition(DstRangePartition):
         self.graph = self.rgraph = None
         torch.cuda.empty_cache()
 
+        copy_stream = torch.cuda.Stream(device=dev)
+
         def one():
-            xd = x_host.to(dev, non_blocking=True)
+            main = torch.cuda.current_stream()
             ed = ei_host.to(dev, non_blocking=True)
+            copy_stream.wait_stream(main)
+            with torch.cuda.stream(copy_stream):       # feature copy overlaps the index builds below
+                xd = x_host.to(dev, non_blocking=True)
             g = self.build_graph(ed)
             rg = self.build_exchange(g)
+            main.wait_stream(copy_stream)
+            xd.record_stream(main)
             out, grads = self.layer_fwd_bwd(xd, W, a_s, a_d, bias, d_out, H, C, conv.feature_dtype, args.algo, graph=g,
                                             rgraph=rg)
             return [t.cpu() for t in grads] + [out[:1].cpu()]

@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q -p no:cacheprovider -k "not headline" 2>&1 | tail -2
+GNNFD_GEMM_WS=1 timeout 600 python -m pytest tests -m gpu -x -q -p no:cacheprovider -k "tc or TC or project or gemm" 2>&1 | tail -1
+GNNFD_GEMM_WS=0 timeout 600 python -m pytest tests -m gpu -x -q -p no:cacheprovider -k "tc or TC or project or gemm" 2>&1 | tail -1
+for W in 1 2 1 2; do
+echo -n "WS=$W "; GNNFD_GEMM_WS=$W timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e 2>/dev/null | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['roofline']['layer']['frac'], d['roofline']['stages_ms'])"
+done
