@@ -359,7 +359,9 @@ gemm_tc(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const float
 // cute::UMMA::Layout_MN_SW128_32B_Atom): atoms of 4 node rows x 128 bytes (32 consecutive o / k), the 32-byte
 // chunk index XOR-ed with (node row % 4); LBO = stride between 32-element MN groups, SBO = stride between
 // 4-node groups.  One K=8 MMA consumes two consecutive node groups.
-template <int NG>   // number of 32-wide k groups of the B operand (N = KPAD <= 32*NG)
+// VEC2: x rows are 8-byte aligned (even ldx), so the B operand is read and staged as float2 pairs -- half the
+// load/store instructions on the LSU pipe, which the two co-resident CTAs share.
+template <int NG, bool VEC2>   // NG = number of 32-wide k groups of the B operand (N = KPAD <= 32*NG), even if VEC2
 __global__ void __launch_bounds__(THREADS)
 dw_tc(const float* __restrict__ dxw, int D, const float* __restrict__ x, int64_t ldx, int64_t N, int K, int kpad,
       int64_t rows_per_slab, float* __restrict__ P)
@@ -403,10 +405,21 @@ dw_tc(const float* __restrict__ dxw, int D, const float* __restrict__ x, int64_t
             const int64_t n = nb + int64_t(kb) * BK + warp * 8 + j;
             const bool ok = n < ne;
             ar[j] = ok ? __ldg(reinterpret_cast<const float4*>(dxw + n * D + m0) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (VEC2) {
+                // lane owns the feature pairs 2*lane + 64*t', t' < NG/2 (K is even: a pair is never split by K)
 #pragma unroll
-            for (int t = 0; t < NG; ++t) {
-                const int kf = lane + 32 * t;
-                br[j][t] = (ok && kf < K) ? __ldg(x + n * ldx + kf) : 0.f;
+                for (int t = 0; t < NG / 2; ++t) {
+                    const int kf = 2 * lane + 64 * t;
+                    const float2 v = (ok && kf < K) ? __ldg(reinterpret_cast<const float2*>(x + n * ldx + kf)) : make_float2(0.f, 0.f);
+                    br[j][2 * t] = v.x;
+                    br[j][2 * t + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < NG; ++t) {
+                    const int kf = lane + 32 * t;
+                    br[j][t] = (ok && kf < K) ? __ldg(x + n * ldx + kf) : 0.f;
+                }
             }
         }
     };
@@ -468,14 +481,28 @@ dw_tc(const float* __restrict__ dxw, int D, const float* __restrict__ x, int64_t
             split_tf32(ar[j].z, h.z, l.z); split_tf32(ar[j].w, h.w, l.w);
             *reinterpret_cast<float4*>(sA_hi + offA) = h;
             *reinterpret_cast<float4*>(sA_lo + offA) = l;
+            if (VEC2) {
 #pragma unroll
-            for (int t = 0; t < NG; ++t) {
-                const uint32_t offB = (kq * uint32_t(NG) + uint32_t(t)) * 512u + jr * 128u +
-                                      ((uint32_t(lane >> 3) ^ jr) << 5) + uint32_t(lane & 7) * 4u;
-                float hh, ll;
-                split_tf32(br[j][t], hh, ll);
-                *reinterpret_cast<float*>(sB_hi + offB) = hh;
-                *reinterpret_cast<float*>(sB_lo + offB) = ll;
+                for (int t = 0; t < NG / 2; ++t) {
+                    // features f = 2*lane + 64*t, f+1: 32-feature group 2t + lane/16, position fi = (2*lane) % 32
+                    const uint32_t grp = uint32_t(2 * t + (lane >> 4)), fi = uint32_t((2 * lane) & 31);
+                    const uint32_t offB = (kq * uint32_t(NG) + grp) * 512u + jr * 128u + (((fi >> 3) ^ jr) << 5) + (fi & 7u) * 4u;
+                    float2 hh, ll;
+                    split_tf32(br[j][2 * t], hh.x, ll.x);
+                    split_tf32(br[j][2 * t + 1], hh.y, ll.y);
+                    *reinterpret_cast<float2*>(sB_hi + offB) = hh;
+                    *reinterpret_cast<float2*>(sB_lo + offB) = ll;
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < NG; ++t) {
+                    const uint32_t offB = (kq * uint32_t(NG) + uint32_t(t)) * 512u + jr * 128u +
+                                          ((uint32_t(lane >> 3) ^ jr) << 5) + uint32_t(lane & 7) * 4u;
+                    float hh, ll;
+                    split_tf32(br[j][t], hh, ll);
+                    *reinterpret_cast<float*>(sB_hi + offB) = hh;
+                    *reinterpret_cast<float*>(sB_lo + offB) = ll;
+                }
             }
         }
         fence_proxy_async();
@@ -526,6 +553,7 @@ inline int kblocks(int64_t Kd) { return int((Kd + BK - 1) / BK); }
 }  // namespace gnnfd
 #include "project_tc_ws.cuh"
 #include "project_tc_ws2.cuh"
+#include "project_tc_dw2.cuh"
 namespace gnnfd {
 
 // ------------------------------------------------------------------------------------------------------
@@ -688,9 +716,30 @@ static int launch_dw(const float* dxw, const float* x, int64_t ldx, int64_t N, i
                      int64_t rps, cudaStream_t st)
 {
     const size_t smem = 2 * (16 * 1024) + 2 * (4 * NG * 1024) + 1024;
-    GNNFD_CUDA(cudaFuncSetAttribute(tc::dw_tc<NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int kpad = int((K + 15) / 16 * 16);
-    tc::dw_tc<NG><<<dim3(D / tc::BM, S), tc::THREADS, smem, st>>>(dxw, D, x, ldx, N, (int)K, kpad, rps, P);
+    const bool vec2 = (NG % 2 == 0) && (K % 2 == 0) && (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+    static const int dw_mode = [] {
+        const char* e = getenv("GNNFD_DW_TC");      // 1 = one-stage kernel (two CTAs per SM), 2 = pipelined 256-row kernel
+        return e ? atoi(e) : 2;
+    }();
+    if (dw_mode == 2 && D % 256 == 0) {
+        const size_t smem2 = tc::dw2_smem<NG>();
+        if (vec2) {
+            GNNFD_CUDA(cudaFuncSetAttribute(tc::dw_tc2<NG, (NG % 2 == 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            tc::dw_tc2<NG, (NG % 2 == 0)><<<dim3(D / 256, S), tc::DW2_THREADS, smem2, st>>>(dxw, D, x, ldx, N, (int)K, kpad, rps, P);
+        } else {
+            GNNFD_CUDA(cudaFuncSetAttribute(tc::dw_tc2<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            tc::dw_tc2<NG, false><<<dim3(D / 256, S), tc::DW2_THREADS, smem2, st>>>(dxw, D, x, ldx, N, (int)K, kpad, rps, P);
+        }
+        return GNNFD_OK;
+    }
+    if (vec2) {
+        GNNFD_CUDA(cudaFuncSetAttribute(tc::dw_tc<NG, (NG % 2 == 0)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::dw_tc<NG, (NG % 2 == 0)><<<dim3(D / tc::BM, S), tc::THREADS, smem, st>>>(dxw, D, x, ldx, N, (int)K, kpad, rps, P);
+    } else {
+        GNNFD_CUDA(cudaFuncSetAttribute(tc::dw_tc<NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc::dw_tc<NG, false><<<dim3(D / tc::BM, S), tc::THREADS, smem, st>>>(dxw, D, x, ldx, N, (int)K, kpad, rps, P);
+    }
     return GNNFD_OK;
 }
 
