@@ -259,12 +259,13 @@ __global__ void alpha_dots(const void* __restrict__ xw_, const float* __restrict
 // datt_src[h,c] = sum_n da_src[n,h] * xw[n,h,c] and xw = x W^T, so
 //   datt_src[h,c] = sum_k W[hC+c,k] * G_src[h,k],   G_src = da_src^T x   ([H,K], reduction over nodes)
 // which needs x (K*4 bytes/node) instead of xw (D*s bytes/node).  Pg[s][2H][K] are slab partials.
-template <int H>
+template <int H, int F>
 __global__ void __launch_bounds__(256)
 dax_partial(const float* __restrict__ x, int64_t ldx, const float* __restrict__ da_src, const float* __restrict__ da_dst,
             int64_t N, int K, int64_t rows_per_slice, float* __restrict__ Pg)
 {
-    // thread = one feature column k (x rows are read as coalesced segments across the CTA), 2H accumulators.
+    // thread = F consecutive feature columns (x rows are read as coalesced segments across the CTA; F = 2 reads
+    // float2 pairs and halves the shared/global load instructions per feature), F*2H accumulators.
     // The [da_src | da_dst] rows of RB nodes are staged through shared memory with cp.async, one block ahead, and
     // read back as broadcasts; the x loads of the next block are in flight while the current one is multiplied.
     constexpr int RB = 16, V = 2 * H / 4;                 // V float4 per staged node row
@@ -283,25 +284,39 @@ dax_partial(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    for (int k0 = 0; k0 < K; k0 += blockDim.x) {
-        const int k = k0 + threadIdx.x;
-        const bool act = k < K;
-        float acc[2 * H];
+    for (int k0 = 0; k0 < K; k0 += F * blockDim.x) {
+        const int k = k0 + F * threadIdx.x;
+        const bool act = k < K;                            // F = 2: K is even, so the pair is inside the row
+        float acc[F][2 * H];
 #pragma unroll
-        for (int h = 0; h < 2 * H; ++h) acc[h] = 0.f;
-        float xv[RB], xn[RB];
-        auto load_x = [&](int64_t n0, float (&v)[RB]) {
+        for (int f = 0; f < F; ++f)
 #pragma unroll
-            for (int u = 0; u < RB; ++u) v[u] = (act && n0 + u < ne) ? __ldg(x + (n0 + u) * ldx + k) : 0.f;
+            for (int h = 0; h < 2 * H; ++h) acc[f][h] = 0.f;
+        float xv[RB][F], xn[RB][F];
+        auto load_x = [&](int64_t n0, float (&v)[RB][F]) {
+#pragma unroll
+            for (int u = 0; u < RB; ++u) {
+                const bool ok = act && n0 + u < ne;
+                if (F == 2) {
+                    const float2 p = ok ? __ldg(reinterpret_cast<const float2*>(x + (n0 + u) * ldx + k)) : make_float2(0.f, 0.f);
+                    v[u][0] = p.x;
+                    v[u][F - 1] = p.y;
+                } else {
+                    v[u][0] = ok ? __ldg(x + (n0 + u) * ldx + k) : 0.f;
+                }
+            }
         };
-        auto fma_blk = [&](int buf, const float (&v)[RB]) {
+        auto fma_blk = [&](int buf, const float (&v)[RB][F]) {
 #pragma unroll
             for (int u = 0; u < RB; ++u) {
 #pragma unroll
                 for (int q = 0; q < V; ++q) {
                     const float4 d4 = *reinterpret_cast<const float4*>(&da_s[buf][u][4 * q]);
-                    acc[4 * q + 0] = fmaf(d4.x, v[u], acc[4 * q + 0]); acc[4 * q + 1] = fmaf(d4.y, v[u], acc[4 * q + 1]);
-                    acc[4 * q + 2] = fmaf(d4.z, v[u], acc[4 * q + 2]); acc[4 * q + 3] = fmaf(d4.w, v[u], acc[4 * q + 3]);
+#pragma unroll
+                    for (int f = 0; f < F; ++f) {
+                        acc[f][4 * q + 0] = fmaf(d4.x, v[u][f], acc[f][4 * q + 0]); acc[f][4 * q + 1] = fmaf(d4.y, v[u][f], acc[f][4 * q + 1]);
+                        acc[f][4 * q + 2] = fmaf(d4.z, v[u][f], acc[f][4 * q + 2]); acc[f][4 * q + 3] = fmaf(d4.w, v[u][f], acc[f][4 * q + 3]);
+                    }
                 }
             }
         };
@@ -328,7 +343,9 @@ dax_partial(const float* __restrict__ x, int64_t ldx, const float* __restrict__ 
         __syncthreads();
         if (act) {
 #pragma unroll
-            for (int h = 0; h < 2 * H; ++h) Pg[(int64_t(blockIdx.x) * 2 * H + h) * K + k] = acc[h];
+            for (int f = 0; f < F; ++f)
+#pragma unroll
+                for (int h = 0; h < 2 * H; ++h) Pg[(int64_t(blockIdx.x) * 2 * H + h) * K + k + f] = acc[f][h];
         }
     }
 }
@@ -445,9 +462,16 @@ int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* d
     if (datt_src && datt_dst) {
         if (H == 8 || H == 4) {
             // G = [da_src | da_dst]^T x over node slabs, then datt = W . G  (xw is not re-read)
-            const int bs = int(K >= 256 ? 256 : ((K + 31) / 32) * 32);
-            if (H == 8) dax_partial<8><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
-            else        dax_partial<4><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
+            const bool pair = (K % 2 == 0) && (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+            const int64_t cols = pair ? K / 2 : K;
+            const int bs = int(cols >= 256 ? 256 : ((cols + 31) / 32) * 32);
+            if (H == 8) {
+                if (pair) dax_partial<8, 2><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
+                else      dax_partial<8, 1><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
+            } else {
+                if (pair) dax_partial<4, 2><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
+                else      dax_partial<4, 1><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
+            }
             reduce_slices<<<(unsigned)((2 * H * K + 255) / 256), 256, 0, st>>>(Pg, int64_t(2) * H * K, Sg, Gm);
             datt_from_g<<<(unsigned)((D * 32 + 255) / 256), 256, 0, st>>>(W, Gm, D, (int)K, H, C, datt_src, datt_dst);
             g_launches += 3;
