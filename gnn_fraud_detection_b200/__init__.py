@@ -2,7 +2,8 @@
 
 Only the hot path lives here: the drop-in ``GATConv`` layer (``nn``), the model classes that host it
 (``models``), the CUDA-built graph structures (``graph``), the autograd glue over the C ABI
-(``functional``), multi-GPU partitioning (``partition``) and synthetic data generators (``synth``).
+(``functional``), multi-GPU partitioning (``partition``), the snapshot builder that feeds the temporal configuration
+(``snapshot``) and synthetic data generators (``synth``).
 Importing the package does not load the CUDA library; the first layer call does, and raises if it is
 missing (there is no CPU or PyTorch fallback).
 """
@@ -10,6 +11,8 @@ from . import _abi  # noqa: F401
 from .graph import GLOBAL_CSR_CACHE, CSRCache, GraphCSR, build_csr  # noqa: F401
 from .models import GAT, TemporalGNN  # noqa: F401
 from .nn import GATConv  # noqa: F401
+from .snapshot import create_temporal_subgraph, select_steps  # noqa: F401
 
-__all__ = ["GATConv", "GAT", "TemporalGNN", "GraphCSR", "build_csr", "CSRCache", "GLOBAL_CSR_CACHE"]
+__all__ = ["GATConv", "GAT", "TemporalGNN", "GraphCSR", "build_csr", "CSRCache", "GLOBAL_CSR_CACHE",
+           "create_temporal_subgraph", "select_steps"]
 __version__ = "0.1.0"

@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -51,6 +51,8 @@ SIGNATURES = {
     "gnnfd_sizeof_item_plan": (_sz, []),
     "gnnfd_item_plan": (_i, [_vp, _i64, _i64, C.c_int32, C.c_int32, _vp, _vp]),
     "gnnfd_invert_perm": (_i, [_vp, _i64, _vp, _vp]),
+    "gnnfd_subgraph_workspace_bytes": (_i, [_i64, _i64, _szp]),
+    "gnnfd_subgraph_build": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64p, _vp, _sz, _vp]),
     "gnnfd_launch_count": (_i64, []),
     "gnnfd_launch_count_reset": (None, []),
     "gnnfd_csr_workspace_bytes": (_i, [_i64, _i64, _i, _szp]),

@@ -534,6 +534,122 @@ int gnnfd_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int flags, 
     return GNNFD_OK;
 }
 
+// ---- snapshot / induced-subgraph builder (vectorised create_temporal_subgraph, src/data/dataset.py:198-240) -----
+// Two order-preserving compactions on the scan machinery above: nodes whose time step is selected (ascending id,
+// relabelled by the exclusive prefix sum of the selection flag), then edges with both endpoints selected (original
+// order, endpoints relabelled).  HBM-bound integer work: reads time_steps (8 B/node) and edge_index (16 B/edge) once
+// for the flags and once for the scatter.
+struct NodeSel {
+    const int64_t* ts;
+    const uint8_t* table;
+    int64_t n_table;
+    int* err;
+    __device__ uint32_t operator()(int64_t i) const
+    {
+        const int64_t t = ts[i];
+        if (t < 0) {
+            *err = 1;
+            return 0;
+        }
+        return (t < n_table && table[t]) ? 1u : 0u;       // steps beyond the table are simply not selected
+    }
+};
+struct NodeScatter {
+    int64_t* node_ids;
+    int64_t* relabel;      // optional int64 copy for the caller
+    int32_t* relabel32;    // workspace: 4 B/node keeps the table the edge passes gather from inside L2
+    uint8_t* sel;          // workspace: 1 B/node selection flag for the edge flag pass
+    __device__ void operator()(int64_t i, uint32_t keep, uint32_t pos) const
+    {
+        const int32_t r = keep ? int32_t(pos) : -1;
+        relabel32[i] = r;
+        sel[i] = uint8_t(keep);
+        if (relabel) relabel[i] = r;
+        if (keep) node_ids[pos] = i;
+    }
+};
+struct EdgeSel {
+    const int64_t* src;
+    const int64_t* dst;
+    const uint8_t* sel;
+    int64_t N;
+    int* err;
+    __device__ uint32_t operator()(int64_t e) const
+    {
+        const int64_t s = src[e], d = dst[e];
+        if (s < 0 || s >= N || d < 0 || d >= N) {
+            *err = 2;
+            return 0;
+        }
+        return (sel[s] & sel[d]) ? 1u : 0u;
+    }
+};
+struct EdgeScatter {
+    const int64_t* src;
+    const int64_t* dst;
+    const int32_t* relabel32;
+    int64_t* out_src;
+    int64_t* out_dst;
+    __device__ void operator()(int64_t e, uint32_t keep, uint32_t pos) const
+    {
+        if (keep) {
+            out_src[pos] = relabel32[src[e]];
+            out_dst[pos] = relabel32[dst[e]];
+        }
+    }
+};
+
+int gnnfd_subgraph_workspace_bytes(int64_t N, int64_t E, size_t* bytes)
+{
+    GNNFD_REQUIRE(bytes != nullptr && N >= 0 && E >= 0, GNNFD_ERR_ARG, "subgraph_workspace_bytes: bad args");
+    const int64_t m = N > E ? N : E;
+    *bytes = carve_bytes(8, 4) + carve_bytes(size_t((m + SC_TILE - 1) / SC_TILE + 2), 4) + carve_bytes(size_t(N), 4) +
+             carve_bytes(size_t(N), 1) + 512;
+    return GNNFD_OK;
+}
+
+int gnnfd_subgraph_build(const int64_t* time_steps, int64_t N, const uint8_t* step_selected, int64_t n_step_table,
+                         const int64_t* edge_index, int64_t E, int64_t* node_ids, int64_t* relabel,
+                         int64_t* sub_edge_index, int64_t ld_sub, int64_t* counts_host, void* ws, size_t ws_bytes,
+                         gnnfd_stream_t stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    GNNFD_REQUIRE(N >= 0 && E >= 0 && n_step_table >= 0, GNNFD_ERR_ARG, "subgraph_build: negative size");
+    GNNFD_REQUIRE(N < (int64_t(1) << 31) && E < (int64_t(1) << 31), GNNFD_ERR_RANGE, "subgraph_build: N/E do not fit 31 bits");
+    GNNFD_REQUIRE(counts_host != nullptr, GNNFD_ERR_ARG, "subgraph_build: counts_host is NULL");
+    GNNFD_REQUIRE(N == 0 || (time_steps && step_selected && node_ids), GNNFD_ERR_ARG, "subgraph_build: NULL node argument");
+    GNNFD_REQUIRE(E == 0 || (edge_index && sub_edge_index && ld_sub >= E), GNNFD_ERR_ARG,
+                  "subgraph_build: NULL edge argument or ld_sub < E");
+    size_t need = 0;
+    int rc = gnnfd_subgraph_workspace_bytes(N, E, &need);
+    if (rc) return rc;
+    GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "subgraph_build: workspace %zu < %zu", ws_bytes, need);
+    char* p = reinterpret_cast<char*>(ws);
+    uint32_t* scalars = carve<uint32_t>(p, 8);              // [0] n_sel, [1] m, [2] error flag
+    const int64_t mx = N > E ? N : E;
+    uint32_t* block_sums = carve<uint32_t>(p, size_t((mx + SC_TILE - 1) / SC_TILE + 2));
+    int32_t* relabel32 = carve<int32_t>(p, size_t(N));
+    uint8_t* sel = carve<uint8_t>(p, size_t(N));
+    GNNFD_CUDA(cudaMemsetAsync(scalars, 0, 8 * sizeof(uint32_t), st));
+    int* err = reinterpret_cast<int*>(scalars + 2);
+    NodeSel ns{time_steps, step_selected, n_step_table, err};
+    NodeScatter nsc{node_ids, relabel, relabel32, sel};
+    rc = exclusive_scan<uint32_t>(ns, nsc, N, block_sums, scalars + 0, st);
+    if (rc) return rc;
+    EdgeSel es{edge_index, edge_index + E, sel, N, err};
+    EdgeScatter esc{edge_index, edge_index + E, relabel32, sub_edge_index, sub_edge_index + ld_sub};
+    rc = exclusive_scan<uint32_t>(es, esc, E, block_sums, scalars + 1, st);
+    if (rc) return rc;
+    uint32_t host_sc[3] = {0, 0, 0};
+    GNNFD_CUDA(cudaMemcpyAsync(host_sc, scalars, sizeof(host_sc), cudaMemcpyDeviceToHost, st));
+    GNNFD_CUDA(cudaStreamSynchronize(st));
+    GNNFD_REQUIRE(host_sc[2] != 1, GNNFD_ERR_RANGE, "subgraph_build: negative time step");
+    GNNFD_REQUIRE(host_sc[2] != 2, GNNFD_ERR_RANGE, "subgraph_build: edge_index has an entry outside [0, %lld)", (long long)N);
+    counts_host[0] = host_sc[0];
+    counts_host[1] = host_sc[1];
+    return GNNFD_OK;
+}
+
 int gnnfd_hub_plan_workspace_bytes(int64_t n_rows, size_t* bytes)
 {
     GNNFD_REQUIRE(bytes != nullptr && n_rows >= 0, GNNFD_ERR_ARG, "hub_plan_workspace_bytes: bad args");

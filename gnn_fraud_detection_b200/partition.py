@@ -55,6 +55,12 @@ def snapshot_batches(x: torch.Tensor, edge_index: torch.Tensor, time_steps: torc
     n_t = torch.stack([(time_steps == t).sum() for t in steps]).tolist()
     e_t = torch.stack([(time_steps[edge_index[1]] == t).sum() for t in steps]).tolist()
     mine = lpt_assign([a + b for a, b in zip(n_t, e_t)], world)[rank]
+    if x.is_cuda:
+        # selection + relabelling + order-preserving edge compaction in libgnnfd_b200.so (gnnfd_subgraph_build)
+        from .snapshot import select_steps
+        node_ids, ei_local, _ = select_steps(time_steps, edge_index, [int(steps[i]) for i in mine])
+        return x[node_ids], ei_local, node_ids
+    # host-side planning on CPU tensors (gloo tests): same semantics with torch index ops
     own = torch.zeros(int(steps.max()) + 1, dtype=torch.bool, device=x.device)
     own[steps[torch.tensor(mine, dtype=torch.long, device=steps.device)]] = True
     nmask = own[time_steps]

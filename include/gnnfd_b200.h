@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 6
+#define GNNFD_ABI_VERSION 7
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -133,6 +133,19 @@ int gnnfd_hub_plan(const int32_t* ptr, int64_t n_rows, int32_t threshold, int32_
                    int32_t* hub_row, int32_t* hub_chunk_ptr, int32_t* chunk_hub,
                    int64_t cap_hub, int64_t cap_chunk, int64_t* counts_host,
                    void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+
+/* Snapshot / induced-subgraph builder: the vectorised form of create_temporal_subgraph
+ * (src/data/dataset.py:198-240: nodes of one time step, edges with both endpoints inside, original orders kept,
+ * endpoints relabelled 0..n_sel-1) generalised to a SET of time steps (block-diagonal batch of snapshots).
+ * A node i is selected iff time_steps[i] < n_step_table and step_selected[time_steps[i]] != 0; negative time steps
+ * and edge endpoints outside [0, N) are GNNFD_ERR_RANGE.  Outputs (device): node_ids[n_sel] ascending original ids,
+ * relabel[N] = new id or -1 (optional, may be NULL), sub_edge_index rows at [0, m) and [ld_sub, ld_sub + m) (ld_sub >= E).
+ * counts_host[0] = n_sel, counts_host[1] = m.  Synchronises `stream` once to return the counts. */
+int gnnfd_subgraph_workspace_bytes(int64_t N, int64_t E, size_t* bytes);
+int gnnfd_subgraph_build(const int64_t* time_steps, int64_t N, const uint8_t* step_selected, int64_t n_step_table,
+                         const int64_t* edge_index, int64_t E, int64_t* node_ids, int64_t* relabel,
+                         int64_t* sub_edge_index, int64_t ld_sub, int64_t* counts_host,
+                         void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 
 /* inv[perm[i]] = i for a permutation of [0,n) (used for csr2csc = inverse of csc_eid). */
 int gnnfd_invert_perm(const int32_t* perm, int64_t n, int32_t* inv, gnnfd_stream_t stream);
