@@ -16,6 +16,7 @@
 
 #include <atomic>
 #include <climits>
+#include <cstdlib>
 
 namespace gnnfd {
 extern std::atomic<long long> g_launches;
@@ -42,7 +43,7 @@ template <class GE, bool CONCAT>
 __device__ __forceinline__ void fwd_epilogue(int64_t i, const float (&m)[GE::H], const float (&s)[GE::H],
                                              float (&acc)[GE::NS][GE::VW], const EpiParams& ep,
                                              float* __restrict__ out, float* __restrict__ rowmax,
-                                             float* __restrict__ rowsum, int lane)
+                                             float* __restrict__ rowsum, int lane, bool write_stats = true)
 {
     constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP, D = GE::D, C = GE::C, G = GE::G;
     const int sub = lane / G;
@@ -52,7 +53,7 @@ __device__ __forceinline__ void fwd_epilogue(int64_t i, const float (&m)[GE::H],
         st[h] = s[h] + 1e-16f;   // PyG softmax: out / (sum + 1e-16)
         inv[h] = 1.f / st[h];
     }
-    if (lane == 0) {
+    if (lane == 0 && write_stats) {
         store_vecH<H>(rowmax + i * H, m);
         store_vecH<H>(rowsum + i * H, st);
     }
@@ -163,6 +164,14 @@ struct RowEpilogue {
                                            float (&acc)[GE::NS][GE::VW], int lane) const
     {
         fwd_epilogue<GE, CONCAT>(row, m, s, acc, ep, out, rowmax, rowsum, lane);
+    }
+    // rows of a pack: the weights were normalised in phase A (which also saved the row statistics)
+    __device__ __forceinline__ void finish_norm(int row, float (&acc)[GE::NS][GE::VW], int lane) const
+    {
+        float m[GE::H], s[GE::H];
+#pragma unroll
+        for (int h = 0; h < GE::H; ++h) { m[h] = 0.f; s[h] = 1.f; }     // 1 + 1e-16 == 1 in fp32: no rescale
+        fwd_epilogue<GE, CONCAT>(row, m, s, acc, ep, out, rowmax, rowsum, lane, /*write_stats=*/false);
     }
     __device__ __forceinline__ void empty(int row, int lane) const
     {
@@ -302,6 +311,207 @@ gat_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ co
     cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
     RowEpilogue<GE, CONCAT> sink{ep, out, rowmax, rowsum};
     fwd_stream<GE, DROPOUT>(cur, ring, sink, rowptr, col, perm, xw, a_src, a_dst, slope, keep, keep_scale, lane);
+}
+
+// ---- low-degree graphs: packs of whole rows share one phase A ---------------------------------------------------
+// lane = edge of the pack; the lane's row is found by a 5-step search over the rows' end offsets, softmax max / sum
+// are SEGMENTED warp scans over the lanes of one row, the weights are stored already normalised (so phase B needs no
+// per-row state) and the lane holding a row's last edge writes the row statistics for the backward.
+template <class GE, bool DROPOUT>
+__device__ __forceinline__ void fwd_phase_a_pack(int row0, int beg, int n, int k, int lane_a, int lane_b,
+                                                 const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                                                 const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                                                 float slope, const uint8_t* __restrict__ keep, float keep_scale,
+                                                 float* __restrict__ rowmax, float* __restrict__ rowsum, float* p_s,
+                                                 int* j_s, int* r_s, int lane)
+{
+    constexpr int H = GE::H;
+    const bool act = lane < n;
+    const int e_id = beg + lane;
+    int lo = 0, hi = k - 1;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {                    // smallest i with end_i > e_id
+        const int mid = (lo + hi) >> 1;
+        const int bm = __shfl_sync(FULL, lane_b, mid);
+        if (bm > e_id) hi = mid; else lo = min(mid + 1, k - 1);
+    }
+    const int i = lo;
+    const int sa = __shfl_sync(FULL, lane_a, i) - beg;          // first / last lane of this lane's row
+    const int sb = __shfl_sync(FULL, lane_b, i) - beg - 1;
+    const int row = row0 + i;
+    float e[H], kp[H];
+    int j = 0;
+    if (act) {
+        j = col[e_id];
+        float as[H], adst[H];
+        load_vecH<H>(a_src + int64_t(j) * H, as);
+        load_vecH<H>(a_dst + int64_t(row) * H, adst);
+#pragma unroll
+        for (int h = 0; h < H; ++h) e[h] = leaky(as[h] + adst[h], slope);
+        if (DROPOUT) {
+            const uint8_t* kb = keep + int64_t(perm[e_id]) * H;
+#pragma unroll
+            for (int h = 0; h < H; ++h) kp[h] = kb[h] ? keep_scale : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) { e[h] = -INFINITY; kp[h] = 0.f; }
+    }
+    float w[H], mrow[H], srow[H];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float mx = e[h];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(FULL, mx, o);
+            if (lane - o >= sa) mx = fmaxf(mx, t);
+        }
+        mrow[h] = __shfl_sync(FULL, mx, sb);
+        const float p = act ? expf(e[h] - mrow[h]) : 0.f;
+        float sm = p;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float t = __shfl_up_sync(FULL, sm, o);
+            if (lane - o >= sa) sm += t;
+        }
+        srow[h] = __shfl_sync(FULL, sm, sb) + 1e-16f;           // PyG softmax: out / (sum + 1e-16)
+        const float pn = p / srow[h];
+        w[h] = DROPOUT ? pn * kp[h] : pn;
+    }
+    if (act && lane == sb) {
+        store_vecH<H>(rowmax + int64_t(row) * H, mrow);
+        store_vecH<H>(rowsum + int64_t(row) * H, srow);
+    }
+    store_vecH<H>(p_s + lane * H, w);
+    j_s[lane] = j;
+    r_s[lane] = act ? (row | (lane == sb ? int(0x80000000u) : 0)) : 0;
+    __syncwarp();
+}
+
+template <class GE, bool CONCAT, bool DROPOUT>
+__device__ __forceinline__ void fwd_stream_pack(ChunkCursor& cur, WarpRing<GE, 256>& ring, const RowEpilogue<GE, CONCAT>& sink,
+                                                const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                const int32_t* __restrict__ perm,
+                                                const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+                                                const float* __restrict__ a_dst, float slope,
+                                                const uint8_t* __restrict__ keep, float keep_scale, int lane)
+{
+    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP;
+    const int sub = lane / GE::G;
+    auto on_empty = [&](int r) { sink.empty(r, lane); };
+    int* r_all = reinterpret_cast<int*>(ring.extra);            // [2][32] row id | last-edge flag per staged edge
+    ChunkStat<H> c0, c1;
+    int kind0 = 0, kind1 = 0;
+    int b0 = 0, beg, k, la, lb;
+    auto phase_a = [&](ChunkStat<H>& c, int kind, int buf) {
+        if (kind == 2)
+            fwd_phase_a_pack<GE, DROPOUT>(c.row, beg, c.n, k, la, lb, col, perm, a_src, a_dst, slope, keep, keep_scale,
+                                          sink.rowmax, sink.rowsum, ring.p_s + buf * 32 * H, ring.j_s + buf * 32,
+                                          r_all + buf * 32, lane);
+        else
+            fwd_phase_a<GE, DROPOUT>(c, beg, col, perm, a_src, a_dst, slope, keep, keep_scale, ring.p_s + buf * 32 * H,
+                                     ring.j_s + buf * 32, lane);
+    };
+    kind0 = cur.next_any(rowptr, lane, c0.row, beg, c0.n, c0.first, c0.last, k, la, lb, on_empty);
+    if (!kind0) return;
+    phase_a(c0, kind0, b0);
+    int issued0 = 0, issued1 = 0;
+    float m[H], s[H], acc[NS][VW];
+    while (true) {
+        const int* j0 = ring.j_s + b0 * 32;
+        const int* j1 = ring.j_s + (b0 ^ 1) * 32;
+        while (ring.has_room() && issued0 < c0.n) ring.issue(xw, j0[issued0++], lane);
+        kind1 = cur.next_any(rowptr, lane, c1.row, beg, c1.n, c1.first, c1.last, k, la, lb, on_empty);
+        issued1 = 0;
+        if (kind1) phase_a(c1, kind1, b0 ^ 1);
+        if (c0.first) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; }
+#pragma unroll
+            for (int q = 0; q < NS; ++q)
+#pragma unroll
+                for (int kk = 0; kk < VW; ++kk) acc[q][kk] = 0.f;
+        }
+        float fq[NS];
+        if (kind0 == 2) {
+#pragma unroll
+            for (int q = 0; q < NS; ++q) fq[q] = 1.f;
+        } else {
+            float fch[H], fold[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float mn = fmaxf(m[h], c0.cm[h]);
+                fold[h] = expf(m[h] - mn);
+                fch[h] = expf(c0.cm[h] - mn);
+                s[h] = s[h] * fold[h] + c0.cs[h] * fch[h];
+                m[h] = mn;
+            }
+            if (!c0.first) {
+#pragma unroll
+                for (int q = 0; q < NS; ++q) {
+                    const float f = pick<HP>(fold, q, sub);
+#pragma unroll
+                    for (int kk = 0; kk < VW; ++kk) acc[q][kk] *= f;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NS; ++q) fq[q] = pick<HP>(fch, q, sub);
+        }
+        const float* p0 = ring.p_s + b0 * 32 * H;
+        const int* r0 = r_all + b0 * 32;
+        for (int t = 0; t < c0.n; ++t) {
+            const uint8_t* rowp = ring.front();
+            float v[NS][VW], wq[NS];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                lds_slot(rowp, q, lane, v[q]);
+                wq[q] = p0[t * H + q * HP + sub] * fq[q];
+            }
+#pragma unroll
+            for (int q = 0; q < NS; ++q)
+#pragma unroll
+                for (int kk = 0; kk < VW; ++kk) acc[q][kk] = fmaf(wq[q], v[q][kk], acc[q][kk]);
+            ring.pop();
+            if (issued0 < c0.n) ring.issue(xw, j0[issued0++], lane);
+            else if (kind1 && issued1 < c1.n) ring.issue(xw, j1[issued1++], lane);
+            if (kind0 == 2) {
+                const int rs = r0[t];
+                if (rs < 0) {                                   // last edge of a packed row
+                    sink.finish_norm(rs & 0x7fffffff, acc, lane);
+#pragma unroll
+                    for (int q = 0; q < NS; ++q)
+#pragma unroll
+                        for (int kk = 0; kk < VW; ++kk) acc[q][kk] = 0.f;
+                }
+            }
+        }
+        if (kind0 == 1 && c0.last) sink.finish(c0.row, m, s, acc, lane);
+        if (!kind1) break;
+        c0 = c1;
+        kind0 = kind1;
+        issued0 = issued1;
+        b0 ^= 1;
+    }
+}
+
+template <class GE, bool CONCAT, bool DROPOUT>
+__global__ void __launch_bounds__(ST_THREADS, 4)
+gat_fwd_items_pack(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                   const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+                   const float* __restrict__ a_dst, EpiParams ep, gnnfd_item_plan_t items,
+                   int hub_threshold, float slope, const uint8_t* __restrict__ keep, float keep_scale,
+                   float* __restrict__ out, float* __restrict__ rowmax, float* __restrict__ rowsum)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * ST_WARPS + warp;
+    if (item >= items.n_items) return;
+    WarpRing<GE, 256> ring;
+    ring.init(smem + warp * StreamGeo<GE, 256>::WARP_BYTES, lane);
+    ChunkCursor cur;
+    cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
+    RowEpilogue<GE, CONCAT> sink{ep, out, rowmax, rowsum};
+    fwd_stream_pack<GE, CONCAT, DROPOUT>(cur, ring, sink, rowptr, col, perm, xw, a_src, a_dst, slope, keep, keep_scale, lane);
 }
 
 // one warp per (hub row, chunk): partial (m, s, unnormalised acc)
@@ -454,9 +664,27 @@ static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_sr
     if (rc) return rc;                                                                                                \
     gat_fwd_items<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, ep,         \
                                                               g->items_dst, thr, slope, keep, ks, out, rowmax, rowsum)
-    if (concat) { if (drop) { GNNFD_FWD_ITEMS(true, true); } else { GNNFD_FWD_ITEMS(true, false); } }
-    else        { if (drop) { GNNFD_FWD_ITEMS(false, true); } else { GNNFD_FWD_ITEMS(false, false); } }
+    // packs of whole short rows share one phase A (gat_fwd_items_pack): 2.2x on the Elliptic-size graph (2 edges per
+    // row), and still 11 % on the 200M-edge power-law graph, whose rows are mostly short.  GNNFD_FWD_PACK=0 disables it.
+    static const bool pack = [] {
+        const char* e = getenv("GNNFD_FWD_PACK");
+        return e ? atoi(e) != 0 : true;
+    }();
+    constexpr int SMEM_P = StreamGeo<GE, 256>::CTA_BYTES;
+#define GNNFD_FWD_ITEMS_PACK(CC, DD)                                                                                  \
+    rc = set_smem(gat_fwd_items_pack<GE, CC, DD>, SMEM_P);                                                            \
+    if (rc) return rc;                                                                                                \
+    gat_fwd_items_pack<GE, CC, DD><<<grid, ST_THREADS, SMEM_P, st>>>(g->rowptr, g->col, g->perm, xw, a_src, a_dst, ep, \
+                                                                     g->items_dst, thr, slope, keep, ks, out, rowmax, rowsum)
+    if (pack) {
+        if (concat) { if (drop) { GNNFD_FWD_ITEMS_PACK(true, true); } else { GNNFD_FWD_ITEMS_PACK(true, false); } }
+        else        { if (drop) { GNNFD_FWD_ITEMS_PACK(false, true); } else { GNNFD_FWD_ITEMS_PACK(false, false); } }
+    } else {
+        if (concat) { if (drop) { GNNFD_FWD_ITEMS(true, true); } else { GNNFD_FWD_ITEMS(true, false); } }
+        else        { if (drop) { GNNFD_FWD_ITEMS(false, true); } else { GNNFD_FWD_ITEMS(false, false); } }
+    }
 #undef GNNFD_FWD_ITEMS
+#undef GNNFD_FWD_ITEMS_PACK
     g_launches += 1;
     if (g->hub_dst.n_hub > 0) {
         const gnnfd_hub_plan_t& pl = g->hub_dst;

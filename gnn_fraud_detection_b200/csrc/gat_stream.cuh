@@ -164,6 +164,39 @@ struct ChunkCursor {
         last = beg >= end;
         return true;
     }
+    // Low-degree graphs: at a row boundary, try to hand out a PACK of k >= 2 whole consecutive rows (each with
+    // 1..32 edges, at most 32 edges in total) as one chunk, so that one phase A serves many rows.  Returns 2 for a
+    // pack (out_row = first row, out_beg = first edge, out_n = edges, pack_rows = k; every lane l < k keeps its row's
+    // edge range in lane_a/lane_b), 1 for an ordinary single-row chunk, 0 when the item is exhausted.
+    template <class OnEmpty>
+    __device__ __forceinline__ int next_any(const int32_t* __restrict__ rowptr, int lane, int& out_row, int& out_beg,
+                                            int& out_n, bool& first, bool& last, int& pack_rows, int& lane_a,
+                                            int& lane_b, OnEmpty on_empty)
+    {
+        if (beg >= end && row + 1 < row_end) {
+            const int r = row + 1;
+            const int ri = min(r + lane, row_end - 1);
+            const int a = rowptr[ri], b = rowptr[ri + 1];
+            const int a0 = __shfl_sync(0xffffffffu, a, 0);
+            const bool ok = (r + lane < row_end) && (b > a) && (b - a0 <= 32);
+            const unsigned bal = __ballot_sync(0xffffffffu, ok);
+            const int k = (bal == 0xffffffffu) ? 32 : __ffs(~bal) - 1;
+            if (k >= 2) {
+                out_row = r;
+                out_beg = a0;
+                out_n = __shfl_sync(0xffffffffu, b, k - 1) - a0;
+                pack_rows = k;
+                lane_a = a;
+                lane_b = b;
+                first = last = true;
+                row = r + k - 1;            // the cursor now sits at the end of the last packed row
+                beg = end = a0 + out_n;
+                fresh = false;
+                return 2;
+            }
+        }
+        return next(rowptr, out_row, out_beg, out_n, first, last, on_empty) ? 1 : 0;
+    }
 };
 
 }  // namespace gnnfd
