@@ -18,6 +18,7 @@
 
 #include <atomic>
 #include <climits>
+#include <cstdlib>
 
 namespace gnnfd {
 extern std::atomic<long long> g_launches;
@@ -315,6 +316,297 @@ gat_bwd_dst_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                                                keep, keep_scale, alpha_used, dz, eg_ld, da_dst, nullptr, 0, lane);
 }
 
+// ---- packs of whole short rows (see ChunkCursor::next_any and the forward's gat_fwd_items_pack) ------------------
+// phase A needs no scans here (the row statistics are saved), but each lane works with the statistics of ITS row;
+// phase B switches the dO slice at the row boundaries inside the pack (the next row's slice is loaded one row
+// ahead, and the pack's dO rows -- contiguous in memory -- are pulled into L2 during phase A); phase C finishes
+// every row of the pack in registers with SEGMENTED warp sums.
+// bits layout per staged edge: [0,8) LeakyReLU-positive, [8,16) dropout keep, [16,21) first lane of the row,
+// [21,26) last lane of the row, bit 26 = this edge is the last of its row.
+template <class GE, bool CONCAT, bool DROPOUT>
+__device__ __forceinline__ void bwd_phase_a_pack(int row0, int beg, int n, int k, int lane_a, int lane_b,
+                                                 const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                                                 const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                                                 const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                                                 const float* __restrict__ d_out, float slope,
+                                                 const uint8_t* __restrict__ keep, float* p_s, int* j_s, int* bits_s, int lane)
+{
+    constexpr int H = GE::H;
+    const bool act = lane < n;
+    const int e_id = beg + lane;
+    int lo = 0, hi = k - 1;
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+        const int mid = (lo + hi) >> 1;
+        const int bm = __shfl_sync(FULL, lane_b, mid);
+        if (bm > e_id) hi = mid; else lo = min(mid + 1, k - 1);
+    }
+    const int sa = __shfl_sync(FULL, lane_a, lo) - beg;
+    const int sb = __shfl_sync(FULL, lane_b, lo) - beg - 1;
+    if (!CONCAT) {
+        // the pack's dO rows are one contiguous block of k*C floats
+        const char* pb = reinterpret_cast<const char*>(d_out + int64_t(row0) * GE::C);
+        const int nbytes = k * GE::C * 4;
+        for (int off = lane * 128; off < nbytes; off += 32 * 128) prefetch_l2(pb + off);
+    }
+    float alpha[H];
+    int j = 0, bits = 0;
+    if (act) {
+        const int64_t row = row0 + lo;
+        RowStat<H> r;
+        load_row_stat<H>(r, row, a_dst, rowmax, rowsum);
+        j = col[e_id];
+        float as[H];
+        load_vecH<H>(a_src + int64_t(j) * H, as);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float z = as[h] + r.adst[h];
+            const bool pos = z > 0.f;
+            bits |= int(pos) << h;
+            alpha[h] = expf((pos ? z : z * slope) - r.m[h]) * r.inv[h];
+        }
+        if (DROPOUT) {
+            const uint8_t* kb = keep + int64_t(perm[e_id]) * H;
+#pragma unroll
+            for (int h = 0; h < H; ++h) bits |= int(kb[h] != 0) << (8 + h);
+        } else {
+            bits |= 0xff00;
+        }
+        bits |= (sa << 16) | (sb << 21) | (int(lane == sb) << 26);
+    } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) alpha[h] = 0.f;
+    }
+    store_vecH<H>(p_s + lane * H, alpha);
+    j_s[lane] = j;
+    bits_s[lane] = bits;
+    __syncwarp();
+}
+
+// inclusive sum over the lanes [sa, lane] of the lane's segment; the row total sits in lane sb afterwards
+__device__ __forceinline__ float seg_total(float v, int sa, int sb, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(FULL, v, o);
+        if (lane - o >= sa) v += t;
+    }
+    return __shfl_sync(FULL, v, sb);
+}
+
+template <class GE, bool CONCAT, bool DROPOUT>
+__device__ __forceinline__ void bwd_dst_stream_pack(ChunkCursor& cur, WarpRing<GE, bwd_extra<GE>()>& ring,
+                                                    const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+                                                    const int32_t* __restrict__ perm, const int32_t* __restrict__ csr2csc,
+                                                    const typename GE::XT* __restrict__ xw,
+                                                    const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                                                    const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                                                    const float* __restrict__ d_out, float slope,
+                                                    const uint8_t* __restrict__ keep, float keep_scale,
+                                                    float* __restrict__ alpha_used, float* __restrict__ dz, int64_t eg_ld,
+                                                    float* __restrict__ da_dst, int lane)
+{
+    constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP, G = GE::G;
+    const int sub = lane / G;
+    float* dal_s = reinterpret_cast<float*>(ring.extra);
+    int* bits_s = reinterpret_cast<int*>(ring.extra + 32 * H * 4);
+    auto on_empty = [&](int r) {
+        if (lane < H) da_dst[int64_t(r) * H + lane] = 0.f;
+    };
+    BwdChunk c0, c1;
+    int kind0 = 0, kind1 = 0, k0 = 0, k1 = 0, la = 0, lb = 0;
+    int b0 = 0;
+    auto phase_a = [&](const BwdChunk& c, int kind, int kk, int buf) {
+        if (kind == 2)
+            bwd_phase_a_pack<GE, CONCAT, DROPOUT>(c.row, c.beg, c.n, kk, la, lb, col, perm, a_src, a_dst, rowmax, rowsum, d_out,
+                                                  slope, keep, ring.p_s + buf * 32 * H, ring.j_s + buf * 32, bits_s + buf * 32, lane);
+        else
+            bwd_phase_a<GE, DROPOUT>(c, col, perm, a_src, a_dst, rowmax, rowsum, slope, keep, ring.p_s + buf * 32 * H,
+                                     ring.j_s + buf * 32, bits_s + buf * 32, lane);
+    };
+    kind0 = cur.next_any(rowptr, lane, c0.row, c0.beg, c0.n, c0.first, c0.last, k0, la, lb, on_empty);
+    if (!kind0) return;
+    phase_a(c0, kind0, k0, b0);
+    float g0[NS][VW], g1[NS][VW];
+    load_g<GE, CONCAT>(g0, c0.row, d_out, lane);
+    int issued0 = 0, issued1 = 0;
+    float trow[H];
+    int row_beg = c0.beg;
+#pragma unroll
+    for (int h = 0; h < H; ++h) trow[h] = 0.f;
+    while (true) {
+        const int* j0 = ring.j_s + b0 * 32;
+        const int* j1 = ring.j_s + (b0 ^ 1) * 32;
+        while (ring.has_room() && issued0 < c0.n) ring.issue(xw, j0[issued0++], lane);
+        kind1 = cur.next_any(rowptr, lane, c1.row, c1.beg, c1.n, c1.first, c1.last, k1, la, lb, on_empty);
+        issued1 = 0;
+        if (kind1) phase_a(c1, kind1, k1, b0 ^ 1);
+        // g1 = dO slice of the NEXT row in stream order: the second row of this pack, else the next chunk's row
+        if (kind0 == 2) load_g<GE, CONCAT>(g1, c0.row + 1, d_out, lane);
+        else if (kind1 && c1.first) load_g<GE, CONCAT>(g1, c1.row, d_out, lane);
+        if (c0.first) {
+            row_beg = c0.beg;
+#pragma unroll
+            for (int h = 0; h < H; ++h) trow[h] = 0.f;
+        }
+        int rows_done = 0;
+        const int* bits0 = bits_s + b0 * 32;
+        for (int t = 0; t < c0.n; ++t) {
+            const uint8_t* row = ring.front();
+            float v[NS][VW];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) lds_slot(row, q, lane, v[q]);
+            float d[NS];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                d[q] = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < VW; ++kk) d[q] = fmaf(g0[q][kk], v[q][kk], d[q]);
+            }
+            if constexpr (NS == 4 && G == 16) {
+                const bool b3 = lane & 8, b2 = lane & 4;
+                const float kk0 = b3 ? d[2] : d[0], kk1 = b3 ? d[3] : d[1];
+                const float s0 = b3 ? d[0] : d[2], s1 = b3 ? d[1] : d[3];
+                const float a0 = kk0 + __shfl_xor_sync(FULL, s0, 8), a1 = kk1 + __shfl_xor_sync(FULL, s1, 8);
+                float b = (b2 ? a1 : a0) + __shfl_xor_sync(FULL, b2 ? a0 : a1, 4);
+                b += __shfl_xor_sync(FULL, b, 2);
+                b += __shfl_xor_sync(FULL, b, 1);
+                if ((lane & 3) == 0) dal_s[t * H + ((lane >> 2) & 3) * HP + sub] = b;
+            } else {
+#pragma unroll
+                for (int q = 0; q < NS; ++q) {
+                    float dq = d[q];
+#pragma unroll
+                    for (int o = G / 2; o > 0; o >>= 1) dq += __shfl_xor_sync(FULL, dq, o);
+                    if ((lane & (G - 1)) == 0) dal_s[t * H + q * HP + sub] = dq;
+                }
+            }
+            ring.pop();
+            if (issued0 < c0.n) ring.issue(xw, j0[issued0++], lane);
+            else if (kind1 && issued1 < c1.n) ring.issue(xw, j1[issued1++], lane);
+            if (kind0 == 2 && t + 1 < c0.n && ((bits0[t] >> 26) & 1)) {
+                // row boundary inside the pack: switch to the next row's dO slice, fetch the one after it
+#pragma unroll
+                for (int q = 0; q < NS; ++q)
+#pragma unroll
+                    for (int kk = 0; kk < VW; ++kk) g0[q][kk] = g1[q][kk];
+                ++rows_done;
+                if (rows_done + 1 < k0) load_g<GE, CONCAT>(g1, c0.row + rows_done + 1, d_out, lane);
+                else if (kind1 && c1.first) load_g<GE, CONCAT>(g1, c1.row, d_out, lane);
+            }
+        }
+        __syncwarp();
+        {
+            float alpha[H], dal[H], u[H], au[H];
+            const float* p0 = ring.p_s + b0 * 32 * H;
+            const int bits = bits0[lane];
+#pragma unroll
+            for (int kk = 0; kk < H / 4; ++kk) {
+                const float4 a4 = *reinterpret_cast<const float4*>(p0 + lane * H + 4 * kk);
+                const float4 d4 = *reinterpret_cast<const float4*>(dal_s + lane * H + 4 * kk);
+                alpha[4 * kk] = a4.x; alpha[4 * kk + 1] = a4.y; alpha[4 * kk + 2] = a4.z; alpha[4 * kk + 3] = a4.w;
+                dal[4 * kk] = d4.x; dal[4 * kk + 1] = d4.y; dal[4 * kk + 2] = d4.z; dal[4 * kk + 3] = d4.w;
+            }
+            const bool live = lane < c0.n;
+            const int64_t pos = live ? csr2csc[c0.beg + lane] : 0;
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float ks = (bits >> (8 + h)) & 1 ? keep_scale : 0.f;
+                u[h] = live ? alpha[h] * dal[h] * ks : 0.f;
+                au[h] = alpha[h] * ks;
+            }
+            if (kind0 == 2) {
+                const int sa = (bits >> 16) & 31, sb = live ? (bits >> 21) & 31 : lane;
+                const bool lastf = live && ((bits >> 26) & 1);
+                float o[H], dad[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float tt = seg_total(u[h], sa, sb, lane);
+                    const float sl = (bits >> h) & 1 ? 1.f : slope;
+                    o[h] = live ? sl * (u[h] - alpha[h] * tt) : 0.f;
+                    dad[h] = seg_total(o[h], sa, sb, lane);
+                }
+                if (live) {
+                    store_vecH<H>(alpha_used + pos * eg_ld, au);
+                    store_vecH<H>(dz + pos * eg_ld, o);
+                }
+                const unsigned lastm = __ballot_sync(FULL, lastf);
+                if (lastf) {
+                    const int64_t r = c0.row + __popc(lastm & ((1u << lane) - 1u));
+                    store_vecH<H>(da_dst + r * H, dad);
+                }
+            } else if (c0.first && c0.last) {
+                float o[H], dad[H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float tt = warp_sum(u[h]);
+                    const float sl = (bits >> h) & 1 ? 1.f : slope;
+                    o[h] = live ? sl * (u[h] - alpha[h] * tt) : 0.f;
+                    dad[h] = warp_sum(o[h]);
+                }
+                if (live) {
+                    store_vecH<H>(alpha_used + pos * eg_ld, au);
+                    store_vecH<H>(dz + pos * eg_ld, o);
+                }
+                if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
+            } else {
+                if (live) {
+                    store_vecH<H>(alpha_used + pos * eg_ld, au);
+                    store_vecH<H>(dz + pos * eg_ld, u);
+                }
+#pragma unroll
+                for (int h = 0; h < H; ++h) trow[h] += warp_sum(u[h]);
+                if (c0.last) {
+                    __syncwarp();
+                    RowStat<H> r;
+                    load_row_stat<H>(r, c0.row, a_dst, rowmax, rowsum);
+                    float dad[H];
+#pragma unroll
+                    for (int h = 0; h < H; ++h) dad[h] = 0.f;
+                    dst_sweep2<GE>(r, row_beg, c0.beg + c0.n, col, csr2csc, a_src, slope, trow, lane, dz, eg_ld, dad);
+#pragma unroll
+                    for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
+                    if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
+                }
+            }
+        }
+        __syncwarp();
+        if (!kind1) break;
+        if (c1.first) {
+#pragma unroll
+            for (int q = 0; q < NS; ++q)
+#pragma unroll
+                for (int kk = 0; kk < VW; ++kk) g0[q][kk] = g1[q][kk];
+        }
+        c0 = c1;
+        kind0 = kind1;
+        k0 = k1;
+        issued0 = issued1;
+        b0 ^= 1;
+    }
+}
+
+template <class GE, bool CONCAT, bool DROPOUT>
+__global__ void __launch_bounds__(ST_THREADS, 4)
+gat_bwd_dst_items_pack(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
+                       const int32_t* __restrict__ csr2csc, const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
+                       const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                       const float* __restrict__ d_out, gnnfd_item_plan_t items, int hub_threshold, float slope,
+                       const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
+                       float* __restrict__ dz, int64_t eg_ld, float* __restrict__ da_dst)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * ST_WARPS + warp;
+    if (item >= items.n_items) return;
+    WarpRing<GE, bwd_extra<GE>()> ring;
+    ring.init(smem + warp * StreamGeo<GE, bwd_extra<GE>()>::WARP_BYTES, lane);
+    ChunkCursor cur;
+    cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
+    bwd_dst_stream_pack<GE, CONCAT, DROPOUT>(cur, ring, rowptr, col, perm, csr2csc, xw, a_src, a_dst, rowmax, rowsum, d_out, slope,
+                                             keep, keep_scale, alpha_used, dz, eg_ld, da_dst, lane);
+}
+
 // hub rows, step 1: one warp per chunk -- first sweep, partial t
 template <class GE, bool CONCAT, bool DROPOUT>
 __global__ void __launch_bounds__(ST_THREADS, 4)
@@ -427,9 +719,25 @@ static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* 
     gat_bwd_dst_items<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, xw, a_src, a_dst, rowmax,  \
                                                                   rowsum, d_out, g->items_dst, thr, slope, keep, ks,    \
                                                                   alpha_used, dz, eg_ld, da_dst)
-    if (concat) { if (drop) { GNNFD_BWD_ITEMS(true, true); } else { GNNFD_BWD_ITEMS(true, false); } }
-    else        { if (drop) { GNNFD_BWD_ITEMS(false, true); } else { GNNFD_BWD_ITEMS(false, false); } }
+    static const bool pack = [] {
+        const char* e = getenv("GNNFD_BWD_PACK");           // packs of whole short rows (gat_bwd_dst_items_pack); 0 disables
+        return e ? atoi(e) != 0 : true;
+    }();
+#define GNNFD_BWD_ITEMS_PACK(CC, DD)                                                                                   \
+    rc = set_smem_bwd(gat_bwd_dst_items_pack<GE, CC, DD>, SMEM);                                                       \
+    if (rc) return rc;                                                                                                 \
+    gat_bwd_dst_items_pack<GE, CC, DD><<<grid, ST_THREADS, SMEM, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, xw, a_src, a_dst,    \
+                                                                       rowmax, rowsum, d_out, g->items_dst, thr, slope, keep, \
+                                                                       ks, alpha_used, dz, eg_ld, da_dst)
+    if (pack) {
+        if (concat) { if (drop) { GNNFD_BWD_ITEMS_PACK(true, true); } else { GNNFD_BWD_ITEMS_PACK(true, false); } }
+        else        { if (drop) { GNNFD_BWD_ITEMS_PACK(false, true); } else { GNNFD_BWD_ITEMS_PACK(false, false); } }
+    } else {
+        if (concat) { if (drop) { GNNFD_BWD_ITEMS(true, true); } else { GNNFD_BWD_ITEMS(true, false); } }
+        else        { if (drop) { GNNFD_BWD_ITEMS(false, true); } else { GNNFD_BWD_ITEMS(false, false); } }
+    }
 #undef GNNFD_BWD_ITEMS
+#undef GNNFD_BWD_ITEMS_PACK
     g_launches += 1;
     if (g->hub_dst.n_hub > 0) {
         const gnnfd_hub_plan_t& pl = g->hub_dst;
