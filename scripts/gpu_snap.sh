@@ -1,5 +1,5 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_snapshot_gpu.py tests/test_models_gpu.py -x -q -p no:cacheprovider 2>&1 | tail -12
+timeout 240 python -m pytest tests/test_snapshot_gpu.py tests/test_models_gpu.py -x -q -p no:cacheprovider 2>&1 | tail -12
 timeout 300 python - <<'PY'
 import torch, time
 from gnn_fraud_detection_b200 import select_steps, synth
