@@ -313,7 +313,7 @@ def run_gpu_arm(args):
     dom_bytes = local["gat_fwd"]
     dom_ms = stage_ms["gat_fwd"]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "gat_fwd_rows (+hub chunks/merge)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roof = {"bound": "hbm", "kernel": "gat_fwd_items_pack (+hub chunks/merge)", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
             "layer": {"algorithmic_bytes": bmodel["total"], "achieved": bmodel["total"] / (ms_per_step * 1e-3) / 1e9 / world,
