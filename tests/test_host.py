@@ -95,3 +95,24 @@ def test_skew_and_powerlaw_generators():
     pl = synth.powerlaw_graph(num_nodes=50000, num_edges=500000, seed=1)
     assert pl.shape == (2, 500000) and int(pl.max()) < 50000 and int(pl.min()) >= 0
     assert int(torch.bincount(pl[1], minlength=50000).max()) > 5000      # ~ E / N^(1/3)
+
+
+def test_snapshot_builder_has_no_cpu_fallback_and_validates_arguments():
+    """create_temporal_subgraph / select_steps (src/data/dataset.py:198-240 mirror) run in the CUDA library only."""
+    from types import SimpleNamespace
+
+    from gnn_fraud_detection_b200 import create_temporal_subgraph, select_steps
+    ts = torch.tensor([1, 1, 2])
+    ei = torch.tensor([[0, 2], [1, 2]])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        select_steps(ts, ei, [1])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        create_temporal_subgraph(SimpleNamespace(x=torch.zeros(3, 2), edge_index=ei, time_steps=ts, y=None), 1)
+    # the multi-GPU dealer keeps a torch-ops path for CPU tensors (host-side planning, gloo tests): same semantics
+    from gnn_fraud_detection_b200.partition import snapshot_batches
+    from oracle import pyg_gatconv as O
+    x = torch.arange(6.0).view(3, 2)
+    xl, el, ids = snapshot_batches(x, ei, ts, 0, 1)
+    assert torch.equal(ids, torch.tensor([0, 1, 2])) and torch.equal(el, ei) and torch.equal(xl, x)
+    xo, eo, ido = O.temporal_subgraph_oracle(x, ei, ts, 1)
+    assert ido.tolist() == [0, 1] and eo.tolist() == [[0], [1]]
