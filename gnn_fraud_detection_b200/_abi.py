@@ -16,9 +16,9 @@ LIB_PATH = os.environ.get("GNNFD_B200_LIB") or os.path.join(_HERE, "libgnnfd_b20
 ADD_SELF_LOOPS, BUILD_CSC = 1, 2
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
-GEMM_AUTO, GEMM_SIMT, GEMM_TC = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_INPUT = 0, 1, 2, 3
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -73,6 +73,22 @@ SIGNATURES = {
     "gnnfd_project_bwd_workspace_bytes": (_i, [_i64, _i64, _i, _i, _i, _szp]),
     "gnnfd_project_bwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp,
                                _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
+    # input-space formulation of the first layer
+    "gnnfd_in_supported": (_i, [_i64, _i, _i, _i]),
+    "gnnfd_in_sizes": (_i, [_i64, _i64, _szp, _szp, _i64p]),
+    "gnnfd_in_logits": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gnnfd_in_prepare": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "gnnfd_in_fwd_workspace_bytes": (_i, [_gp, _szp]),
+    "gnnfd_in_fwd": (_i, [_gp, _vp, _i64, _i64, _vp, _vp, _f, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gnnfd_in_out": (_i, [_vp, _i64, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gnnfd_in_bwd_gd": (_i, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "gnnfd_in_bwd_edges_workspace_bytes": (_i, [_gp, _szp]),
+    "gnnfd_in_bwd_edges": (_i, [_gp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f, _vp, _f,
+                                _vp, _vp, _vp, _sz, _i, _vp]),
+    "gnnfd_in_bwd_dasrc": (_i, [_gp, _vp, _vp, _vp]),
+    "gnnfd_in_bwd_params_workspace_bytes": (_i, [_i64, _i64, _szp]),
+    "gnnfd_in_bwd_params": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                 _vp]),
 }
 
 

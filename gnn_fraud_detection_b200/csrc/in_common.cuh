@@ -32,7 +32,7 @@ constexpr int TILE = 128;                // rows (nodes) per image tile
 constexpr int PLANE = TILE * 128;        // 16 KB: one fp16 plane of one k-block (64 features) of one tile
 constexpr int KBLOCK = 2 * PLANE;        // hi plane then lo plane
 
-struct GI { static constexpr int H = in::H; };   // what the shared phase-A code needs
+struct GI { static constexpr int H = in::H, C = in::C; };   // what the shared phase-A code needs
 
 struct Dims {
     int K, KP, F, NKB;
@@ -93,6 +93,100 @@ __host__ __device__ inline size_t prep_off_u(const Dims& d) { return prep_off_wg
 __host__ __device__ inline size_t prep_bytes(const Dims& d) { return prep_off_u(d) + ((prep_u_bytes(d) + 1023) & ~size_t(1023)) + 1024; }
 
 inline size_t zimg_bytes(int64_t n_rows, const Dims& d) { return size_t((n_rows + TILE - 1) / TILE) * d.NKB * KBLOCK; }
+
+}  // namespace in
+}  // namespace gnnfd
+
+namespace gnnfd {
+namespace in {
+
+// ---- per-warp ring of staged x rows ------------------------------------------------------------------------------
+// Row j starts at x + j*ldx, which is only 4- or 8-byte aligned (K = 166: 664-byte stride).  cp.async.bulk needs
+// 16-byte aligned source and size, so lane 0 fetches the enclosing 16-byte aligned span into the slot and the consumer
+// adds (address & 15).  Sizes are run-time (they depend on K); per-warp layout:
+//   [R slots][p_s: 2 x 32 x H floats][j_s: 2 x 32 ints][R+1 mbarriers][extra]
+constexpr int IN_WARPS = 4;
+constexpr int IN_THREADS = IN_WARPS * 32;
+constexpr int IN_R = 10;                                   // ring slots per warp
+constexpr int IN_P_BYTES = 2 * 32 * H * 4, IN_J_BYTES = 2 * 32 * 4, IN_BAR_BYTES = ((IN_R + 1) * 8 + 15) / 16 * 16;
+
+__host__ __device__ inline int in_slot_bytes(int K) { return (K * 4 + 12 + 15) / 16 * 16; }
+__host__ __device__ inline int in_warp_bytes(int K, int extra)
+{
+    return (IN_R * in_slot_bytes(K) + IN_P_BYTES + IN_J_BYTES + IN_BAR_BYTES + extra + 127) / 128 * 128;
+}
+
+struct InRing {
+    uint8_t* ring;
+    uint8_t* extra;
+    float* p_s;      // [2][32*H]
+    int* j_s;        // [2][32]
+    uint64_t* full;  // [IN_R] + one spare barrier (index IN_R) for kernel-specific use
+    int slot, issued = 0, consumed = 0;
+    uint64_t xaddr;
+    uint32_t ldxb, rowb;
+
+    __device__ __forceinline__ void init(uint8_t* base, const float* x, int64_t ldx, int K, int lane)
+    {
+        slot = in_slot_bytes(K);
+        ring = base;
+        p_s = reinterpret_cast<float*>(base + IN_R * slot);
+        j_s = reinterpret_cast<int*>(base + IN_R * slot + IN_P_BYTES);
+        full = reinterpret_cast<uint64_t*>(base + IN_R * slot + IN_P_BYTES + IN_J_BYTES);
+        extra = base + IN_R * slot + IN_P_BYTES + IN_J_BYTES + IN_BAR_BYTES;
+        xaddr = reinterpret_cast<uint64_t>(x);
+        ldxb = uint32_t(ldx) * 4u;
+        rowb = uint32_t(K) * 4u;
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i <= IN_R; ++i) st_mbar_init(&full[i], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ bool has_room() const { return issued - consumed < IN_R; }
+    __device__ __forceinline__ void issue(int j, int lane)
+    {
+        if (lane == 0) {
+            const int s = issued % IN_R;
+            const uint64_t a = xaddr + uint64_t(uint32_t(j)) * ldxb;
+            const uint64_t a0 = a & ~uint64_t(15);
+            const uint32_t bytes = uint32_t(((a + rowb + 15) & ~uint64_t(15)) - a0);
+            st_mbar_expect_tx(&full[s], bytes);
+            st_bulk_g2s(ring + s * slot, reinterpret_cast<const void*>(a0), bytes, &full[s]);
+        }
+        ++issued;
+    }
+    // wait for the oldest in-flight row (source id j); returns the address of its first element
+    __device__ __forceinline__ const float* front(int j)
+    {
+        const int s = consumed % IN_R;
+        st_mbar_wait(&full[s], (consumed / IN_R) & 1);
+        const uint32_t off = uint32_t(xaddr + uint64_t(uint32_t(j)) * ldxb) & 15u;
+        return reinterpret_cast<const float*>(ring + s * slot + off);
+    }
+    __device__ __forceinline__ void pop()
+    {
+        __syncwarp();
+        ++consumed;
+    }
+};
+
+// the features of one staged row owned by this lane: pairs (64r + 2*lane, +1), zero beyond K
+template <bool VEC2>
+__device__ __forceinline__ void load_xrow(const float* __restrict__ row, int lane, int K, float2 (&v)[NSLOT])
+{
+#pragma unroll
+    for (int r = 0; r < NSLOT; ++r) {
+        const int f = 64 * r + 2 * lane;
+        if (VEC2) {   // K even, rows 8-byte aligned: a pair is inside the row or outside
+            v[r] = (f < K) ? *reinterpret_cast<const float2*>(row + f) : make_float2(0.f, 0.f);
+        } else {
+            v[r].x = (f < K) ? row[f] : 0.f;
+            v[r].y = (f + 1 < K) ? row[f + 1] : 0.f;
+        }
+    }
+}
 
 }  // namespace in
 }  // namespace gnnfd

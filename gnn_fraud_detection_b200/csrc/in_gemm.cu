@@ -1,0 +1,615 @@
+// Dense stages of the input-space GAT layer (in_common.cuh) on the 5th-gen tensor cores, fed by the bulk-copy engine.
+//
+//   in_out_gemm   out[n, C]  = epi( Z[n, F] @ W_r[F, C] )         K-major A = the fp16-pair image written by gnnfd_in_fwd
+//   in_dw_gemm    dWr[F, C]  = Z[n, F]^T @ dO[n, C]               MN-major A = the SAME image, reduction over nodes
+//
+// Both read Z as ready-made 128B-swizzled shared-memory tiles: one cp.async.bulk per k-block (32 KB: fp16 hi plane +
+// fp16 lo plane), completion on an mbarrier, no operand-staging warps.  Error-compensated fp16 arithmetic:
+// v*s = hi + lo with s a power of two chosen so that max|v|*s is in [2^11, 2^12); the three products hi*hi, hi*lo,
+// lo*hi are accumulated in fp32 in TMEM (kind::f16), which carries 22 mantissa bits per operand -- the same accuracy
+// class as the 3xTF32 projection (project_tc.cu) at half the operand bytes.  One elected thread issues the MMAs;
+// tcgen05.commit releases smem stages / hands accumulators to the epilogue warps.
+//
+// Replaces, for the reference's first layer (src/models/gat.py:39,80), the dense part of GATConv.forward
+// (lin_src + head mean + bias) and of its autograd mirror (dW), cf. gnnfd_project_fwd / gnnfd_project_bwd.
+#include "in_common.cuh"
+
+#include <atomic>
+
+namespace gnnfd {
+extern std::atomic<long long> g_launches;
+int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who);
+int in_gd_gemm(const float* d_out, int64_t n, int K, const void* prep, float* gd, cudaStream_t st);                 // project_tc.cu
+size_t in_param_ws_bytes(int64_t N, int64_t K);                                                                     // project_simt.cu
+int in_param_grads_simt(const float* x, int64_t ldx, const float* W, const float* da_src, const float* da_dst,
+                        const float* d_out, int64_t N, int64_t K, float* datt_src, float* datt_dst, float* dbias,
+                        float* Gm, void* ws, size_t ws_bytes, cudaStream_t st);
+
+namespace in {
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(st_smem_u32(smem_dst)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(st_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version = 1 [46,48), layout type [61,64) = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= uint64_t((saddr & 0x3FFFF) >> 4);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= uint64_t(1) << 46;
+    d |= uint64_t(2) << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor), kind::f16: D = F32 [4,6) = 1, A = F16 [7,10) = 0, B = F16 [10,13) = 0,
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int a_mn, int b_mn)
+{
+    return (1u << 4) | (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// ======================================================================================================================
+// out = epi(Z W_r):  persistent, one CTA per SM, 6 warps: bulk-copy producer, MMA issuer, 4 epilogue warps
+// ======================================================================================================================
+constexpr int G1_STAGES = 4;
+constexpr uint32_t G1_A = KBLOCK;                  // 32 KB: hi + lo planes of one k-block of one 128-row tile
+constexpr uint32_t G1_B = 16384;                   // hi + lo [64 x 128 B] of the W image
+constexpr uint32_t G1_STAGE = G1_A + G1_B;
+constexpr int G1_THREADS = 192;
+constexpr int G1_STG_LD = 36;
+constexpr size_t G1_SMEM = size_t(G1_STAGES) * G1_STAGE + 4 * 32 * G1_STG_LD * 4 + 1024;
+
+struct OutEpi {
+    const float* bias;
+    const float* scale;
+    const float* shift;
+    const float* residual;
+    int act;
+};
+__device__ __forceinline__ float out_act(float v, int act)
+{
+    if (act == GNNFD_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == GNNFD_ACT_ELU) return v > 0.f ? v : expm1f(v);
+    return v;
+}
+
+__global__ void __launch_bounds__(G1_THREADS, 1)
+in_out_gemm(const uint8_t* __restrict__ zimg, const uint8_t* __restrict__ wimg, const float* __restrict__ scal, int64_t n,
+            int NKB, OutEpi ep, float* __restrict__ out)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    __shared__ uint64_t full[G1_STAGES], empty[G1_STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+
+    if (tid == 0) {
+        for (int s = 0; s < G1_STAGES; ++s) {
+            st_mbar_init(&full[s], 1);
+            st_mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            st_mbar_init(&acc_full[s], 1);
+            st_mbar_init(&acc_empty[s], 4);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ---------------- producer: one 32 KB copy of Z and one 16 KB copy of W per k-block -----------------------
+        int64_t step = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            for (int kb = 0; kb < NKB; ++kb, ++step) {
+                const int s = int(step % G1_STAGES);
+                const int64_t u = step / G1_STAGES;
+                if (u > 0) st_mbar_wait(&empty[s], uint32_t((u - 1) & 1));
+                if (elect_one()) {
+                    uint8_t* stage = smem + size_t(s) * G1_STAGE;
+                    st_mbar_expect_tx(&full[s], G1_STAGE);
+                    st_bulk_g2s(stage, zimg + (size_t(t) * NKB + kb) * KBLOCK, G1_A, &full[s]);
+                    st_bulk_g2s(stage + G1_A, wimg + size_t(kb) * G1_B, G1_B, &full[s]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issue --------------------------------------------------------------------------------
+        constexpr uint32_t IDESC = make_idesc_f16(128, C, 0, 0);
+        int64_t step = 0, j = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+            const int buf = int(j & 1);
+            if ((j >> 1) > 0) {
+                st_mbar_wait(&acc_empty[buf], uint32_t(((j >> 1) - 1) & 1));
+                tc_fence_after();
+            }
+            for (int kb = 0; kb < NKB; ++kb, ++step) {
+                const int s = int(step % G1_STAGES);
+                st_mbar_wait(&full[s], uint32_t((step / G1_STAGES) & 1));
+                tc_fence_after();
+                const uint32_t a_hi = st_smem_u32(smem + size_t(s) * G1_STAGE), a_lo = a_hi + PLANE;
+                const uint32_t b_hi = a_hi + G1_A, b_lo = b_hi + 8192;
+                // two accumulators per tile (even / odd k-blocks) halve the length of the round-toward-zero chain
+                const uint32_t d = tmem_base + uint32_t(buf * 128 + (kb & 1) * 64);
+                if (elect_one()) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t ko = ks * 32;            // 16 fp16 = 32 bytes inside the swizzled row
+                        const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                        const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                        umma_f16(d, dah, dbh, IDESC, (kb >= 2 || ks > 0) ? 1u : 0u);
+                        umma_f16(d, dah, dbl, IDESC, 1u);
+                        umma_f16(d, dal, dbh, IDESC, 1u);
+                    }
+                    umma_commit(&empty[s]);
+                    if (kb == NKB - 1) umma_commit(&acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------- epilogue: warps 2..5 -> TMEM lane quadrants 2,3,0,1 -----------------------------------------
+        const int quad = warp & 3;
+        float* stg = reinterpret_cast<float*>(smem + size_t(G1_STAGES) * G1_STAGE) + (warp - 2) * (32 * G1_STG_LD);
+        const float inv = scal[2];
+        int64_t j = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+            const int buf = int(j & 1);
+            st_mbar_wait(&acc_full[buf], uint32_t((j >> 1) & 1));
+            tc_fence_after();
+            const int64_t m0 = t * TILE + quad * 32;
+#pragma unroll 1
+            for (int ch = 0; ch < C / 32; ++ch) {
+                uint32_t v0[32], v1[32];
+                tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(buf * 128 + ch * 32), v0);
+                if (NKB > 1) {
+                    tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(buf * 128 + 64 + ch * 32), v1);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) v0[c] = __float_as_uint(__uint_as_float(v0[c]) + __uint_as_float(v1[c]));
+                }
+                __syncwarp();
+#pragma unroll
+                for (int c = 0; c < 32; c += 4)
+                    *reinterpret_cast<float4*>(stg + lane * G1_STG_LD + c) =
+                        make_float4(__uint_as_float(v0[c]), __uint_as_float(v0[c + 1]), __uint_as_float(v0[c + 2]),
+                                    __uint_as_float(v0[c + 3]));
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + (lane >> 3), cq = ch * 32 + (lane & 7) * 4;
+                    const int64_t gm = m0 + r;
+                    const float4 o = *reinterpret_cast<const float4*>(stg + r * G1_STG_LD + (lane & 7) * 4);
+                    if (gm < n) {
+                        float ov[4] = {o.x * inv, o.y * inv, o.z * inv, o.w * inv};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float v = ov[k] + (ep.bias ? ep.bias[cq + k] : 0.f);
+                            if (ep.scale) v = fmaf(v, ep.scale[cq + k], ep.shift[cq + k]);
+                            v = out_act(v, ep.act);
+                            if (ep.residual) v += ep.residual[gm * C + cq + k];
+                            ov[k] = v;
+                        }
+                        *reinterpret_cast<float4*>(out + gm * C + cq) = make_float4(ov[0], ov[1], ov[2], ov[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// ======================================================================================================================
+// dWr partials:  P[slab][f][c] = sum_{i in slab} Z[i,f] * dO[i,c]   (both operands MN-major, reduction over nodes)
+// ======================================================================================================================
+// A CTA owns a slab of node tiles and HALF of the feature M-tiles (TMEM holds 6 accumulators of 128 x 64).  Per node
+// tile the four producer warps split dO (fp32 -> scaled fp16 hi/lo, swizzled) once; the bulk-copy warp streams the Z
+// k-block pairs (64 KB: one M = 128 tile of features); the issuer runs 8 k-steps x 3 MMAs per M-tile.  Every FLUSH
+// node tiles the accumulators are drained into the CTA's private fp32 partial with RED.ADD (L2-resident), which bounds
+// the round-toward-zero accumulation chain; partials are summed in slab order afterwards (deterministic).
+constexpr int G3_THREADS = 192;
+constexpr uint32_t G3_A = 2 * KBLOCK;              // 64 KB: two consecutive k-blocks (128 features), hi + lo each
+constexpr uint32_t G3_B = 2 * PLANE;               // 32 KB: dO tile, hi + lo planes
+constexpr int G3_FLUSH = 8;
+constexpr int G3_STG_LD = 33;
+constexpr size_t G3_SMEM = 2 * size_t(G3_A) + 2 * size_t(G3_B) + 4 * 32 * G3_STG_LD * 4 + 1024;
+constexpr int G3_MAX_MT = 6;
+
+__global__ void __launch_bounds__(G3_THREADS, 1)
+in_dw_gemm(const uint8_t* __restrict__ zimg, const float* __restrict__ d_out, const float* __restrict__ dmax, int64_t n,
+           int NKB, int F, int64_t tiles_per_slab, float* __restrict__ P, int64_t p_slab_stride)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                              // [2][G3_A]
+    uint8_t* sB = smem + 2 * size_t(G3_A);           // [2][G3_B]
+    __shared__ uint64_t a_full[2], a_empty[2], b_full[2], b_empty[2], acc_full, acc_empty;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int slab = blockIdx.x >> 1, half = blockIdx.x & 1;
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const int64_t t0 = int64_t(slab) * tiles_per_slab;
+    const int64_t t1 = (t0 + tiles_per_slab < n_tiles) ? t0 + tiles_per_slab : n_tiles;
+    const int nt = t1 > t0 ? int(t1 - t0) : 0;
+    const int MT = (NKB + 1) / 2, MT0 = (MT + 1) / 2;
+    const int m_base = half ? MT0 : 0;
+    const int my_mt = half ? MT - MT0 : MT0;
+
+    if (tid == 0) {
+        for (int s = 0; s < 2; ++s) {
+            st_mbar_init(&a_full[s], 1);
+            st_mbar_init(&a_empty[s], 1);
+            st_mbar_init(&b_full[s], 4);
+            st_mbar_init(&b_empty[s], 1);
+        }
+        st_mbar_init(&acc_full, 1);
+        st_mbar_init(&acc_empty, 4);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (my_mt > 0 && nt > 0) {
+        if (warp == 0) {
+            // ---------------- A producer: one 64 KB copy (two k-blocks of the image) per (node tile, M-tile) -------------
+            int64_t step = 0;
+            for (int i = 0; i < nt; ++i) {
+                for (int mm = 0; mm < my_mt; ++mm, ++step) {
+                    const int s = int(step & 1);
+                    if (step >= 2) st_mbar_wait(&a_empty[s], uint32_t(((step >> 1) - 1) & 1));
+                    const int kb0 = 2 * (m_base + mm);
+                    const uint32_t bytes = (kb0 + 1 < NKB) ? G3_A : uint32_t(KBLOCK);   // odd NKB: the last pair is half
+                    if (elect_one()) {
+                        st_mbar_expect_tx(&a_full[s], bytes);
+                        st_bulk_g2s(sA + size_t(s) * G3_A, zimg + (size_t(t0 + i) * NKB + kb0) * KBLOCK, bytes, &a_full[s]);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else if (warp == 1) {
+            // ---------------- MMA issue ------------------------------------------------------------------------------
+            constexpr uint32_t IDESC = make_idesc_f16(128, C, 1, 1);
+            int64_t step = 0;
+            for (int i = 0; i < nt; ++i) {
+                const int bb = i & 1;
+                st_mbar_wait(&b_full[bb], uint32_t((i >> 1) & 1));
+                if (i > 0 && i % G3_FLUSH == 0) st_mbar_wait(&acc_empty, uint32_t(((i / G3_FLUSH) - 1) & 1));
+                tc_fence_after();
+                const uint32_t b_hi = st_smem_u32(sB + size_t(bb) * G3_B), b_lo = b_hi + PLANE;
+                const bool restart = (i % G3_FLUSH) == 0;
+                for (int mm = 0; mm < my_mt; ++mm, ++step) {
+                    const int s = int(step & 1);
+                    st_mbar_wait(&a_full[s], uint32_t((step >> 1) & 1));
+                    tc_fence_after();
+                    // stage layout: [k-block 2m: hi | lo][k-block 2m+1: hi | lo]; the two 64-feature atoms of the M = 128
+                    // operand are KBLOCK bytes apart (LBO), consecutive 8-node groups 1024 bytes (SBO)
+                    const uint32_t a_hi = st_smem_u32(sA + size_t(s) * G3_A), a_lo = a_hi + PLANE;
+                    const uint32_t d = tmem_base + uint32_t(mm * 64);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {         // 16 nodes per k-step = two 8-node groups
+                            const uint32_t ko = ks * 2048;
+                            const uint64_t dah = make_desc(a_hi + ko, KBLOCK, 1024), dal = make_desc(a_lo + ko, KBLOCK, 1024);
+                            const uint64_t dbh = make_desc(b_hi + ko, PLANE, 1024), dbl = make_desc(b_lo + ko, PLANE, 1024);
+                            umma_f16(d, dah, dbh, IDESC, (restart && ks == 0) ? 0u : 1u);
+                            umma_f16(d, dah, dbl, IDESC, 1u);
+                            umma_f16(d, dal, dbh, IDESC, 1u);
+                        }
+                        umma_commit(&a_empty[s]);
+                        if (mm == my_mt - 1) {
+                            umma_commit(&b_empty[bb]);
+                            if ((i + 1) % G3_FLUSH == 0 || i == nt - 1) umma_commit(&acc_full);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            // ---------------- dO producers (warps 2..5, 32 nodes each) + accumulator flush (TMEM quadrants 2,3,0,1) ------
+            const int w = warp - 2, quad = warp & 3;
+            const float sd = pow2_scale(*dmax);
+            float* stg = reinterpret_cast<float*>(smem + 2 * size_t(G3_A) + 2 * size_t(G3_B)) + w * (32 * G3_STG_LD);
+            float* Ps = P + int64_t(slab) * p_slab_stride;
+            int flushes = 0;
+            for (int i = 0; i < nt; ++i) {
+                const int bb = i & 1;
+                if (i >= 2) st_mbar_wait(&b_empty[bb], uint32_t(((i >> 1) - 1) & 1));
+                uint8_t* b_hi = sB + size_t(bb) * G3_B;
+                const int64_t node0 = (t0 + i) * TILE + w * 32;
+                // lane owns channels 2*lane, 2*lane+1 of every node row: coalesced 256-byte row reads
+                float2 v[32];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    const int64_t node = node0 + r;
+                    v[r] = (node < n) ? __ldg(reinterpret_cast<const float2*>(d_out + node * C) + lane) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                    __half2 hi, lo;
+                    split_h2(v[r].x * sd, v[r].y * sd, hi, lo);
+                    const uint32_t off = plane_off(w * 32 + r, 2 * lane);
+                    *reinterpret_cast<__half2*>(b_hi + off) = hi;
+                    *reinterpret_cast<__half2*>(b_hi + PLANE + off) = lo;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&b_full[bb]);
+                if ((i + 1) % G3_FLUSH == 0 || i == nt - 1) {
+                    st_mbar_wait(&acc_full, uint32_t(flushes & 1));
+                    tc_fence_after();
+                    ++flushes;
+                    for (int mm = 0; mm < my_mt; ++mm) {
+                        const int f0 = (m_base + mm) * 128 + quad * 32;          // this warp's 32 feature rows
+#pragma unroll 1
+                        for (int ch = 0; ch < C / 32; ++ch) {
+                            uint32_t acc[32];
+                            tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(mm * 64 + ch * 32), acc);
+                            __syncwarp();
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) stg[lane * G3_STG_LD + c] = __uint_as_float(acc[c]);
+                            __syncwarp();
+                            // fire-and-forget fp32 reductions into this CTA's private partial: 128-byte coalesced
+#pragma unroll 8
+                            for (int r = 0; r < 32; ++r)
+                                if (f0 + r < F) atomicAdd(Ps + int64_t(f0 + r) * C + ch * 32 + lane, stg[r * G3_STG_LD + lane]);
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dW[o = h*C + c, k] = inv * sum_slab P[slab][f = h*KP + k][c] + att_src[o] * Gm[h][k] + att_dst[o] * Gm[H + h][k]
+__global__ void in_dw_finalize(const float* __restrict__ P, int n_slabs, int64_t p_slab_stride, const float* __restrict__ scal,
+                               const float* __restrict__ dmax, const float* __restrict__ Gm, const float* __restrict__ att_src,
+                               const float* __restrict__ att_dst, int K, int KP, float* __restrict__ dW)
+{
+    const float inv = 1.f / (scal[0] * pow2_scale(*dmax) * float(H));
+    const int total = H * C * K;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        // c fastest across threads: the partials are read as 256-byte runs
+        const int c = idx % C, hk = idx / C, k = hk % K, h = hk / K;
+        const int64_t pf = int64_t(h * KP + k) * C + c;
+        float s = 0.f;
+        for (int sl = 0; sl < n_slabs; ++sl) s += P[int64_t(sl) * p_slab_stride + pf];
+        const int o = h * C + c;
+        dW[int64_t(o) * K + k] = s * inv + att_src[o] * Gm[h * K + k] + att_dst[o] * Gm[(H + h) * K + k];
+    }
+}
+
+__global__ void in_absmax_kernel(const float* __restrict__ a, int64_t n, unsigned* __restrict__ out_bits)
+{
+    float m = 0.f;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+        m = fmaxf(m, fabsf(a[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out_bits, __float_as_uint(m));
+}
+
+// da_src[j,h] = sum of dz over the out-edges of source j (dz rows are in source-major order): thread per (j, h)
+__global__ void in_dasrc_kernel(const int32_t* __restrict__ colptr, const float* __restrict__ dz, int64_t n_src,
+                                float* __restrict__ da_src)
+{
+    const int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+    const int64_t j = idx / H;
+    const int h = int(idx % H);
+    if (j >= n_src) return;
+    const int beg = colptr[j], end = colptr[j + 1];
+    float s0 = 0.f, s1 = 0.f;
+    int p = beg;
+    for (; p + 1 < end; p += 2) {
+        s0 += dz[int64_t(p) * H + h];
+        s1 += dz[int64_t(p + 1) * H + h];
+    }
+    if (p < end) s0 += dz[int64_t(p) * H + h];
+    da_src[j * H + h] = s0 + s1;
+}
+
+static int dw_slabs(int64_t n_tiles)
+{
+    int64_t s = sm_count() / 2;
+    if (s > n_tiles) s = n_tiles;
+    if (s < 1) s = 1;
+    return (int)s;
+}
+static size_t dw_partial_floats(const Dims& d) { return size_t((d.NKB + 1) / 2) * 128 * C; }
+
+}  // namespace in
+}  // namespace gnnfd
+
+using namespace gnnfd;
+using namespace gnnfd::in;
+
+extern "C" {
+
+/* out [n, C] = act((Z W_r / H + bias) * post_scale + post_shift) + residual   (cf. gnnfd_gat_fwd_fused) */
+int gnnfd_in_out(const void* zimg, int64_t n, int64_t K, const void* prep, const float* bias, int act,
+                 const float* post_scale, const float* post_shift, const float* residual, float* out,
+                 gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && n >= 0, GNNFD_ERR_ARG, "in_out: bad shape");
+    if (n == 0) return GNNFD_OK;
+    GNNFD_REQUIRE(zimg && prep && out, GNNFD_ERR_ARG, "in_out: NULL tensor");
+    GNNFD_REQUIRE((post_scale == nullptr) == (post_shift == nullptr), GNNFD_ERR_ARG,
+                  "in_out: post_scale and post_shift must be given together");
+    GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(zimg) & 1023) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, GNNFD_ERR_ARG,
+                  "in_out: zimg must be 1024-byte and out 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const Dims d((int)K);
+    const char* p = reinterpret_cast<const char*>(prep);
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const unsigned grid = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());
+    GNNFD_CUDA(cudaFuncSetAttribute(in_out_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G1_SMEM));
+    const OutEpi ep{bias, post_scale, post_shift, residual, act};
+    in_out_gemm<<<grid, G1_THREADS, G1_SMEM, st>>>(reinterpret_cast<const uint8_t*>(zimg),
+                                                   reinterpret_cast<const uint8_t*>(p + prep_off_wout(d)),
+                                                   reinterpret_cast<const float*>(p), n, d.NKB, ep, out);
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+
+/* gd [n, F] = d_out [n, C] @ W_r^T / H  (F = gnnfd_in_sizes' gd_ld): the per-destination vectors whose dot product with
+ * x[j] is d_alpha.  Row-range agnostic: call it on a block of rows to bound the size of gd. */
+int gnnfd_in_bwd_gd(const float* d_out, int64_t n, int64_t K, const void* prep, float* gd, gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && n >= 0, GNNFD_ERR_ARG, "in_bwd_gd: bad shape");
+    if (n == 0) return GNNFD_OK;
+    GNNFD_REQUIRE(d_out && prep && gd, GNNFD_ERR_ARG, "in_bwd_gd: NULL tensor");
+    GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(gd) & 15) == 0, GNNFD_ERR_ARG, "in_bwd_gd: gd must be 16-byte aligned");
+    return in_gd_gemm(d_out, n, (int)K, prep, gd, (cudaStream_t)stream);
+}
+
+/* da_src [n_src, H] = per-source sums of dz (source-major order, as gnnfd_in_bwd_edges writes it); needs the CSC twin. */
+int gnnfd_in_bwd_dasrc(const gnnfd_graph_t* g, const float* dz, float* da_src, gnnfd_stream_t stream)
+{
+    int rc = check_graph(g, true, "in_bwd_dasrc");
+    if (rc) return rc;
+    if (g->n_src == 0) return GNNFD_OK;
+    GNNFD_REQUIRE(da_src && (g->n_edges == 0 || dz), GNNFD_ERR_ARG, "in_bwd_dasrc: NULL tensor");
+    const int64_t total = g->n_src * H;
+    in_dasrc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(g->colptr, dz, g->n_src, da_src);
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+
+int gnnfd_in_bwd_params_workspace_bytes(int64_t n, int64_t K, size_t* bytes)
+{
+    GNNFD_REQUIRE(bytes && K >= 1 && K <= MAX_K && n >= 0, GNNFD_ERR_ARG, "in_bwd_params_workspace_bytes: bad argument");
+    const Dims d((int)K);
+    const int S = dw_slabs((n + TILE - 1) / TILE);
+    *bytes = in_param_ws_bytes(n, K) + carve_bytes(size_t(S) * dw_partial_floats(d), 4) + carve_bytes(size_t(2) * H * K, 4) + 1024;
+    return GNNFD_OK;
+}
+
+/* Parameter gradients of the layer from the saved image and the logit gradients of THIS rank's n rows:
+ *   dW [H*C, K], datt_src / datt_dst [H*C], dbias [C]   (x, da_src, da_dst, d_out: rows [0, n)). */
+int gnnfd_in_bwd_params(const void* zimg, const float* d_out, const float* x, int64_t ldx, int64_t n, int64_t K,
+                        const float* W, const float* att_src, const float* att_dst, const float* da_src,
+                        const float* da_dst, const void* prep, float* dW, float* datt_src, float* datt_dst,
+                        float* dbias, void* ws, size_t ws_bytes, gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && n >= 0 && ldx >= K, GNNFD_ERR_ARG, "in_bwd_params: bad shape");
+    GNNFD_REQUIRE(W && att_src && att_dst && prep && dW && datt_src && datt_dst && dbias, GNNFD_ERR_ARG, "in_bwd_params: NULL argument");
+    GNNFD_REQUIRE(n == 0 || (zimg && d_out && x && da_src && da_dst), GNNFD_ERR_ARG, "in_bwd_params: NULL tensor");
+    size_t need = 0;
+    gnnfd_in_bwd_params_workspace_bytes(n, K, &need);
+    GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "in_bwd_params: workspace %zu < %zu", ws_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Dims d((int)K);
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    const int S = dw_slabs(n_tiles);
+    char* p = reinterpret_cast<char*>(ws);
+    const size_t simt_bytes = in_param_ws_bytes(n, K);
+    char* q = p + ((simt_bytes + 255) & ~size_t(255));
+    float* P = carve<float>(q, size_t(S) * dw_partial_floats(d));
+    float* Gm = carve<float>(q, size_t(2) * H * K);
+    unsigned* dmax = reinterpret_cast<unsigned*>(carve<float>(q, 16));
+    // datt, dbias and G = [da_src | da_dst]^T x (node reductions over x, shared with the projected-feature path)
+    int rc = in_param_grads_simt(x, ldx, W, da_src, da_dst, d_out, n, K, datt_src, datt_dst, dbias, Gm, p, simt_bytes, st);
+    if (rc) return rc;
+    const int64_t pstride = (int64_t)dw_partial_floats(d);
+    GNNFD_CUDA(cudaMemsetAsync(P, 0, size_t(S) * pstride * sizeof(float), st));
+    GNNFD_CUDA(cudaMemsetAsync(dmax, 0, 64, st));
+    if (n > 0) {
+        int64_t blocks = (n * C + 255) / 256;
+        if (blocks > int64_t(sm_count()) * 8) blocks = int64_t(sm_count()) * 8;
+        in_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_out, n * C, dmax);
+        const int64_t tps = (n_tiles + S - 1) / S;
+        GNNFD_CUDA(cudaFuncSetAttribute(in_dw_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3_SMEM));
+        in_dw_gemm<<<2 * S, G3_THREADS, G3_SMEM, st>>>(reinterpret_cast<const uint8_t*>(zimg), d_out,
+                                                       reinterpret_cast<const float*>(dmax), n, d.NKB, d.F, tps, P, pstride);
+        g_launches += 2;
+    }
+    in_dw_finalize<<<(H * C * d.K + 255) / 256, 256, 0, st>>>(P, S, pstride, reinterpret_cast<const float*>(prep),
+                                                             reinterpret_cast<const float*>(dmax), Gm, att_src, att_dst, d.K,
+                                                             d.KP, dW);
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+
+}  // extern "C"

@@ -501,4 +501,42 @@ int project_bwd_simt(const float* x, int64_t ldx, const float* W, const float* d
     return GNNFD_OK;
 }
 
+// ---- input-space path (in_gemm.cu): datt_src / datt_dst / dbias and G = [da_src | da_dst]^T x -----------------------
+size_t in_param_ws_bytes(int64_t N, int64_t K)
+{
+    const int Sg = col_slices(N);
+    return carve_bytes(size_t(Sg) * 2 * 8 * K, 4) + carve_bytes(size_t(Sg) * 64, 4) + 512;
+}
+int in_param_grads_simt(const float* x, int64_t ldx, const float* W, const float* da_src, const float* da_dst,
+                        const float* d_out, int64_t N, int64_t K, float* datt_src, float* datt_dst, float* dbias,
+                        float* Gm, void* ws, size_t ws_bytes, cudaStream_t st)
+{
+    constexpr int H = 8, C = 64, D = H * C;
+    GNNFD_REQUIRE(ws_bytes >= in_param_ws_bytes(N, K), GNNFD_ERR_WORKSPACE, "in_param_grads: workspace too small");
+    if (N == 0) {
+        cudaMemsetAsync(datt_src, 0, sizeof(float) * D, st);
+        cudaMemsetAsync(datt_dst, 0, sizeof(float) * D, st);
+        cudaMemsetAsync(dbias, 0, sizeof(float) * C, st);
+        cudaMemsetAsync(Gm, 0, sizeof(float) * 2 * H * K, st);
+        return GNNFD_OK;
+    }
+    char* p = reinterpret_cast<char*>(ws);
+    const int Sg = col_slices(N);
+    const int64_t rpg = (N + Sg - 1) / Sg;
+    float* Pg = carve<float>(p, size_t(Sg) * 2 * H * K);
+    float* Pc = carve<float>(p, size_t(Sg) * C);
+    const bool pair = (K % 2 == 0) && (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+    const int64_t cols = pair ? K / 2 : K;
+    const int bs = int(cols >= 256 ? 256 : ((cols + 31) / 32) * 32);
+    if (pair) dax_partial<8, 2><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
+    else      dax_partial<8, 1><<<Sg, bs, 0, st>>>(x, ldx, da_src, da_dst, N, (int)K, rpg, Pg);
+    reduce_slices<<<(unsigned)((2 * H * K + 255) / 256), 256, 0, st>>>(Pg, int64_t(2) * H * K, Sg, Gm);
+    datt_from_g<<<(unsigned)((D * 32 + 255) / 256), 256, 0, st>>>(W, Gm, D, (int)K, H, C, datt_src, datt_dst);
+    colsum_partial<<<Sg, 64, 0, st>>>(d_out, N, C, rpg, Pc);
+    reduce_slices<<<1, 64, 0, st>>>(Pc, C, Sg, dbias);
+    g_launches += 5;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+
 }  // namespace gnnfd

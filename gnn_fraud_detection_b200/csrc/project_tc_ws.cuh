@@ -275,6 +275,8 @@ gemm_tc_ws(const float* __restrict__ A, int64_t lda, int64_t M, int Kd, const fl
                             } else {
                                 *reinterpret_cast<float4*>(Cf + gm * ldc + col0 + cq) = o;
                             }
+                        } else if (EPI == 2) {     // plain fp32 store, ldc and n_valid multiples of 4: one 16-byte store
+                            if (col0 + cq < n_valid) *reinterpret_cast<float4*>(Cf + gm * ldc + col0 + cq) = o;
                         } else {
                             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll

@@ -155,6 +155,170 @@ def project_bwd(x, W, dxw, xw, da_src, da_dst, d_out, H, C_, Co, need_dx, algo=_
     return dW, datt_src, datt_dst, dbias, dx
 
 
+# ------------------------------------------------------------------------------------------------
+# input-space formulation of the first layer (include/gnnfd_b200.h section (5), csrc/in_common.cuh)
+# ------------------------------------------------------------------------------------------------
+def _aligned_u8(nbytes: int, device, align: int = 1024) -> torch.Tensor:
+    """uint8 buffer whose data_ptr is ``align``-byte aligned (torch guarantees only 512)."""
+    raw = torch.empty(int(nbytes) + align, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % align
+    return raw[off: off + int(nbytes)]
+
+
+def in_supported(K: int, H: int, C_: int, concat: bool) -> bool:
+    return bool(_abi.lib().gnnfd_in_supported(int(K), int(H), int(C_), int(bool(concat))))
+
+
+def in_sizes(n_dst: int, K: int):
+    pb, zb, ld = C.c_size_t(), C.c_size_t(), C.c_int64()
+    _abi.check(_abi.lib().gnnfd_in_sizes(int(n_dst), int(K), C.byref(pb), C.byref(zb), C.byref(ld)))
+    return pb.value, zb.value, ld.value
+
+
+def in_logits(x, W, att_src, att_dst, prep, xmax, n_rows=None):
+    """a_src, a_dst [n,H] straight from the rows of ``x``; accumulates max|x| into ``xmax`` (a zeroed 1-element tensor)."""
+    N, K = x.shape if n_rows is None else (n_rows, x.size(1))
+    a_src = torch.empty(N, 8, dtype=torch.float32, device=x.device)
+    a_dst = torch.empty(N, 8, dtype=torch.float32, device=x.device)
+    _abi.check(_abi.lib().gnnfd_in_logits(x.data_ptr(), x.stride(0), N, K, W.data_ptr(), att_src.data_ptr(),
+                                          att_dst.data_ptr(), a_src.data_ptr(), a_dst.data_ptr(), xmax.data_ptr(),
+                                          prep.data_ptr(), _stream()))
+    return a_src, a_dst
+
+
+def in_prepare(W, K, xmax, prep):
+    _abi.check(_abi.lib().gnnfd_in_prepare(W.data_ptr(), int(K), xmax.data_ptr(), prep.data_ptr(), _stream()))
+
+
+def in_fwd(g: GraphCSR, x, a_src, a_dst, negative_slope, prep, keep_mask=None, p_drop=0.0):
+    """Aggregation in input space -> (zimg, rowmax, rowsum)."""
+    L = _abi.lib()
+    dev, K = x.device, x.size(1)
+    _, zb, _ = in_sizes(g.n_dst, K)
+    zimg = _aligned_u8(zb, dev)
+    rowmax = torch.empty(g.n_dst, 8, dtype=torch.float32, device=dev)
+    rowsum = torch.empty(g.n_dst, 8, dtype=torch.float32, device=dev)
+    nb = C.c_size_t()
+    _abi.check(L.gnnfd_in_fwd_workspace_bytes(g.ref(), C.byref(nb)))
+    ws = _ws(nb.value, dev)
+    _abi.check(L.gnnfd_in_fwd(g.ref(), x.data_ptr(), x.stride(0), K, a_src.data_ptr(), a_dst.data_ptr(),
+                              float(negative_slope), _abi.ptr(keep_mask), float(p_drop), prep.data_ptr(), zimg.data_ptr(),
+                              rowmax.data_ptr(), rowsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return zimg, rowmax, rowsum
+
+
+def in_out(zimg, n, K, prep, bias, act=_abi.ACT_NONE, post_scale=None, post_shift=None, residual=None):
+    out = torch.empty(n, 64, dtype=torch.float32, device=zimg.device)
+    _abi.check(_abi.lib().gnnfd_in_out(zimg.data_ptr(), int(n), int(K), prep.data_ptr(), _abi.ptr(bias), int(act),
+                                       _abi.ptr(post_scale), _abi.ptr(post_shift), _abi.ptr(residual), out.data_ptr(),
+                                       _stream()))
+    return out
+
+
+IN_GD_BLOCK_BYTES = 8 << 30     # upper bound of the Gd buffer of the backward edge pass (rows are processed in blocks)
+
+
+def in_bwd_edges(g: GraphCSR, x, a_src, a_dst, rowmax, rowsum, d_out, prep, negative_slope, keep_mask=None, p_drop=0.0,
+                 n_blocks=None):
+    """Gd GEMM + backward edge pass, in blocks of destination rows.  Returns dz [E',H] (source-major) and da_dst."""
+    L = _abi.lib()
+    dev, K = x.device, x.size(1)
+    _, _, F = in_sizes(g.n_dst, K)
+    dz = torch.empty(g.n_edges, 8, dtype=torch.float32, device=dev)
+    da_dst = torch.empty(g.n_dst, 8, dtype=torch.float32, device=dev)
+    nb = C.c_size_t()
+    _abi.check(L.gnnfd_in_bwd_edges_workspace_bytes(g.ref(), C.byref(nb)))
+    ws = _ws(nb.value, dev)
+    if n_blocks is None:
+        n_blocks = max(1, -(-g.n_dst * F * 4 // IN_GD_BLOCK_BYTES))
+    blocks = g.item_blocks(n_blocks)
+    gd = torch.empty(max(hi - lo for _, _, lo, hi in blocks), F, dtype=torch.float32, device=dev)
+    for bi, (i_lo, i_hi, r_lo, r_hi) in enumerate(blocks):
+        if r_hi > r_lo:
+            _abi.check(L.gnnfd_in_bwd_gd(d_out[r_lo:r_hi].data_ptr(), r_hi - r_lo, K, prep.data_ptr(), gd.data_ptr(), _stream()))
+        phase = 1 | (2 if bi == len(blocks) - 1 else 0)
+        _abi.check(L.gnnfd_in_bwd_edges(g.ref(), x.data_ptr(), x.stride(0), K, a_src.data_ptr(), a_dst.data_ptr(),
+                                        rowmax.data_ptr(), rowsum.data_ptr(), gd.data_ptr(), r_lo, i_lo, i_hi, r_lo, r_hi,
+                                        float(negative_slope), _abi.ptr(keep_mask), float(p_drop), dz.data_ptr(),
+                                        da_dst.data_ptr(), ws.data_ptr(), ws.numel(), phase, _stream()))
+    return dz, da_dst
+
+
+def in_dasrc(g: GraphCSR, dz):
+    da_src = torch.empty(g.n_src, 8, dtype=torch.float32, device=dz.device)
+    _abi.check(_abi.lib().gnnfd_in_bwd_dasrc(g.ref(), dz.data_ptr(), da_src.data_ptr(), _stream()))
+    return da_src
+
+
+def in_bwd_params(zimg, d_out, x, W, att_src, att_dst, da_src, da_dst, prep):
+    """dW, datt_src, datt_dst, dbias from the saved image and the logit gradients of x's rows."""
+    L = _abi.lib()
+    n, K = x.shape
+    dev = x.device
+    dW = torch.empty(512, K, dtype=torch.float32, device=dev)
+    datt_src = torch.empty(512, dtype=torch.float32, device=dev)
+    datt_dst = torch.empty(512, dtype=torch.float32, device=dev)
+    dbias = torch.empty(64, dtype=torch.float32, device=dev)
+    nb = C.c_size_t()
+    _abi.check(L.gnnfd_in_bwd_params_workspace_bytes(n, K, C.byref(nb)))
+    ws = _ws(nb.value, dev)
+    _abi.check(L.gnnfd_in_bwd_params(zimg.data_ptr(), d_out.data_ptr(), x.data_ptr(), x.stride(0), n, K, W.data_ptr(),
+                                     att_src.data_ptr(), att_dst.data_ptr(), da_src.data_ptr(), da_dst.data_ptr(),
+                                     prep.data_ptr(), dW.data_ptr(), datt_src.data_ptr(), datt_dst.data_ptr(),
+                                     dbias.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
+    return dW, datt_src, datt_dst, dbias
+
+
+class GATConvInputSpaceFunction(torch.autograd.Function):
+    """First-layer GATConv (x needs no gradient, concat=False, H=8, C=64) in the input-space formulation."""
+
+    @staticmethod
+    def forward(ctx, x, W, att_src, att_dst, bias, g: GraphCSR, negative_slope, keep_mask, p_drop, want_stats):
+        _require_f32_cuda("x", x)
+        _require_f32_cuda("lin_src.weight", W)
+        if x.dim() != 2 or x.size(1) != W.size(1):
+            raise ValueError(f"x must be [N,{W.size(1)}], got {tuple(x.shape)}")
+        if x.size(0) != g.n_src:
+            raise ValueError(f"x has {x.size(0)} rows but the graph has {g.n_src} source nodes")
+        if x.stride(1) != 1:
+            x = x.contiguous()
+        W = W.contiguous()
+        a_s, a_d = att_src.contiguous().view(-1), att_dst.contiguous().view(-1)
+        K = x.size(1)
+        with torch.cuda.device(x.device):
+            pb, _, _ = in_sizes(g.n_dst, K)
+            prep = _aligned_u8(pb, x.device)
+            xmax = torch.zeros(16, dtype=torch.float32, device=x.device)
+            a_src, a_dst = in_logits(x, W, a_s, a_d, prep, xmax)
+            in_prepare(W, K, xmax, prep)
+            zimg, rowmax, rowsum = in_fwd(g, x, a_src, a_dst, negative_slope, prep, keep_mask, p_drop)
+            out = in_out(zimg, g.n_dst, K, prep, bias)
+        ctx.save_for_backward(x, W, a_s, a_d, a_src, a_dst, rowmax, rowsum, keep_mask, zimg, prep)
+        ctx.g, ctx.slope, ctx.p = g, negative_slope, p_drop
+        ctx.has_bias = bias is not None
+        ctx.att_shape = att_src.shape
+        if want_stats:
+            ctx.mark_non_differentiable(a_src, a_dst, rowmax, rowsum)
+            return out, a_src, a_dst, rowmax, rowsum
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out, *unused):
+        x, W, a_s, a_d, a_src, a_dst, rowmax, rowsum, keep_mask, zimg, prep = ctx.saved_tensors
+        g = ctx.g
+        if not g.has_csc:
+            raise RuntimeError("backward needs the CSC twin; build the graph with build_csc=True")
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("the input-space formulation computes no gradient w.r.t. x (first layer only)")
+        d_out = d_out.contiguous().float()
+        with torch.cuda.device(x.device):
+            dz, da_dst = in_bwd_edges(g, x, a_src, a_dst, rowmax, rowsum, d_out, prep, ctx.slope, keep_mask, ctx.p)
+            da_src = in_dasrc(g, dz)
+            dW, datt_src, datt_dst, dbias = in_bwd_params(zimg, d_out, x, W, a_s, a_d, da_src, da_dst, prep)
+        return (None, dW, datt_src.view(ctx.att_shape), datt_dst.view(ctx.att_shape), dbias if ctx.has_bias else None,
+                None, None, None, None, None)
+
+
 class GATConvFunction(torch.autograd.Function):
     """out = GATConv(x, edge_index') with every stage in the CUDA library."""
 
@@ -204,5 +368,12 @@ class GATConvFunction(torch.autograd.Function):
 
 def gatconv(x, W, att_src, att_dst, bias, g: GraphCSR, heads, out_channels, concat=False, negative_slope=0.2,
             keep_mask=None, p_drop=0.0, xw_dtype=torch.float32, algo=_abi.GEMM_AUTO, want_stats=False):
+    if algo == _abi.GEMM_INPUT:
+        need_dx = x.requires_grad and torch.is_grad_enabled()
+        if need_dx or xw_dtype != torch.float32 or not in_supported(x.size(1), heads, out_channels, concat) or p_drop > 0.9:
+            raise _abi.GnnfdError(-5, "input-space formulation: needs x without gradient, concat=False, heads=8, "
+                                      "out_channels=64, in_channels <= 192, fp32 features, dropout <= 0.9")
+        return GATConvInputSpaceFunction.apply(x, W, att_src, att_dst, bias, g, negative_slope, keep_mask, p_drop,
+                                               want_stats)
     return GATConvFunction.apply(x, W, att_src, att_dst, bias, g, heads, out_channels, concat, negative_slope,
                                  keep_mask, p_drop, xw_dtype, algo, want_stats)

@@ -46,6 +46,8 @@ class GraphCSR:
                 self.c.hub_src = self._plan(colptr, self.n_src, hub_threshold, hub_chunk)
         # per-row charge in edge units: a dst row costs ~one 256 B epilogue, a src row writes a 2 KB dxw row
         self.c.items_dst = self._items(rowptr, self.n_dst, row_weight=1)
+        self._item_start_dst = self._hub_tensors[-1] if self.c.items_dst.n_items > 0 else None
+        self._item_blocks = {}
         if colptr is not None:
             self.c.items_src = self._items(colptr, self.n_src, row_weight=8)
 
@@ -98,6 +100,23 @@ class GraphCSR:
         plan.hub_row, plan.hub_chunk_ptr, plan.chunk_hub = hub_row.data_ptr(), hub_chunk_ptr.data_ptr(), \
             chunk_hub.data_ptr()
         return plan
+
+    def item_blocks(self, n_blocks: int):
+        """Split the dst-major work items into ``n_blocks`` contiguous runs: [(item_lo, item_hi, row_lo, row_hi)].
+        Item boundaries are row boundaries, so a block is a contiguous range of destination rows (cached; one small
+        device->host read per graph and block count)."""
+        n_items = int(self.c.items_dst.n_items)
+        if n_items == 0:
+            return [(0, 0, 0, self.n_dst)]
+        n_blocks = max(1, min(int(n_blocks), n_items))
+        hit = self._item_blocks.get(n_blocks)
+        if hit is None:
+            cuts = [b * n_items // n_blocks for b in range(n_blocks + 1)]
+            rows = self._item_start_dst[torch.tensor(cuts, device=self.device)].tolist()
+            rows[0], rows[-1] = 0, self.n_dst
+            hit = [(cuts[b], cuts[b + 1], int(rows[b]), int(rows[b + 1])) for b in range(n_blocks)]
+            self._item_blocks[n_blocks] = hit
+        return hit
 
     def ref(self):
         return C.byref(self.c)

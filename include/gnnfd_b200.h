@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 7
+#define GNNFD_ABI_VERSION 8
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -222,6 +222,55 @@ int gnnfd_project_bwd(const float* x, int64_t ldx, const float* W, const float* 
                       int64_t N, int64_t K, int H, int C, int Co, int algo, float* dW, float* datt_src,
                       float* datt_dst, float* dbias, float* dx, int64_t lddx, void* ws, size_t ws_bytes,
                       gnnfd_stream_t stream);
+
+/* ---- (5) input-space formulation of the FIRST layer (no gradient w.r.t. x, concat = 0, H = 8, C = 64, K <= 192) -------
+ * Same reference stages as (2)-(4) (GATConv.forward / backward at src/models/gat.py:39,80, src/train.py:142) evaluated
+ * without projected features:  Z[i,h,:] = sum_e alpha[e,h] x[j,:] ;  out = Z W_r / H + bias ;  logits from x . (W_h^T att);
+ * backward d_alpha[e,h] = Gd[i,h,:] . x[j,:] with Gd = dO W_r^T / H, dW from the saved Z.  The per-edge gather is K*4
+ * bytes instead of H*C*4, and across GPUs (destination ranges, x replicated) only [N,H] logits / logit gradients travel.
+ * Z lives in HBM as the fp16-pair tensor-core image described in csrc/in_common.cuh (opaque to the caller).
+ *   prep  : per-call constants + weight images, gnnfd_in_sizes().prep_bytes, 1024-byte aligned, built by
+ *           gnnfd_in_logits (u) + gnnfd_in_prepare (scales, images); valid until W / att / max|x| change
+ *   zimg  : gnnfd_in_sizes().zimg_bytes for n_dst rows, 1024-byte aligned; written by gnnfd_in_fwd, read by gnnfd_in_out
+ *           and gnnfd_in_bwd_params
+ *   gd    : [rows, gd_ld] fp32, gd_ld = gnnfd_in_sizes().gd_ld */
+int gnnfd_in_supported(int64_t K, int H, int C, int concat);
+int gnnfd_in_sizes(int64_t n_dst, int64_t K, size_t* prep_bytes, size_t* zimg_bytes, int64_t* gd_ld);
+/* a_src / a_dst [N,H] of rows [0,N) of x; xmax[0] = max(xmax[0], max|x|) (zero it before the first call; across GPUs
+ * max-reduce it before gnnfd_in_prepare). */
+int gnnfd_in_logits(const float* x, int64_t ldx, int64_t N, int64_t K, const float* W, const float* att_src,
+                    const float* att_dst, float* a_src, float* a_dst, float* xmax, void* prep,
+                    gnnfd_stream_t stream);
+int gnnfd_in_prepare(const float* W, int64_t K, const float* xmax, void* prep, gnnfd_stream_t stream);
+int gnnfd_in_fwd_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes);
+/* edge_update + message + aggregate in input space -> zimg, rowmax / rowsum [n_dst,H] (as gnnfd_gat_fwd saves them). */
+int gnnfd_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src,
+                 const float* a_dst, float negative_slope, const uint8_t* keep_mask, float p_drop,
+                 const void* prep, void* zimg, float* rowmax, float* rowsum, void* ws, size_t ws_bytes,
+                 gnnfd_stream_t stream);
+/* out [n,C] = act((Z W_r / H + bias) * post_scale + post_shift) + residual  (epilogue as gnnfd_gat_fwd_fused). */
+int gnnfd_in_out(const void* zimg, int64_t n, int64_t K, const void* prep, const float* bias, int act,
+                 const float* post_scale, const float* post_shift, const float* residual, float* out,
+                 gnnfd_stream_t stream);
+/* gd [n, gd_ld] = d_out [n,C] W_r^T / H; row-range agnostic (call per block of rows to bound gd). */
+int gnnfd_in_bwd_gd(const float* d_out, int64_t n, int64_t K, const void* prep, float* gd, gnnfd_stream_t stream);
+int gnnfd_in_bwd_edges_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes);
+/* dz [E',H] (source-major order, row csr2csc[e]) and da_dst [n_dst,H] for the destination rows covered by the work items
+ * [item_lo, item_hi) = rows [row_lo, row_hi) (0, n_items, 0, n_dst for everything); gd holds the Gd rows from gd_row0 on.
+ * phase bit 0: process the block; bit 1: finish the hub rows (after the last block, same ws).  Needs the CSC twin. */
+int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src,
+                       const float* a_dst, const float* rowmax, const float* rowsum, const float* gd,
+                       int64_t gd_row0, int64_t item_lo, int64_t item_hi, int64_t row_lo, int64_t row_hi,
+                       float negative_slope, const uint8_t* keep_mask, float p_drop, float* dz, float* da_dst,
+                       void* ws, size_t ws_bytes, int phase, gnnfd_stream_t stream);
+/* da_src [n_src,H] = per-source sums of dz (over g's CSC). */
+int gnnfd_in_bwd_dasrc(const gnnfd_graph_t* g, const float* dz, float* da_src, gnnfd_stream_t stream);
+int gnnfd_in_bwd_params_workspace_bytes(int64_t n, int64_t K, size_t* bytes);
+/* dW [H*C,K], datt_src / datt_dst [H*C], dbias [C] from the saved image and the logit gradients of rows [0,n). */
+int gnnfd_in_bwd_params(const void* zimg, const float* d_out, const float* x, int64_t ldx, int64_t n, int64_t K,
+                        const float* W, const float* att_src, const float* att_dst, const float* da_src,
+                        const float* da_dst, const void* prep, float* dW, float* datt_src, float* datt_dst,
+                        float* dbias, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 
 #ifdef __cplusplus
 }
