@@ -243,7 +243,14 @@ def run_gpu_arm(args):
         d_out = torch.full((n_local, C), 1.0 / N, device=dev)
     gen_s = time.perf_counter() - t_gen
 
-    stages = ["project_fwd", "gat_fwd", "gat_bwd_dst_src", "project_bwd"]
+    input_space = args.algo == _abi.GEMM_INPUT
+    if input_space:
+        stages = ["in_logits", "in_fwd_edges", "in_out_gemm", "in_bwd_gd_edges", "in_bwd_dasrc", "in_bwd_params"]
+        in_prep = Fn._aligned_u8(Fn.in_sizes(n_local, K)[0], dev)
+        x = Fn.in_pad_x(x)            # static first-layer input: padded once, like the CSR
+        in_xmax = torch.zeros(16, device=dev)
+    else:
+        stages = ["project_fwd", "gat_fwd", "gat_bwd_dst_src", "project_bwd"]
     ev = {}
 
     def step(timed: bool):
@@ -251,7 +258,23 @@ def run_gpu_arm(args):
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] if timed else None
         if timed:
             marks[0].record()
-        if part is None:
+        if part is None and input_space:
+            in_xmax.zero_()
+            a_src, a_dst = Fn.in_logits(x, W, a_s, a_d, in_prep, in_xmax)
+            Fn.in_prepare(W, K, in_xmax, in_prep)
+            if timed: marks[1].record()
+            zimg, rowmax, rowsum = Fn.in_fwd(g, x, a_src, a_dst, 0.2, in_prep)
+            if timed: marks[2].record()
+            out = Fn.in_out(zimg, N, K, in_prep, bias)
+            if timed: marks[3].record()
+            dz, da_dst = Fn.in_bwd_edges(g, x, a_src, a_dst, rowmax, rowsum, d_out, in_prep, 0.2)
+            if timed: marks[4].record()
+            da_src = Fn.in_dasrc(g, dz)
+            if timed: marks[5].record()
+            grads = Fn.in_bwd_params(zimg, d_out, x, W, a_s, a_d, da_src, da_dst, in_prep)
+            if timed: marks[6].record()
+            del zimg, dz
+        elif part is None:
             xw, a_src, a_dst = Fn.project_fwd(x, W, a_s, a_d, H, C, xw_dtype, args.algo)
             if timed: marks[1].record()
             out, rowmax, rowsum = Fn.gat_fwd(g, xw, a_src, a_dst, bias, H, C, 0.2, False)
@@ -307,28 +330,48 @@ def run_gpu_arm(args):
         Ep_total = int(te.item())
     else:
         Ep_total = Ep
+    # SURVEY.md 8(d) byte model (projected-feature formulation): the figure `layer` is quoted against, whichever
+    # formulation ran.  `own` = the byte model of the formulation that actually ran on this rank.
     bmodel = roofline.stage_bytes(N, Ep_total, K, H, C, False, s_bytes, need_dx=False)
-    local = roofline.stage_bytes(n_local, Ep, K, H, C, False, s_bytes, need_dx=False, n_src=(N if world > 1 else None))
-    # dominant kernel = the forward fused softmax/aggregation kernel (one launch per step on this rank)
-    dom_bytes = local["gat_fwd"]
-    dom_ms = stage_ms["gat_fwd"]
+    if input_space:
+        own = roofline.stage_bytes_input_space(n_local, Ep, K, H, C, n_src=(N if world > 1 else None))
+        stage_b = {"in_logits": own["in_logits"], "in_fwd_edges": own["in_fwd_edges"], "in_out_gemm": own["in_out_gemm"],
+                   "in_bwd_gd_edges": own["in_bwd_gd"] + own["in_bwd_edges"], "in_bwd_dasrc": own["in_bwd_dasrc"],
+                   "in_bwd_params": own["in_bwd_params"]}
+        kernels = {"in_logits": "in_logits_kernel", "in_fwd_edges": "gat_in_fwd_items (+hub chunks/merge)",
+                   "in_out_gemm": "in_out_gemm (tcgen05 kind::f16, bulk-fed)",
+                   "in_bwd_gd_edges": "gemm_tc_ws<2> (Gd) + gat_in_bwd_items (+hub)", "in_bwd_dasrc": "in_dasrc_kernel",
+                   "in_bwd_params": "in_dw_gemm (tcgen05 kind::f16, MN-major) + dax_partial"}
+    else:
+        own = roofline.stage_bytes(n_local, Ep, K, H, C, False, s_bytes, need_dx=False, n_src=(N if world > 1 else None))
+        stage_b = {"project_fwd": own["project_fwd"], "gat_fwd": own["gat_fwd"],
+                   "gat_bwd_dst_src": own["gat_bwd_dst"] + own["gat_bwd_src"], "project_bwd": own["project_bwd"]}
+        kernels = {"project_fwd": "tc::gemm_tc_ws2", "gat_fwd": "gat_fwd_items_pack (+hub chunks/merge)",
+                   "gat_bwd_dst_src": "gat_bwd_dst_items_pack (+hub) + gat_bwd_src_rows", "project_bwd": "tc::dw_tc2 + dax_partial"}
+    # dominant stage = the one with the largest measured time on this rank
+    dom = max(stages, key=lambda k: stage_ms[k])
+    dom_bytes, dom_ms = stage_b[dom], stage_ms[dom]
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "gat_fwd_items_pack (+hub chunks/merge)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
-            "layer": {"algorithmic_bytes": bmodel["total"], "achieved": bmodel["total"] / (ms_per_step * 1e-3) / 1e9 / world,
-                      "frac": bmodel["total"] / (ms_per_step * 1e-3) / 1e9 / world / peak},
-            "stages_ms": stage_ms,
-            "stages_gbs": {"project_fwd": local["project_fwd"] / stage_ms["project_fwd"] / 1e6,
-                           "gat_fwd": local["gat_fwd"] / stage_ms["gat_fwd"] / 1e6,
-                           "gat_bwd_dst_src": (local["gat_bwd_dst"] + local["gat_bwd_src"]) / stage_ms["gat_bwd_dst_src"] / 1e6,
-                           "project_bwd": local["project_bwd"] / stage_ms["project_bwd"] / 1e6}}
+    own_total = sum(stage_b.values())
+    traffic = None
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roof["traffic"] = json.load(open(traffic_file)).get(workload, {}).get("gat_fwd_rows")
+            traffic = json.load(open(traffic_file)).get(workload, {}).get(dom)
         except Exception:
-            pass
+            traffic = None
+    roof = {"bound": "hbm", "kernel": kernels[dom], "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dom_bytes, "ms_per_launch": dom_ms,
+            "formulation": "input-space (csrc/in_common.cuh)" if input_space else "projected-feature (PyG order of operations)",
+            "layer": {"algorithmic_bytes": bmodel["total"], "achieved": bmodel["total"] / (ms_per_step * 1e-3) / 1e9 / world,
+                      "frac": bmodel["total"] / (ms_per_step * 1e-3) / 1e9 / world / peak,
+                      "byte_model": "SURVEY.md 8(d), projected-feature formulation"},
+            "layer_own_model": {"algorithmic_bytes": own_total, "achieved": own_total / (ms_per_step * 1e-3) / 1e9,
+                                "frac": own_total / (ms_per_step * 1e-3) / 1e9 / peak,
+                                "byte_model": "bytes of the formulation that ran, this rank"},
+            "stages_ms": stage_ms,
+            "stages_gbs": {k: stage_b[k] / stage_ms[k] / 1e6 for k in stages}}
 
     value = E_total / (ms_per_step * 1e-3)
 
@@ -435,7 +478,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="powerlaw_200m", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", type=int, default=0, help="projection GEMM: 0 auto, 1 fp32 SIMT, 2 tensor core")
+    ap.add_argument("--algo", type=int, default=0, help="0 auto, 1 fp32 SIMT projection, 2 tensor-core projection, "
+                    "3 input-space formulation (first layer)")
     ap.add_argument("--bf16", action="store_true", help="bf16 storage of projected features")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -75,7 +75,8 @@ SIGNATURES = {
                                _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     # input-space formulation of the first layer
     "gnnfd_in_supported": (_i, [_i64, _i, _i, _i]),
-    "gnnfd_in_sizes": (_i, [_i64, _i64, _szp, _szp, _i64p]),
+    "gnnfd_in_sizes": (_i, [_i64, _i64, _szp, _szp, _i64p, _i64p]),
+    "gnnfd_in_pad_x": (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "gnnfd_in_logits": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gnnfd_in_prepare": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "gnnfd_in_fwd_workspace_bytes": (_i, [_gp, _szp]),

@@ -19,77 +19,78 @@ extern std::atomic<long long> g_launches;
 int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who);
 
 namespace in {
+bool in_x_ok(const float* x, int64_t ldx, int KP);   // gat_in_fwd.cu
+
 
 // per-warp scratch beyond the ring: dal_s [32][H] floats, bits_s [2][32] ints, the Gd row buffer [F] floats
 __host__ __device__ inline int bwd_extra_bytes(int F) { return 32 * H * 4 + 2 * 32 * 4 + F * 4; }
 
-// Gd row of the destination being processed: fetched with one bulk copy into shared memory (no registers in flight)
+// Gd row of the destination being processed: fetched with one bulk copy into shared memory (no registers in flight);
+// lane (h, q) then keeps the float4s 4*i + q of head h in registers
+template <int N4>
 struct GdBuf {
-    float* buf;
-    uint64_t* bar;
+    using RG = RowGeo<N4>;
+    uint32_t buf_u32, bar;
     const float* gd;
     int F, KP;
-    int pending = -1, loads = 0;
+    int pending = -1, loads = 0, deferred = -1;
+    // WAR hazard: the copy engine (async proxy) may overwrite the buffer while the ld.shared of take() are still in
+    // flight -- __syncwarp orders instruction issue, not load completion, and an L2-resident Gd row arrives within a few
+    // hundred cycles.  A prefetch that follows a take() is therefore only REQUESTED (want_later) and issued by
+    // flush() after the next edge has been processed: its FMAs consume every loaded register, so the loads have landed.
+    __device__ __forceinline__ void want_later(int row) { deferred = row; }
+    __device__ __forceinline__ void flush(int lane)
+    {
+        if (deferred >= 0) {
+            want(deferred, lane);
+            deferred = -1;
+        }
+    }
     __device__ __forceinline__ void want(int row, int lane)
     {
         if (pending == row) return;
         if (lane == 0) {
-            st_mbar_expect_tx(bar, uint32_t(F) * 4u);
-            st_bulk_g2s(buf, gd + int64_t(row) * F, uint32_t(F) * 4u, bar);
+            mbar_expect_tx_u32(bar, uint32_t(F) * 4u);
+            bulk_g2s_u32(buf_u32, gd + int64_t(row) * F, uint32_t(F) * 4u, bar);
         }
         pending = row;
     }
-    __device__ __forceinline__ void take(int row, int lane, float2 (&g)[H][NSLOT])
+    __device__ __forceinline__ void take(int row, int lane, float4 (&g)[RG::NI])
     {
+        deferred = -1;
         if (pending != row) {
             if (pending >= 0) {                 // a wrong guess is in flight: let it land before the buffer is reused
-                st_mbar_wait(bar, uint32_t(loads & 1));
+                mbar_wait_u32(bar, uint32_t(loads & 1));
                 ++loads;
                 __syncwarp();
                 pending = -1;
             }
             want(row, lane);
         }
-        st_mbar_wait(bar, uint32_t(loads & 1));
+        mbar_wait_u32(bar, uint32_t(loads & 1));
         ++loads;
+        const int h = lane >> 2, q = lane & 3, n4 = KP >> 2;
 #pragma unroll
-        for (int h = 0; h < H; ++h)
-#pragma unroll
-            for (int r = 0; r < NSLOT; ++r) {
-                const int k = 64 * r + 2 * lane;
-                g[h][r] = (k < KP) ? *reinterpret_cast<const float2*>(buf + h * KP + k) : make_float2(0.f, 0.f);
-            }
+        for (int i = 0; i < RG::NI; ++i)
+            g[i] = RG::valid(i, q, n4) ? lds128(buf_u32 + uint32_t(h * KP + 16 * i + 4 * q) * 4u) : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();                           // every lane has read the buffer before the next copy is issued
         pending = -1;
     }
 };
 
-// 8 per-lane partial dot products -> full warp sums; head (lane>>2)&7 in bit order b4 b3 b2 ends in the lanes of its quad
-__device__ __forceinline__ float reduce8(const float (&d)[H], int lane)
-{
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-    float a[4], b[2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = (b4 ? d[4 + i] : d[i]) + __shfl_xor_sync(FULL, b4 ? d[i] : d[4 + i], 16);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) b[i] = (b3 ? a[2 + i] : a[i]) + __shfl_xor_sync(FULL, b3 ? a[i] : a[2 + i], 8);
-    float c = (b2 ? b[1] : b[0]) + __shfl_xor_sync(FULL, b2 ? b[0] : b[1], 4);
-    c += __shfl_xor_sync(FULL, c, 2);
-    c += __shfl_xor_sync(FULL, c, 1);
-    return c;
-}
-
 // HUB = false: whole rows (optionally packs of short rows), results go to da_dst.  HUB = true: one (row, range) segment,
 // the partial t of the segment goes to part_t[chunk_id]; the second sweep is a separate kernel.
-template <bool VEC2, bool DROPOUT, bool PACK, bool HUB>
-__device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, GdBuf& gdb, const int32_t* __restrict__ rowptr,
+template <int N4, bool DROPOUT, bool PACK, bool HUB>
+__device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, GdBuf<N4>& gdb, const int32_t* __restrict__ rowptr,
                                               const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                                              const int32_t* __restrict__ csr2csc, int K, const float* __restrict__ a_src,
+                                              const int32_t* __restrict__ csr2csc, const float* __restrict__ a_src,
                                               const float* __restrict__ a_dst, const float* __restrict__ rowmax,
                                               const float* __restrict__ rowsum, float slope, const uint8_t* __restrict__ keep,
                                               float keep_scale, float* __restrict__ dz, float* __restrict__ da_dst,
                                               float* __restrict__ part_t, int chunk_id, int lane)
 {
+    using RG = RowGeo<N4>;
+    const int h = lane >> 2, q = lane & 3, n4 = gdb.KP >> 2;
     float* dal_s = reinterpret_cast<float*>(ring.extra);
     int* bits_s = reinterpret_cast<int*>(ring.extra + 32 * H * 4);
     auto on_empty = [&](int r) {
@@ -114,14 +115,14 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
     if (!kind0) return;
     gdb.want(c0.row, lane);
     phase_a(c0, kind0, k0, b0);
-    float2 g[H][NSLOT];
+    float4 g[RG::NI];
     gdb.take(c0.row, lane, g);
-    if (PACK && kind0 == 2 && k0 > 1) gdb.want(c0.row + 1, lane);
+    if (PACK && kind0 == 2 && k0 > 1) gdb.want_later(c0.row + 1);
     int issued0 = 0, issued1 = 0;
     float trow[H];
     int row_beg = c0.beg;
 #pragma unroll
-    for (int h = 0; h < H; ++h) trow[h] = 0.f;
+    for (int hh = 0; hh < H; ++hh) trow[hh] = 0.f;
     while (true) {
         const int* j0 = ring.j_s + b0 * 32;
         const int* j1 = ring.j_s + (b0 ^ 1) * 32;
@@ -131,39 +132,40 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
         if (kind1) {
             phase_a(c1, kind1, k1, b0 ^ 1);
             // the next destination row in stream order, unless a row of the current pack is still to come
-            if (c1.first && gdb.pending < 0 && !(PACK && kind0 == 2 && k0 > 1)) gdb.want(c1.row, lane);
+            if (c1.first && gdb.pending < 0 && gdb.deferred < 0 && !(PACK && kind0 == 2 && k0 > 1)) gdb.want_later(c1.row);
         }
         if (c0.first) {
             row_beg = c0.beg;
 #pragma unroll
-            for (int h = 0; h < H; ++h) trow[h] = 0.f;
+            for (int hh = 0; hh < H; ++hh) trow[hh] = 0.f;
         }
         int rows_done = 0;
         const int* bits0 = bits_s + b0 * 32;
-        // phase B: dot products of the staged x rows with this row's Gd
+        // phase B: dot products of the staged x rows with this row's Gd (lane = head, quarter)
         for (int t = 0; t < c0.n; ++t) {
-            const float* row = ring.front(j0[t]);
-            float2 v[NSLOT];
-            load_xrow<VEC2>(row, lane, K, v);
-            float d[H];
+            const uint32_t a = ring.front() + uint32_t(q) * 16u;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;     // four independent FMA chains
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                float s = 0.f;
-#pragma unroll
-                for (int r = 0; r < NSLOT; ++r) s = fmaf(g[h][r].x, v[r].x, fmaf(g[h][r].y, v[r].y, s));
-                d[h] = s;
-            }
-            const float tot = reduce8(d, lane);
-            if ((lane & 3) == 0) dal_s[t * H + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = tot;
+            for (int i = 0; i < RG::NI; ++i)
+                if (RG::valid(i, q, n4)) {
+                    const float4 v = lds128(a + uint32_t(i) * 64u);
+                    d0 = fmaf(g[i].x, v.x, d0); d1 = fmaf(g[i].y, v.y, d1);
+                    d2 = fmaf(g[i].z, v.z, d2); d3 = fmaf(g[i].w, v.w, d3);
+                }
+            float d = (d0 + d1) + (d2 + d3);
+            d += __shfl_xor_sync(FULL, d, 1);
+            d += __shfl_xor_sync(FULL, d, 2);
+            if (q == 0) dal_s[t * H + h] = d;
             ring.pop();
+            gdb.flush(lane);                 // every lane has consumed g in the FMAs above
             if (issued0 < c0.n) ring.issue(j0[issued0++], lane);
             else if (kind1 && issued1 < c1.n) ring.issue(j1[issued1++], lane);
             if (PACK && kind0 == 2 && t + 1 < c0.n && ((bits0[t] >> 26) & 1)) {
                 // row boundary inside the pack: switch to the next row's Gd, prefetch the one after it
                 ++rows_done;
                 gdb.take(c0.row + rows_done, lane, g);
-                if (rows_done + 1 < k0) gdb.want(c0.row + rows_done + 1, lane);
-                else if (kind1 && c1.first) gdb.want(c1.row, lane);
+                if (rows_done + 1 < k0) gdb.want_later(c0.row + rows_done + 1);
+                else if (kind1 && c1.first) gdb.want_later(c1.row);
             }
         }
         __syncwarp();
@@ -182,20 +184,20 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
             const bool live = lane < c0.n;
             const int64_t pos = live ? csr2csc[c0.beg + lane] : 0;    // source-major slot of this edge
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const float ks = (bits >> (8 + h)) & 1 ? keep_scale : 0.f;
-                u[h] = live ? alpha[h] * dal[h] * ks : 0.f;
+            for (int hh = 0; hh < H; ++hh) {
+                const float ks = (bits >> (8 + hh)) & 1 ? keep_scale : 0.f;
+                u[hh] = live ? alpha[hh] * dal[hh] * ks : 0.f;
             }
             if (PACK && kind0 == 2) {
                 const int sa = (bits >> 16) & 31, sb = live ? (bits >> 21) & 31 : lane;
                 const bool lastf = live && ((bits >> 26) & 1);
                 float o[H], dad[H];
 #pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    const float tt = seg_total(u[h], sa, sb, lane);
-                    const float sl = (bits >> h) & 1 ? 1.f : slope;
-                    o[h] = live ? sl * (u[h] - alpha[h] * tt) : 0.f;
-                    dad[h] = seg_total(o[h], sa, sb, lane);
+                for (int hh = 0; hh < H; ++hh) {
+                    const float tt = seg_total(u[hh], sa, sb, lane);
+                    const float sl = (bits >> hh) & 1 ? 1.f : slope;
+                    o[hh] = live ? sl * (u[hh] - alpha[hh] * tt) : 0.f;
+                    dad[hh] = seg_total(o[hh], sa, sb, lane);
                 }
                 if (live) store_vecH<H>(dz + pos * H, o);
                 const unsigned lastm = __ballot_sync(FULL, lastf);
@@ -206,18 +208,18 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
             } else if (!HUB && c0.first && c0.last) {
                 float o[H], dad[H];
 #pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    const float tt = warp_sum(u[h]);
-                    const float sl = (bits >> h) & 1 ? 1.f : slope;
-                    o[h] = live ? sl * (u[h] - alpha[h] * tt) : 0.f;
-                    dad[h] = warp_sum(o[h]);
+                for (int hh = 0; hh < H; ++hh) {
+                    const float tt = warp_sum(u[hh]);
+                    const float sl = (bits >> hh) & 1 ? 1.f : slope;
+                    o[hh] = live ? sl * (u[hh] - alpha[hh] * tt) : 0.f;
+                    dad[hh] = warp_sum(o[hh]);
                 }
                 if (live) store_vecH<H>(dz + pos * H, o);
                 if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
             } else {
                 if (live) store_vecH<H>(dz + pos * H, u);       // parked until t is known
 #pragma unroll
-                for (int h = 0; h < H; ++h) trow[h] += warp_sum(u[h]);
+                for (int hh = 0; hh < H; ++hh) trow[hh] += warp_sum(u[hh]);
                 if (c0.last) {
                     if (HUB) {
                         if (lane == 0) store_vecH<H>(part_t + int64_t(chunk_id) * H, trow);
@@ -227,10 +229,10 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
                         load_row_stat<H>(r, c0.row, a_dst, rowmax, rowsum);
                         float dad[H];
 #pragma unroll
-                        for (int h = 0; h < H; ++h) dad[h] = 0.f;
+                        for (int hh = 0; hh < H; ++hh) dad[hh] = 0.f;
                         dst_sweep2<GI>(r, row_beg, c0.beg + c0.n, col, csr2csc, a_src, slope, trow, lane, dz, H, dad);
 #pragma unroll
-                        for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
+                        for (int hh = 0; hh < H; ++hh) dad[hh] = warp_sum(dad[hh]);
                         if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
                     }
                 }
@@ -240,7 +242,7 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
         if (!kind1) break;
         if (c1.first) {
             gdb.take(c1.row, lane, g);
-            if (PACK && kind1 == 2 && k1 > 1) gdb.want(c1.row + 1, lane);
+            if (PACK && kind1 == 2 && k1 > 1) gdb.want_later(c1.row + 1);
         }
         c0 = c1;
         kind0 = kind1;
@@ -250,19 +252,20 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
     }
 }
 
-__device__ __forceinline__ void gdbuf_init(GdBuf& gdb, InRing& ring, const float* gd, int F, int KP)
+template <int N4>
+__device__ __forceinline__ void gdbuf_init(GdBuf<N4>& gdb, InRing& ring, const float* gd, int F, int KP)
 {
-    gdb.buf = reinterpret_cast<float*>(ring.extra + 32 * H * 4 + 2 * 32 * 4);
-    gdb.bar = &ring.full[IN_R];
+    gdb.buf_u32 = st_smem_u32(ring.extra + 32 * H * 4 + 2 * 32 * 4);
+    gdb.bar = ring.spare_bar();
     gdb.gd = gd;
     gdb.F = F;
     gdb.KP = KP;
 }
 
-template <bool VEC2, bool DROPOUT, bool PACK>
+template <int N4, bool DROPOUT, bool PACK>
 __global__ void __launch_bounds__(IN_THREADS, 3)
 gat_in_bwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                 const int32_t* __restrict__ csr2csc, const float* __restrict__ x, int64_t ldx, int K,
+                 const int32_t* __restrict__ csr2csc, const float* __restrict__ x, int64_t ldx, int KP,
                  const float* __restrict__ a_src, const float* __restrict__ a_dst, const float* __restrict__ rowmax,
                  const float* __restrict__ rowsum, const float* __restrict__ gd, gnnfd_item_plan_t items, int item_lo,
                  int item_hi, int hub_threshold, float slope, const uint8_t* __restrict__ keep, float keep_scale,
@@ -272,22 +275,22 @@ gat_in_bwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int item = item_lo + blockIdx.x * IN_WARPS + warp;
     if (item >= item_hi) return;
-    const Dims d(K);
+    const int F = H * KP;
     InRing ring;
-    ring.init(smem + warp * in_warp_bytes(K, bwd_extra_bytes(d.F)), x, ldx, K, lane);
-    GdBuf gdb;
-    gdbuf_init(gdb, ring, gd, d.F, d.KP);
+    ring.init(smem + warp * in_warp_bytes(KP, bwd_extra_bytes(F)), x, ldx, KP, lane);
+    GdBuf<N4> gdb;
+    gdbuf_init(gdb, ring, gd, F, KP);
     ChunkCursor cur;
     cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
-    in_bwd_stream<VEC2, DROPOUT, PACK, false>(cur, ring, gdb, rowptr, col, perm, csr2csc, K, a_src, a_dst, rowmax, rowsum, slope,
-                                              keep, keep_scale, dz, da_dst, nullptr, 0, lane);
+    in_bwd_stream<N4, DROPOUT, PACK, false>(cur, ring, gdb, rowptr, col, perm, csr2csc, a_src, a_dst, rowmax, rowsum, slope, keep,
+                                            keep_scale, dz, da_dst, nullptr, 0, lane);
 }
 
 // hub rows, step 1: one warp per chunk -- first sweep, partial t (rows outside [row_lo, row_hi) belong to another block)
-template <bool VEC2, bool DROPOUT>
+template <int N4, bool DROPOUT>
 __global__ void __launch_bounds__(IN_THREADS, 3)
 gat_in_bwd_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                const int32_t* __restrict__ csr2csc, const float* __restrict__ x, int64_t ldx, int K,
+                const int32_t* __restrict__ csr2csc, const float* __restrict__ x, int64_t ldx, int KP,
                 const float* __restrict__ a_src, const float* __restrict__ a_dst, const float* __restrict__ rowmax,
                 const float* __restrict__ rowsum, const float* __restrict__ gd, gnnfd_hub_plan_t plan, int row_lo, int row_hi,
                 float slope, const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ dz,
@@ -302,15 +305,15 @@ gat_in_bwd_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
     if (i < row_lo || i >= row_hi) return;
     const int beg = rowptr[i] + (c - plan.hub_chunk_ptr[slot]) * plan.chunk;
     const int end = min(rowptr[i + 1], beg + plan.chunk);
-    const Dims d(K);
+    const int F = H * KP;
     InRing ring;
-    ring.init(smem + warp * in_warp_bytes(K, bwd_extra_bytes(d.F)), x, ldx, K, lane);
-    GdBuf gdb;
-    gdbuf_init(gdb, ring, gd, d.F, d.KP);
+    ring.init(smem + warp * in_warp_bytes(KP, bwd_extra_bytes(F)), x, ldx, KP, lane);
+    GdBuf<N4> gdb;
+    gdbuf_init(gdb, ring, gd, F, KP);
     ChunkCursor cur;
     cur.start_segment(i, beg, end);
-    in_bwd_stream<VEC2, DROPOUT, false, true>(cur, ring, gdb, rowptr, col, perm, csr2csc, K, a_src, a_dst, rowmax, rowsum, slope,
-                                              keep, keep_scale, dz, nullptr, part_t, c, lane);
+    in_bwd_stream<N4, DROPOUT, false, true>(cur, ring, gdb, rowptr, col, perm, csr2csc, a_src, a_dst, rowmax, rowsum, slope, keep,
+                                            keep_scale, dz, nullptr, part_t, c, lane);
 }
 
 template <class Kn>
@@ -347,7 +350,7 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
 {
     int rc = check_graph(g, true, "in_bwd_edges");
     if (rc) return rc;
-    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && ldx >= K, GNNFD_ERR_ARG, "in_bwd_edges: bad shape (K <= %d)", MAX_K);
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K, GNNFD_ERR_ARG, "in_bwd_edges: bad shape (K <= %d)", MAX_K);
     if (g->n_dst == 0) return GNNFD_OK;
     GNNFD_REQUIRE(x && a_src && a_dst && rowmax && rowsum && gd && da_dst, GNNFD_ERR_ARG, "in_bwd_edges: NULL tensor");
     GNNFD_REQUIRE(g->n_edges == 0 || (dz && g->csr2csc), GNNFD_ERR_ARG, "in_bwd_edges: dz / csr2csc is NULL");
@@ -362,8 +365,9 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
     const bool drop = keep_mask != nullptr && p_drop > 0.f;
     const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
     const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
-    const bool v2 = (d.K % 2 == 0) && (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
-    const int smem = IN_WARPS * in_warp_bytes(d.K, bwd_extra_bytes(d.F));
+    GNNFD_REQUIRE(in_x_ok(x, ldx, d.KP), GNNFD_ERR_ARG,
+                  "in_bwd_edges: x rows must be 16-byte aligned and zero-padded to %d floats (gnnfd_in_pad_x)", d.KP);
+    const int smem = IN_WARPS * in_warp_bytes(d.KP, bwd_extra_bytes(d.F));
     const float* gd0 = gd - gd_row0 * d.F;          // indexed by global destination row
     const gnnfd_hub_plan_t& pl = g->hub_dst;
     float *part_t = nullptr, *part_dad = nullptr, *t_total = nullptr;
@@ -382,34 +386,33 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
     }();
     if ((phase & 1) && item_hi > item_lo) {
         const unsigned grid = (unsigned)((item_hi - item_lo + IN_WARPS - 1) / IN_WARPS);
-#define GNNFD_IN_BWD(VV, DD, PP)                                                                                       \
-    rc = in_set_smem_bwd(gat_in_bwd_items<VV, DD, PP>, smem);                                                          \
+        const unsigned gc = (unsigned)((pl.n_chunk + IN_WARPS - 1) / IN_WARPS);
+#define GNNFD_IN_BWD(NN, DD, PP)                                                                                       \
+    rc = in_set_smem_bwd(gat_in_bwd_items<NN, DD, PP>, smem);                                                          \
     if (rc) return rc;                                                                                                 \
-    gat_in_bwd_items<VV, DD, PP><<<grid, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, x, ldx, d.K, a_src, \
+    gat_in_bwd_items<NN, DD, PP><<<grid, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, x, ldx, d.KP, a_src, \
                                                                  a_dst, rowmax, rowsum, gd0, g->items_dst, (int)item_lo,   \
                                                                  (int)item_hi, thr, negative_slope, keep_mask, ks, dz, da_dst)
-        if (pack) {
-            if (v2) { if (drop) { GNNFD_IN_BWD(true, true, true); } else { GNNFD_IN_BWD(true, false, true); } }
-            else    { if (drop) { GNNFD_IN_BWD(false, true, true); } else { GNNFD_IN_BWD(false, false, true); } }
-        } else {
-            if (v2) { if (drop) { GNNFD_IN_BWD(true, true, false); } else { GNNFD_IN_BWD(true, false, false); } }
-            else    { if (drop) { GNNFD_IN_BWD(false, true, false); } else { GNNFD_IN_BWD(false, false, false); } }
-        }
-#undef GNNFD_IN_BWD
-        g_launches += 1;
-        if (pl.n_hub > 0) {
-            const unsigned gc = (unsigned)((pl.n_chunk + IN_WARPS - 1) / IN_WARPS);
-#define GNNFD_IN_HUB1(VV, DD)                                                                                          \
-    rc = in_set_smem_bwd(gat_in_bwd_hub1<VV, DD>, smem);                                                               \
+#define GNNFD_IN_HUB1(NN, DD)                                                                                          \
+    rc = in_set_smem_bwd(gat_in_bwd_hub1<NN, DD>, smem);                                                               \
     if (rc) return rc;                                                                                                 \
-    gat_in_bwd_hub1<VV, DD><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, x, ldx, d.K, a_src, a_dst,  \
+    gat_in_bwd_hub1<NN, DD><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, x, ldx, d.KP, a_src, a_dst, \
                                                           rowmax, rowsum, gd0, pl, (int)row_lo, (int)row_hi, negative_slope, \
                                                           keep_mask, ks, dz, part_t)
-            if (v2) { if (drop) { GNNFD_IN_HUB1(true, true); } else { GNNFD_IN_HUB1(true, false); } }
-            else    { if (drop) { GNNFD_IN_HUB1(false, true); } else { GNNFD_IN_HUB1(false, false); } }
+#define GNNFD_IN_BWD_ALL(NN)                                                                                           \
+    if (pack) { if (drop) { GNNFD_IN_BWD(NN, true, true); } else { GNNFD_IN_BWD(NN, false, true); } }                  \
+    else      { if (drop) { GNNFD_IN_BWD(NN, true, false); } else { GNNFD_IN_BWD(NN, false, false); } }                \
+    g_launches += 1;                                                                                                   \
+    if (pl.n_hub > 0) {                                                                                                \
+        if (drop) { GNNFD_IN_HUB1(NN, true); } else { GNNFD_IN_HUB1(NN, false); }                                      \
+        g_launches += 1;                                                                                               \
+    }
+        if (d.KP == 168) { GNNFD_IN_BWD_ALL(42) }
+        else if (d.KP == 64) { GNNFD_IN_BWD_ALL(16) }
+        else { GNNFD_IN_BWD_ALL(0) }
+#undef GNNFD_IN_BWD_ALL
 #undef GNNFD_IN_HUB1
-            g_launches += 1;
-        }
+#undef GNNFD_IN_BWD
     }
     if ((phase & 2) && pl.n_hub > 0) {
         const unsigned gh = (unsigned)((pl.n_hub + ROW_WARPS - 1) / ROW_WARPS);

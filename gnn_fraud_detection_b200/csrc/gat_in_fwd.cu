@@ -38,61 +38,98 @@ __global__ void in_u_kernel(const float* __restrict__ W, const float* __restrict
     }
 }
 
-// 16 per-lane values -> the full warp sums, value o ends up in the lanes with (lane >> 1) == o (both lanes of the pair)
-__device__ __forceinline__ float reduce16(float (&d)[16], int lane)
-{
-    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-    float a[8], b[4], c[2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = (b4 ? d[8 + i] : d[i]) + __shfl_xor_sync(FULL, b4 ? d[i] : d[8 + i], 16);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) b[i] = (b3 ? a[4 + i] : a[i]) + __shfl_xor_sync(FULL, b3 ? a[i] : a[4 + i], 8);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) c[i] = (b2 ? b[2 + i] : b[i]) + __shfl_xor_sync(FULL, b2 ? b[i] : b[2 + i], 4);
-    float r = (b1 ? c[1] : c[0]) + __shfl_xor_sync(FULL, b1 ? c[0] : c[1], 2);
-    r += __shfl_xor_sync(FULL, r, 1);
-    return r;
-}
-
-// a_src[n,h] = x[n,:] . u[h,:], a_dst[n,h] = x[n,:] . u[H+h,:]; warp per row, lanes over features
-template <bool VEC2>
-__global__ void __launch_bounds__(256, 2)
-in_logits_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int K, const float* __restrict__ u, int KP,
+// a_src[n,h] = x[n,:] . u[h,:], a_dst[n,h] = x[n,:] . u[H+h,:].  The CTA streams tiles of 64 consecutive rows through
+// shared memory (ONE bulk copy per tile, double-buffered); lane = (head h, quarter q) as in the edge kernels: 44 + 44
+// u values in registers, per row 11 shared loads, 88 FMAs and two 2-step quad reductions.  Also max |x|.
+constexpr int LG_ROWS = 64, LG_WARPS = 8;
+template <int N4>
+__global__ void __launch_bounds__(LG_WARPS * 32, 2)
+in_logits_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int KP, const float* __restrict__ u,
                  float* __restrict__ a_src, float* __restrict__ a_dst, unsigned* __restrict__ xmax_bits)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2 uu[2 * H][NSLOT];
+    using RG = RowGeo<N4>;
+    extern __shared__ __align__(128) uint8_t lsm[];
+    __shared__ uint64_t full[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h = lane >> 2, q = lane & 3;
+    const int n4 = KP >> 2;
+    const uint32_t rowb = uint32_t(KP) * 4u;
+    const bool dense = (ldx == KP);                    // a tile is one contiguous block
+    float4 us[RG::NI], ud[RG::NI];
 #pragma unroll
-    for (int o = 0; o < 2 * H; ++o)
-#pragma unroll
-        for (int r = 0; r < NSLOT; ++r) {
-            const int f = 64 * r + 2 * lane;
-            uu[o][r].x = (f < K) ? u[o * KP + f] : 0.f;
-            uu[o][r].y = (f + 1 < K) ? u[o * KP + f + 1] : 0.f;
+    for (int i = 0; i < RG::NI; ++i) {
+        us[i] = ud[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (RG::valid(i, q, n4)) {
+            us[i] = *reinterpret_cast<const float4*>(u + h * KP + 16 * i + 4 * q);
+            ud[i] = *reinterpret_cast<const float4*>(u + (H + h) * KP + 16 * i + 4 * q);
         }
+    }
+    if (tid == 0) {
+        st_mbar_init(&full[0], 1);
+        st_mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t n_tiles = (N + LG_ROWS - 1) / LG_ROWS;
+    const uint32_t buf_bytes = LG_ROWS * rowb;
+    auto load_tile = [&](int64_t t, int b) {           // thread 0
+        const int64_t r0 = t * LG_ROWS;
+        const int rows = int(N - r0 < LG_ROWS ? N - r0 : LG_ROWS);
+        const uint32_t bar = st_smem_u32(&full[b]);
+        mbar_expect_tx_u32(bar, uint32_t(rows) * rowb);
+        if (dense) bulk_g2s_u32(st_smem_u32(lsm) + b * buf_bytes, x + r0 * ldx, uint32_t(rows) * rowb, bar);
+        else
+            for (int r = 0; r < rows; ++r) bulk_g2s_u32(st_smem_u32(lsm) + b * buf_bytes + r * rowb, x + (r0 + r) * ldx, rowb, bar);
+    };
     float mx = 0.f;
-    for (int64_t n = int64_t(blockIdx.x) * 8 + warp; n < N; n += int64_t(gridDim.x) * 8) {
-        float2 v[NSLOT];
-        load_xrow<VEC2>(x + n * ldx, lane, K, v);
-        float d[2 * H];
+    int64_t it = 0;
+    if (tid == 0 && blockIdx.x < n_tiles) load_tile(blockIdx.x, 0);
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+        const int b = int(it & 1);
+        if (tid == 0 && t + gridDim.x < n_tiles) load_tile(t + gridDim.x, b ^ 1);   // buffer b^1 was released by the barrier below
+        mbar_wait_u32(st_smem_u32(&full[b]), uint32_t((it >> 1) & 1));
+        const int64_t r0 = t * LG_ROWS;
+        const int rows = int(N - r0 < LG_ROWS ? N - r0 : LG_ROWS);
+        for (int r = warp; r < rows; r += LG_WARPS) {
+            const uint32_t a = st_smem_u32(lsm) + b * buf_bytes + r * rowb;
+            float ds = 0.f, dd = 0.f;
 #pragma unroll
-        for (int o = 0; o < 2 * H; ++o) {
-            float s = 0.f;
-#pragma unroll
-            for (int r = 0; r < NSLOT; ++r) s = fmaf(uu[o][r].x, v[r].x, fmaf(uu[o][r].y, v[r].y, s));
-            d[o] = s;
+            for (int i = 0; i < RG::NI; ++i)
+                if (RG::valid(i, q, n4)) {
+                    const float4 v = lds128(a + uint32_t(4 * i + q) * 16u);
+                    ds = fmaf(us[i].x, v.x, fmaf(us[i].y, v.y, fmaf(us[i].z, v.z, fmaf(us[i].w, v.w, ds))));
+                    dd = fmaf(ud[i].x, v.x, fmaf(ud[i].y, v.y, fmaf(ud[i].z, v.z, fmaf(ud[i].w, v.w, dd))));
+                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                }
+            ds += __shfl_xor_sync(FULL, ds, 1); dd += __shfl_xor_sync(FULL, dd, 1);
+            ds += __shfl_xor_sync(FULL, ds, 2); dd += __shfl_xor_sync(FULL, dd, 2);
+            if (q == 0) {
+                a_src[(r0 + r) * H + h] = ds;
+                a_dst[(r0 + r) * H + h] = dd;
+            }
         }
-#pragma unroll
-        for (int r = 0; r < NSLOT; ++r) mx = fmaxf(mx, fmaxf(fabsf(v[r].x), fabsf(v[r].y)));
-        const float r = reduce16(d, lane);
-        if ((lane & 1) == 0) {
-            const int o = lane >> 1;
-            if (o < H) a_src[n * H + o] = r;
-            else a_dst[n * H + (o - H)] = r;
-        }
+        __syncthreads();                                // every warp is done with buffer b
     }
     mx = warp_max(mx);
     if (lane == 0 && mx > 0.f) atomicMax(xmax_bits, __float_as_uint(mx));   // non-negative floats order like their bits
+}
+
+// x16 [N, KP] = x [N, K] zero-padded to KP = round_up(K, 8) floats per row (16-byte aligned rows for the bulk copies)
+__global__ void in_pad_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int K, int KP, float* __restrict__ x16)
+{
+    const int n4 = KP >> 2;
+    const int64_t total = N * n4;
+    for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total; idx += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t n = idx / n4;
+        const int k = int(idx - n * n4) * 4;
+        const float* p = x + n * ldx + k;
+        float4 v;
+        v.x = (k < K) ? p[0] : 0.f;
+        v.y = (k + 1 < K) ? p[1] : 0.f;
+        v.z = (k + 2 < K) ? p[2] : 0.f;
+        v.w = (k + 3 < K) ? p[3] : 0.f;
+        *reinterpret_cast<float4*>(x16 + n * KP + k) = v;
+    }
 }
 
 // scal[0] = sx, [1] = sw, [2] = 1/(sx*sw*H), [3] = 1/sx;  one block
@@ -137,99 +174,87 @@ __global__ void in_wout_image_kernel(const float* __restrict__ W, int K, int KP,
 }
 
 // ---- sinks: what happens when a row (or a hub chunk) is complete --------------------------------------------------------
+// lane (h, q) holds acc[i] = the float4 16*i + 4*q .. +4 of head h's aggregated input
+template <int N4>
 struct ZSink {      // normalise, save the row statistics, write the row of the fp16-pair image
+    using RG = RowGeo<N4>;
     uint8_t* zimg; float* rowmax; float* rowsum; const float* scal; int KP, NKB;
-    __device__ __forceinline__ void write_row(int row, float2 (&acc)[H][NSLOT], const float (&inv)[H], int lane) const
+    __device__ __forceinline__ void write_row(int row, float4 (&acc)[RG::NI], float inv, int lane) const
     {
-        const float sx = scal[0];
-        const int rr = row & (TILE - 1);
-        uint8_t* base = zimg + size_t(row >> 7) * size_t(NKB) * KBLOCK + uint32_t(rr >> 3) * 1024u + uint32_t(rr & 7) * 128u;
+        const int h = lane >> 2, q = lane & 3, n4 = KP >> 2;
+        const float f = inv * scal[0];
+        const uint32_t rr = uint32_t(row) & (TILE - 1);
+        uint8_t* base = zimg + size_t(row >> 7) * size_t(NKB) * KBLOCK + (rr >> 3) * 1024u + (rr & 7u) * 128u;
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-            const float f = inv[h] * sx;
-#pragma unroll
-            for (int r = 0; r < NSLOT; ++r) {
-                const int k = 64 * r + 2 * lane;
-                if (k < KP) {
-                    const int ft = h * KP + k, kb = ft >> 6, e = ft & 63;
-                    __half2 hi, lo;
-                    split_h2(acc[h][r].x * f, acc[h][r].y * f, hi, lo);
-                    uint8_t* p = base + size_t(kb) * KBLOCK + ((uint32_t(e >> 3) ^ uint32_t(rr & 7)) << 4) + uint32_t(e & 7) * 2u;
-                    *reinterpret_cast<__half2*>(p) = hi;
-                    *reinterpret_cast<__half2*>(p + PLANE) = lo;
-                }
+        for (int i = 0; i < RG::NI; ++i)
+            if (RG::valid(i, q, n4)) {
+                // 4 consecutive features = half a 16-byte chunk; the 4 q-lanes of a head fill one 32-byte sector per plane
+                const uint32_t ft = uint32_t(h * KP + 16 * i + 4 * q), kb = ft >> 6, e = ft & 63u;
+                __half2 h0, l0, h1, l1;
+                split_h2(acc[i].x * f, acc[i].y * f, h0, l0);
+                split_h2(acc[i].z * f, acc[i].w * f, h1, l1);
+                uint8_t* p = base + size_t(kb) * KBLOCK + (((e >> 3) ^ (rr & 7u)) << 4) + (e & 7u) * 2u;
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<uint32_t*>(&h0); hv.y = *reinterpret_cast<uint32_t*>(&h1);
+                lv.x = *reinterpret_cast<uint32_t*>(&l0); lv.y = *reinterpret_cast<uint32_t*>(&l1);
+                *reinterpret_cast<uint2*>(p) = hv;
+                *reinterpret_cast<uint2*>(p + PLANE) = lv;
             }
-        }
     }
-    __device__ __forceinline__ void finish(int row, const float (&m)[H], const float (&s)[H], float2 (&acc)[H][NSLOT], int lane) const
+    __device__ __forceinline__ void finish(int row, float m, float s, float4 (&acc)[RG::NI], int lane) const
     {
-        float st[H], inv[H];
-#pragma unroll
-        for (int h = 0; h < H; ++h) {
-            st[h] = s[h] + 1e-16f;        // PyG softmax: out / (sum + 1e-16)
-            inv[h] = 1.f / st[h];
+        const float st = s + 1e-16f;                       // PyG softmax: out / (sum + 1e-16)
+        if ((lane & 3) == 0) {
+            rowmax[int64_t(row) * H + (lane >> 2)] = m;
+            rowsum[int64_t(row) * H + (lane >> 2)] = st;
         }
-        if (lane == 0) {
-            store_vecH<H>(rowmax + int64_t(row) * H, m);
-            store_vecH<H>(rowsum + int64_t(row) * H, st);
-        }
-        write_row(row, acc, inv, lane);
+        write_row(row, acc, 1.f / st, lane);
     }
-    __device__ __forceinline__ void finish_norm(int row, float2 (&acc)[H][NSLOT], int lane) const
-    {
-        float inv[H];
-#pragma unroll
-        for (int h = 0; h < H; ++h) inv[h] = 1.f;
-        write_row(row, acc, inv, lane);
-    }
+    __device__ __forceinline__ void finish_norm(int row, float4 (&acc)[RG::NI], int lane) const { write_row(row, acc, 1.f, lane); }
     __device__ __forceinline__ void empty(int row, int lane) const
     {
-        float m[H], s[H];
-        float2 acc[H][NSLOT];
+        float4 acc[RG::NI];
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-            m[h] = 0.f; s[h] = 0.f;
-#pragma unroll
-            for (int r = 0; r < NSLOT; ++r) acc[h][r] = make_float2(0.f, 0.f);
-        }
-        finish(row, m, s, acc, lane);
+        for (int i = 0; i < RG::NI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        finish(row, 0.f, 0.f, acc, lane);
     }
 };
-constexpr int PART_ACC = H * NSLOT * 64;     // floats of one partial accumulator set
+template <int N4>
 struct ZPartialSink {   // hub chunk c: unnormalised partial (m, s, acc)
+    using RG = RowGeo<N4>;
+    static constexpr int PART_ACC = RG::NI * 32 * 4;      // floats of one partial accumulator set
     float* part_ms; float* part_acc; int c;
-    __device__ __forceinline__ void finish(int, const float (&m)[H], const float (&s)[H], float2 (&acc)[H][NSLOT], int lane) const
+    __device__ __forceinline__ void finish(int, float m, float s, float4 (&acc)[RG::NI], int lane) const
     {
-        if (lane == 0) {
-            store_vecH<H>(part_ms + int64_t(c) * 2 * H, m);
-            store_vecH<H>(part_ms + int64_t(c) * 2 * H + H, s);
+        if ((lane & 3) == 0) {
+            part_ms[int64_t(c) * 2 * H + (lane >> 2)] = m;
+            part_ms[int64_t(c) * 2 * H + H + (lane >> 2)] = s;
         }
-        float2* p = reinterpret_cast<float2*>(part_acc + int64_t(c) * PART_ACC);
+        float4* p = reinterpret_cast<float4*>(part_acc + int64_t(c) * PART_ACC);
 #pragma unroll
-        for (int h = 0; h < H; ++h)
-#pragma unroll
-            for (int r = 0; r < NSLOT; ++r) p[(h * NSLOT + r) * 32 + lane] = acc[h][r];
+        for (int i = 0; i < RG::NI; ++i) p[i * 32 + lane] = acc[i];
     }
-    __device__ __forceinline__ void finish_norm(int, float2 (&)[H][NSLOT], int) const {}
+    __device__ __forceinline__ void finish_norm(int, float4 (&)[RG::NI], int) const {}
     __device__ __forceinline__ void empty(int, int) const {}
 };
 
-__device__ __forceinline__ void acc_zero(float2 (&acc)[H][NSLOT])
+template <int NI>
+__device__ __forceinline__ void acc_zero(float4 (&acc)[NI])
 {
 #pragma unroll
-    for (int h = 0; h < H; ++h)
-#pragma unroll
-        for (int r = 0; r < NSLOT; ++r) acc[h][r] = make_float2(0.f, 0.f);
+    for (int i = 0; i < NI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // The stream loop (PACK: packs of whole short rows share one phase A, as in gat_fwd_items_pack).
-template <bool VEC2, bool DROPOUT, bool PACK, class Sink>
+template <int N4, bool DROPOUT, bool PACK, class Sink>
 __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, const Sink& sink, float* rowmax, float* rowsum,
                                               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                              const int32_t* __restrict__ perm, int K, const float* __restrict__ a_src,
+                                              const int32_t* __restrict__ perm, int n4, const float* __restrict__ a_src,
                                               const float* __restrict__ a_dst, float slope, const uint8_t* __restrict__ keep,
                                               float keep_scale, int lane)
 {
+    using RG = RowGeo<N4>;
+    const int h = lane >> 2, q = lane & 3;
     auto on_empty = [&](int r) { sink.empty(r, lane); };
     int* r_all = reinterpret_cast<int*>(ring.extra);            // [2][32] row id | last-edge flag per staged edge (packs)
     ChunkStat<H> c0, c1;
@@ -251,8 +276,9 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
     if (!kind0) return;
     phase_a(c0, kind0, b0);
     int issued0 = 0, issued1 = 0;
-    float m[H], s[H];
-    float2 acc[H][NSLOT];
+    float m = -INFINITY, s = 0.f;                       // online-softmax state of THIS lane's head
+    float4 acc[RG::NI];
+    acc_zero(acc);
     while (true) {
         const int* j0 = ring.j_s + b0 * 32;
         const int* j1 = ring.j_s + (b0 ^ 1) * 32;
@@ -261,50 +287,34 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
         issued1 = 0;
         if (kind1) phase_a(c1, kind1, b0 ^ 1);
         if (c0.first) {
-#pragma unroll
-            for (int h = 0; h < H; ++h) { m[h] = -INFINITY; s[h] = 0.f; }
+            m = -INFINITY;
+            s = 0.f;
             acc_zero(acc);
         }
-        float fch[H];
-        if (PACK && kind0 == 2) {
-#pragma unroll
-            for (int h = 0; h < H; ++h) fch[h] = 1.f;
-        } else {
-            float fold[H];
-#pragma unroll
-            for (int h = 0; h < H; ++h) {
-                const float mn = fmaxf(m[h], c0.cm[h]);
-                fold[h] = expf(m[h] - mn);              // 0 on the first chunk (m = -inf)
-                fch[h] = expf(c0.cm[h] - mn);
-                s[h] = s[h] * fold[h] + c0.cs[h] * fch[h];
-                m[h] = mn;
-            }
+        float fch = 1.f;
+        if (!(PACK && kind0 == 2)) {
+            const float cm = pick_head(c0.cm, h), cs = pick_head(c0.cs, h);
+            const float mn = fmaxf(m, cm);
+            const float fold = expf(m - mn);            // 0 on the first chunk (m = -inf)
+            fch = expf(cm - mn);
+            s = s * fold + cs * fch;
+            m = mn;
             if (!c0.first) {
 #pragma unroll
-                for (int h = 0; h < H; ++h)
-#pragma unroll
-                    for (int r = 0; r < NSLOT; ++r) { acc[h][r].x *= fold[h]; acc[h][r].y *= fold[h]; }
+                for (int i = 0; i < RG::NI; ++i) { acc[i].x *= fold; acc[i].y *= fold; acc[i].z *= fold; acc[i].w *= fold; }
             }
         }
-        const float* p0 = ring.p_s + b0 * 32 * H;
+        const float* p0 = ring.p_s + b0 * 32 * H + h;
         const int* r0 = r_all + b0 * 32;
         for (int t = 0; t < c0.n; ++t) {
-            const float* row = ring.front(j0[t]);
-            float2 v[NSLOT];
-            load_xrow<VEC2>(row, lane, K, v);
-            float w[H];
-            {
-                const float4 w0 = *reinterpret_cast<const float4*>(p0 + t * H);
-                const float4 w1 = *reinterpret_cast<const float4*>(p0 + t * H + 4);
-                w[0] = w0.x * fch[0]; w[1] = w0.y * fch[1]; w[2] = w0.z * fch[2]; w[3] = w0.w * fch[3];
-                w[4] = w1.x * fch[4]; w[5] = w1.y * fch[5]; w[6] = w1.z * fch[6]; w[7] = w1.w * fch[7];
-            }
+            const uint32_t a = ring.front() + uint32_t(q) * 16u;
+            const float w = p0[t * H] * fch;
 #pragma unroll
-            for (int h = 0; h < H; ++h)
-#pragma unroll
-                for (int r = 0; r < NSLOT; ++r) {
-                    acc[h][r].x = fmaf(w[h], v[r].x, acc[h][r].x);
-                    acc[h][r].y = fmaf(w[h], v[r].y, acc[h][r].y);
+            for (int i = 0; i < RG::NI; ++i)
+                if (RG::valid(i, q, n4)) {
+                    const float4 v = lds128(a + uint32_t(i) * 64u);
+                    acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y);
+                    acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
                 }
             ring.pop();
             if (issued0 < c0.n) ring.issue(j0[issued0++], lane);
@@ -328,30 +338,30 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
 
 constexpr int FWD_EXTRA = 256;   // r_all
 
-template <bool VEC2, bool DROPOUT, bool PACK>
-__global__ void __launch_bounds__(IN_THREADS, 3)
+template <int N4, bool DROPOUT, bool PACK>
+__global__ void __launch_bounds__(IN_THREADS, 4)
 gat_in_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                 const float* __restrict__ x, int64_t ldx, int K, const float* __restrict__ a_src,
+                 const float* __restrict__ x, int64_t ldx, const float* __restrict__ a_src,
                  const float* __restrict__ a_dst, gnnfd_item_plan_t items, int hub_threshold, float slope,
-                 const uint8_t* __restrict__ keep, float keep_scale, ZSink sink)
+                 const uint8_t* __restrict__ keep, float keep_scale, ZSink<N4> sink)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int item = blockIdx.x * IN_WARPS + warp;
     if (item >= items.n_items) return;
     InRing ring;
-    ring.init(smem + warp * in_warp_bytes(K, FWD_EXTRA), x, ldx, K, lane);
+    ring.init(smem + warp * in_warp_bytes(sink.KP, FWD_EXTRA), x, ldx, sink.KP, lane);
     ChunkCursor cur;
     cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
-    in_fwd_stream<VEC2, DROPOUT, PACK>(cur, ring, sink, sink.rowmax, sink.rowsum, rowptr, col, perm, K, a_src, a_dst, slope,
-                                       keep, keep_scale, lane);
+    in_fwd_stream<N4, DROPOUT, PACK>(cur, ring, sink, sink.rowmax, sink.rowsum, rowptr, col, perm, sink.KP >> 2, a_src, a_dst,
+                                     slope, keep, keep_scale, lane);
 }
 
 // one warp per (hub row, chunk): partial (m, s, unnormalised acc)
-template <bool VEC2, bool DROPOUT>
-__global__ void __launch_bounds__(IN_THREADS, 3)
+template <int N4, bool DROPOUT>
+__global__ void __launch_bounds__(IN_THREADS, 4)
 gat_in_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                      const float* __restrict__ x, int64_t ldx, int K, const float* __restrict__ a_src,
+                      const float* __restrict__ x, int64_t ldx, int KP, const float* __restrict__ a_src,
                       const float* __restrict__ a_dst, gnnfd_hub_plan_t plan, float slope,
                       const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ part_ms,
                       float* __restrict__ part_acc)
@@ -365,69 +375,58 @@ gat_in_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restr
     const int beg = rowptr[i] + (c - plan.hub_chunk_ptr[slot]) * plan.chunk;
     const int end = min(rowptr[i + 1], beg + plan.chunk);
     InRing ring;
-    ring.init(smem + warp * in_warp_bytes(K, FWD_EXTRA), x, ldx, K, lane);
+    ring.init(smem + warp * in_warp_bytes(KP, FWD_EXTRA), x, ldx, KP, lane);
     ChunkCursor cur;
     cur.start_segment(i, beg, end);
-    ZPartialSink sink{part_ms, part_acc, c};
-    in_fwd_stream<VEC2, DROPOUT, false>(cur, ring, sink, nullptr, nullptr, rowptr, col, perm, K, a_src, a_dst, slope, keep,
-                                        keep_scale, lane);
+    ZPartialSink<N4> sink{part_ms, part_acc, c};
+    in_fwd_stream<N4, DROPOUT, false>(cur, ring, sink, nullptr, nullptr, rowptr, col, perm, KP >> 2, a_src, a_dst, slope, keep,
+                                      keep_scale, lane);
 }
 
 // one CTA per hub row: warp w folds chunks w, w+8, ... (online-softmax combine), the eight warp states are folded in
 // warp order -- a fixed order, so the result is deterministic
+template <int N4>
 __global__ void __launch_bounds__(ROW_THREADS)
-gat_in_fwd_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_ms, const float* __restrict__ part_acc, ZSink sink)
+gat_in_fwd_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_ms, const float* __restrict__ part_acc, ZSink<N4> sink)
 {
+    using RG = RowGeo<N4>;
+    constexpr int PART_ACC = ZPartialSink<N4>::PART_ACC;
     extern __shared__ __align__(16) float msm[];               // [ROW_WARPS][2H] then [ROW_WARPS][PART_ACC]
     float* st_ms = msm;
-    float2* st_acc = reinterpret_cast<float2*>(msm + ROW_WARPS * 2 * H);
+    float4* st_acc = reinterpret_cast<float4*>(msm + ROW_WARPS * 2 * H);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = lane >> 2;
     const int slot = blockIdx.x;
     const int i = plan.hub_row[slot];
     const int c0 = plan.hub_chunk_ptr[slot], c1 = plan.hub_chunk_ptr[slot + 1];
-    float M[H], s[H];
-    float2 acc[H][NSLOT];
-#pragma unroll
-    for (int h = 0; h < H; ++h) { M[h] = -INFINITY; s[h] = 0.f; }
+    float M = -INFINITY, s = 0.f;
+    float4 acc[RG::NI];
     acc_zero(acc);
-    auto fold = [&](const float (&mc)[H], const float (&sc)[H], const float2* __restrict__ pacc) {
+    auto fold = [&](float mc, float sc, const float4* __restrict__ pacc) {
+        const float mn = fmaxf(M, mc);
+        const float fo = (M == -INFINITY) ? 0.f : expf(M - mn);
+        const float fn = (mc == -INFINITY) ? 0.f : expf(mc - mn);
+        s = s * fo + sc * fn;
+        M = mn;
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-            const float mn = fmaxf(M[h], mc[h]);
-            const float fo = (M[h] == -INFINITY) ? 0.f : expf(M[h] - mn);
-            const float fn = (mc[h] == -INFINITY) ? 0.f : expf(mc[h] - mn);
-            s[h] = s[h] * fo + sc[h] * fn;
-            M[h] = mn;
-#pragma unroll
-            for (int r = 0; r < NSLOT; ++r) {
-                const float2 v = pacc[(h * NSLOT + r) * 32 + lane];
-                acc[h][r].x = fmaf(v.x, fn, acc[h][r].x * fo);
-                acc[h][r].y = fmaf(v.y, fn, acc[h][r].y * fo);
-            }
+        for (int k = 0; k < RG::NI; ++k) {
+            const float4 v = pacc[k * 32 + lane];
+            acc[k].x = fmaf(v.x, fn, acc[k].x * fo); acc[k].y = fmaf(v.y, fn, acc[k].y * fo);
+            acc[k].z = fmaf(v.z, fn, acc[k].z * fo); acc[k].w = fmaf(v.w, fn, acc[k].w * fo);
         }
     };
-    for (int c = c0 + warp; c < c1; c += ROW_WARPS) {
-        float mc[H], sc[H];
-        load_vecH<H>(part_ms + int64_t(c) * 2 * H, mc);
-        load_vecH<H>(part_ms + int64_t(c) * 2 * H + H, sc);
-        fold(mc, sc, reinterpret_cast<const float2*>(part_acc + int64_t(c) * PART_ACC));
-    }
-    if (lane == 0) {
-        store_vecH<H>(st_ms + warp * 2 * H, M);
-        store_vecH<H>(st_ms + warp * 2 * H + H, s);
+    for (int c = c0 + warp; c < c1; c += ROW_WARPS)
+        fold(part_ms[int64_t(c) * 2 * H + h], part_ms[int64_t(c) * 2 * H + H + h],
+             reinterpret_cast<const float4*>(part_acc + int64_t(c) * PART_ACC));
+    if ((lane & 3) == 0) {
+        st_ms[warp * 2 * H + h] = M;
+        st_ms[warp * 2 * H + H + h] = s;
     }
 #pragma unroll
-    for (int h = 0; h < H; ++h)
-#pragma unroll
-        for (int r = 0; r < NSLOT; ++r) st_acc[warp * (PART_ACC / 2) + (h * NSLOT + r) * 32 + lane] = acc[h][r];
+    for (int k = 0; k < RG::NI; ++k) st_acc[warp * (PART_ACC / 4) + k * 32 + lane] = acc[k];
     __syncthreads();
     if (warp != 0) return;
-    for (int w = 1; w < ROW_WARPS; ++w) {
-        float mc[H], sc[H];
-#pragma unroll
-        for (int h = 0; h < H; ++h) { mc[h] = st_ms[w * 2 * H + h]; sc[h] = st_ms[w * 2 * H + H + h]; }
-        fold(mc, sc, st_acc + w * (PART_ACC / 2));
-    }
+    for (int w = 1; w < ROW_WARPS; ++w) fold(st_ms[w * 2 * H + h], st_ms[w * 2 * H + H + h], st_acc + w * (PART_ACC / 4));
     sink.finish(i, M, s, acc, lane);
 }
 
@@ -438,9 +437,62 @@ static int in_set_smem(Kn kernel, int bytes)
     return GNNFD_OK;
 }
 
-static bool vec2_ok(const float* x, int64_t ldx, int K)
+// x as the edge kernels need it: 16-byte aligned rows of at least KP floats
+bool in_x_ok(const float* x, int64_t ldx, int KP) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ldx % 4 == 0 && ldx >= KP; }
+
+template <int N4>
+static int launch_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, const Dims& d, const float* a_src, const float* a_dst,
+                         float slope, const uint8_t* keep, float p_drop, const float* scal, void* zimg, float* rowmax,
+                         float* rowsum, void* ws, size_t ws_bytes, cudaStream_t st)
 {
-    return (K % 2 == 0) && (ldx % 2 == 0) && (reinterpret_cast<uintptr_t>(x) & 7) == 0;
+    const bool drop = keep != nullptr && p_drop > 0.f;
+    const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
+    const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
+    const int smem = IN_WARPS * in_warp_bytes(d.KP, FWD_EXTRA);
+    const unsigned grid = (unsigned)((g->items_dst.n_items + IN_WARPS - 1) / IN_WARPS);
+    ZSink<N4> sink{reinterpret_cast<uint8_t*>(zimg), rowmax, rowsum, scal, d.KP, d.NKB};
+    static const bool pack = [] {
+        const char* e = getenv("GNNFD_FWD_PACK");
+        return e ? atoi(e) != 0 : true;
+    }();
+    int rc = GNNFD_OK;
+#define GNNFD_IN_FWD(DD, PP)                                                                                           \
+    rc = in_set_smem(gat_in_fwd_items<N4, DD, PP>, smem);                                                              \
+    if (rc) return rc;                                                                                                 \
+    gat_in_fwd_items<N4, DD, PP><<<grid, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, x, ldx, a_src, a_dst,       \
+                                                                 g->items_dst, thr, slope, keep, ks, sink)
+    if (pack) { if (drop) { GNNFD_IN_FWD(true, true); } else { GNNFD_IN_FWD(false, true); } }
+    else      { if (drop) { GNNFD_IN_FWD(true, false); } else { GNNFD_IN_FWD(false, false); } }
+#undef GNNFD_IN_FWD
+    g_launches += 1;
+    if (g->hub_dst.n_hub > 0) {
+        constexpr int PART_ACC = ZPartialSink<N4>::PART_ACC;
+        const gnnfd_hub_plan_t& pl = g->hub_dst;
+        const size_t need = carve_bytes(size_t(pl.n_chunk) * 2 * H, 4) + carve_bytes(size_t(pl.n_chunk) * PART_ACC, 4);
+        GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "in_fwd: workspace %zu < %zu", ws_bytes, need);
+        char* p = reinterpret_cast<char*>(ws);
+        float* part_ms = carve<float>(p, size_t(pl.n_chunk) * 2 * H);
+        float* part_acc = carve<float>(p, size_t(pl.n_chunk) * PART_ACC);
+        const unsigned gc = (unsigned)((pl.n_chunk + IN_WARPS - 1) / IN_WARPS);
+        if (drop) {
+            rc = in_set_smem(gat_in_fwd_hub_chunks<N4, true>, smem);
+            if (rc) return rc;
+            gat_in_fwd_hub_chunks<N4, true><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, x, ldx, d.KP, a_src, a_dst, pl,
+                                                                         slope, keep, ks, part_ms, part_acc);
+        } else {
+            rc = in_set_smem(gat_in_fwd_hub_chunks<N4, false>, smem);
+            if (rc) return rc;
+            gat_in_fwd_hub_chunks<N4, false><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, x, ldx, d.KP, a_src, a_dst, pl,
+                                                                          slope, keep, ks, part_ms, part_acc);
+        }
+        const int msm = (ROW_WARPS * 2 * H + ROW_WARPS * PART_ACC) * 4;
+        rc = in_set_smem(gat_in_fwd_hub_merge<N4>, msm);
+        if (rc) return rc;
+        gat_in_fwd_hub_merge<N4><<<(unsigned)pl.n_hub, ROW_THREADS, msm, st>>>(pl, part_ms, part_acc, sink);
+        g_launches += 2;
+    }
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
 }
 
 }  // namespace in
@@ -456,39 +508,68 @@ int gnnfd_in_supported(int64_t K, int H_, int C_, int concat)
     return (K >= 1 && K <= MAX_K && H_ == H && C_ == C && !concat) ? 1 : 0;
 }
 
-int gnnfd_in_sizes(int64_t n_dst, int64_t K, size_t* prep_bytes_out, size_t* zimg_bytes_out, int64_t* gd_ld_out)
+int gnnfd_in_sizes(int64_t n_dst, int64_t K, size_t* prep_bytes_out, size_t* zimg_bytes_out, int64_t* gd_ld_out,
+                   int64_t* x_ld_out)
 {
     GNNFD_REQUIRE(K >= 1 && K <= MAX_K && n_dst >= 0, GNNFD_ERR_ARG, "in_sizes: K must be in [1,%d]", MAX_K);
     const Dims d((int)K);
     if (prep_bytes_out) *prep_bytes_out = prep_bytes(d);
     if (zimg_bytes_out) *zimg_bytes_out = zimg_bytes(n_dst, d) + 1024;
     if (gd_ld_out) *gd_ld_out = d.F;
+    if (x_ld_out) *x_ld_out = d.KP;
+    return GNNFD_OK;
+}
+
+/* x16 [N, x_ld] (x_ld = gnnfd_in_sizes' x_ld) = x zero-padded: 16-byte aligned rows for the bulk-copy gathers. */
+int gnnfd_in_pad_x(const float* x, int64_t ldx, int64_t N, int64_t K, float* x16, gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && ldx >= K && N >= 0, GNNFD_ERR_ARG, "in_pad_x: bad shape");
+    if (N == 0) return GNNFD_OK;
+    GNNFD_REQUIRE(x && x16 && (reinterpret_cast<uintptr_t>(x16) & 15) == 0, GNNFD_ERR_ARG, "in_pad_x: NULL or misaligned tensor");
+    const Dims d((int)K);
+    int64_t blocks = (N * (d.KP / 4) + 255) / 256;
+    if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
+    in_pad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, N, d.K, d.KP, x16);
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
     return GNNFD_OK;
 }
 
 /* a_src / a_dst [N,H] for rows [0,N) of x, and xmax[0] = max(xmax[0], max |x|) (caller zeroes xmax before the first call;
- * across GPUs the per-rank maxima are max-reduced before gnnfd_in_prepare).  ws: 2H*KP floats. */
+ * across GPUs the per-rank maxima are max-reduced before gnnfd_in_prepare).  x: padded rows (gnnfd_in_pad_x layout). */
 int gnnfd_in_logits(const float* x, int64_t ldx, int64_t N, int64_t K, const float* W, const float* att_src,
                     const float* att_dst, float* a_src, float* a_dst, float* xmax, void* prep, gnnfd_stream_t stream)
 {
-    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && ldx >= K && N >= 0, GNNFD_ERR_ARG, "in_logits: bad shape (K <= %d)", MAX_K);
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && N >= 0, GNNFD_ERR_ARG, "in_logits: bad shape (K <= %d)", MAX_K);
     GNNFD_REQUIRE(W && att_src && att_dst && xmax && prep, GNNFD_ERR_ARG, "in_logits: NULL argument");
     GNNFD_REQUIRE(N == 0 || (x && a_src && a_dst), GNNFD_ERR_ARG, "in_logits: NULL tensor");
     cudaStream_t st = (cudaStream_t)stream;
     const Dims d((int)K);
+    GNNFD_REQUIRE(N == 0 || in_x_ok(x, ldx, d.KP), GNNFD_ERR_ARG,
+                  "in_logits: x rows must be 16-byte aligned and zero-padded to %d floats (gnnfd_in_pad_x)", d.KP);
     float* u = reinterpret_cast<float*>(reinterpret_cast<char*>(prep) + prep_off_u(d));
     in_u_kernel<<<2 * H, 192, 0, st>>>(W, att_src, att_dst, d.K, d.KP, u);
     g_launches += 1;
     if (N > 0) {
-        int64_t blocks = (N + 7) / 8;
-        const int64_t cap = int64_t(sm_count()) * 2 * 4;
-        if (blocks > cap) blocks = cap;
-        if (vec2_ok(x, ldx, d.K))
-            in_logits_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, N, d.K, u, d.KP, a_src, a_dst,
-                                                                    reinterpret_cast<unsigned*>(xmax));
-        else
-            in_logits_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x, ldx, N, d.K, u, d.KP, a_src, a_dst,
-                                                                     reinterpret_cast<unsigned*>(xmax));
+        const int64_t n_tiles = (N + LG_ROWS - 1) / LG_ROWS;
+        const int64_t cap = int64_t(sm_count()) * 2;
+        const unsigned blocks = (unsigned)(n_tiles < cap ? n_tiles : cap);
+        const int smem = 2 * LG_ROWS * d.KP * 4;
+        unsigned* xb = reinterpret_cast<unsigned*>(xmax);
+        int rc;
+        if (d.KP == 168) {
+            rc = in_set_smem(in_logits_kernel<42>, smem);
+            if (rc) return rc;
+            in_logits_kernel<42><<<blocks, LG_WARPS * 32, smem, st>>>(x, ldx, N, d.KP, u, a_src, a_dst, xb);
+        } else if (d.KP == 64) {
+            rc = in_set_smem(in_logits_kernel<16>, smem);
+            if (rc) return rc;
+            in_logits_kernel<16><<<blocks, LG_WARPS * 32, smem, st>>>(x, ldx, N, d.KP, u, a_src, a_dst, xb);
+        } else {
+            rc = in_set_smem(in_logits_kernel<0>, smem);
+            if (rc) return rc;
+            in_logits_kernel<0><<<blocks, LG_WARPS * 32, smem, st>>>(x, ldx, N, d.KP, u, a_src, a_dst, xb);
+        }
         g_launches += 1;
     }
     GNNFD_LAUNCH_CHECK();
@@ -515,7 +596,7 @@ int gnnfd_in_fwd_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes)
 {
     GNNFD_REQUIRE(g && bytes, GNNFD_ERR_ARG, "in_fwd_workspace_bytes: NULL argument");
     const size_t nc = (size_t)g->hub_dst.n_chunk;
-    *bytes = carve_bytes(nc * 2 * H, 4) + carve_bytes(nc * size_t(PART_ACC), 4) + 256;
+    *bytes = carve_bytes(nc * 2 * H, 4) + carve_bytes(nc * size_t(ZPartialSink<0>::PART_ACC), 4) + 256;
     return GNNFD_OK;
 }
 
@@ -526,72 +607,28 @@ int gnnfd_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K,
 {
     int rc = check_graph(g, false, "in_fwd");
     if (rc) return rc;
-    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && ldx >= K, GNNFD_ERR_ARG, "in_fwd: bad shape (K <= %d)", MAX_K);
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K, GNNFD_ERR_ARG, "in_fwd: bad shape (K <= %d)", MAX_K);
     GNNFD_REQUIRE(g->n_dst == 0 || (x && a_src && a_dst && prep && zimg && rowmax && rowsum), GNNFD_ERR_ARG, "in_fwd: NULL tensor");
     GNNFD_REQUIRE(p_drop >= 0.f && p_drop <= 0.9f, GNNFD_ERR_ARG, "in_fwd: dropout p must be in [0,0.9] on the input-space path");
-    GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(zimg) & 1023) == 0 && (reinterpret_cast<uintptr_t>(x) & 3) == 0, GNNFD_ERR_ARG,
-                  "in_fwd: zimg must be 1024-byte aligned");
-    GNNFD_REQUIRE(g->n_src * ldx * 4 < (int64_t(1) << 46), GNNFD_ERR_ARG, "in_fwd: x too large");
+    GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(zimg) & 1023) == 0, GNNFD_ERR_ARG, "in_fwd: zimg must be 1024-byte aligned");
     if (g->n_dst == 0) return GNNFD_OK;
+    const Dims d((int)K);
+    GNNFD_REQUIRE(in_x_ok(x, ldx, d.KP), GNNFD_ERR_ARG,
+                  "in_fwd: x rows must be 16-byte aligned and zero-padded to %d floats (gnnfd_in_pad_x)", d.KP);
     GNNFD_REQUIRE(g->items_dst.n_items > 0 && g->items_dst.item_start, GNNFD_ERR_ARG,
                   "in_fwd: the graph has no work-item plan over rowptr (gnnfd_item_plan)");
     cudaStream_t st = (cudaStream_t)stream;
-    const Dims d((int)K);
-    const bool drop = keep_mask != nullptr && p_drop > 0.f;
-    const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
-    const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
-    const bool v2 = vec2_ok(x, ldx, d.K);
-    const int smem = IN_WARPS * in_warp_bytes(d.K, FWD_EXTRA);
-    const unsigned grid = (unsigned)((g->items_dst.n_items + IN_WARPS - 1) / IN_WARPS);
     const float* scal = reinterpret_cast<const float*>(prep);
-    ZSink sink{reinterpret_cast<uint8_t*>(zimg), rowmax, rowsum, scal, d.KP, d.NKB};
     // rows of the last tile beyond n_dst are read by the node-reduction GEMM (dW): they must be zero, not stale
     if (g->n_dst % TILE) {
         const size_t last = size_t(g->n_dst / TILE) * d.NKB * KBLOCK;
         GNNFD_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(zimg) + last, 0, size_t(d.NKB) * KBLOCK, st));
     }
-    static const bool pack = [] {
-        const char* e = getenv("GNNFD_FWD_PACK");
-        return e ? atoi(e) != 0 : true;
-    }();
-#define GNNFD_IN_FWD(VV, DD, PP)                                                                                       \
-    rc = in_set_smem(gat_in_fwd_items<VV, DD, PP>, smem);                                                              \
-    if (rc) return rc;                                                                                                 \
-    gat_in_fwd_items<VV, DD, PP><<<grid, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, x, ldx, d.K, a_src, a_dst, \
-                                                                 g->items_dst, thr, negative_slope, keep_mask, ks, sink)
-    if (pack) {
-        if (v2) { if (drop) { GNNFD_IN_FWD(true, true, true); } else { GNNFD_IN_FWD(true, false, true); } }
-        else    { if (drop) { GNNFD_IN_FWD(false, true, true); } else { GNNFD_IN_FWD(false, false, true); } }
-    } else {
-        if (v2) { if (drop) { GNNFD_IN_FWD(true, true, false); } else { GNNFD_IN_FWD(true, false, false); } }
-        else    { if (drop) { GNNFD_IN_FWD(false, true, false); } else { GNNFD_IN_FWD(false, false, false); } }
-    }
-#undef GNNFD_IN_FWD
-    g_launches += 1;
-    if (g->hub_dst.n_hub > 0) {
-        const gnnfd_hub_plan_t& pl = g->hub_dst;
-        const size_t need = carve_bytes(size_t(pl.n_chunk) * 2 * H, 4) + carve_bytes(size_t(pl.n_chunk) * PART_ACC, 4);
-        GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "in_fwd: workspace %zu < %zu", ws_bytes, need);
-        char* p = reinterpret_cast<char*>(ws);
-        float* part_ms = carve<float>(p, size_t(pl.n_chunk) * 2 * H);
-        float* part_acc = carve<float>(p, size_t(pl.n_chunk) * PART_ACC);
-        const unsigned gc = (unsigned)((pl.n_chunk + IN_WARPS - 1) / IN_WARPS);
-#define GNNFD_IN_HUB(VV, DD)                                                                                           \
-    rc = in_set_smem(gat_in_fwd_hub_chunks<VV, DD>, smem);                                                             \
-    if (rc) return rc;                                                                                                 \
-    gat_in_fwd_hub_chunks<VV, DD><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, x, ldx, d.K, a_src, a_dst, pl, \
-                                                                negative_slope, keep_mask, ks, part_ms, part_acc)
-        if (v2) { if (drop) { GNNFD_IN_HUB(true, true); } else { GNNFD_IN_HUB(true, false); } }
-        else    { if (drop) { GNNFD_IN_HUB(false, true); } else { GNNFD_IN_HUB(false, false); } }
-#undef GNNFD_IN_HUB
-        const int msm = (ROW_WARPS * 2 * H + ROW_WARPS * PART_ACC) * 4;
-        rc = in_set_smem(gat_in_fwd_hub_merge, msm);
-        if (rc) return rc;
-        gat_in_fwd_hub_merge<<<(unsigned)pl.n_hub, ROW_THREADS, msm, st>>>(pl, part_ms, part_acc, sink);
-        g_launches += 2;
-    }
-    GNNFD_LAUNCH_CHECK();
-    return GNNFD_OK;
+    if (d.KP == 168)
+        return launch_in_fwd<42>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
+    if (d.KP == 64)
+        return launch_in_fwd<16>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
+    return launch_in_fwd<0>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
 }
 
 }  // extern "C"

@@ -26,8 +26,7 @@ namespace gnnfd {
 namespace in {
 
 constexpr int H = 8, C = 64;
-constexpr int NSLOT = 3;                 // a lane holds features 64*r + 2*lane, +1 (r < NSLOT)  =>  K <= 192
-constexpr int MAX_K = 64 * NSLOT;
+constexpr int MAX_K = 192;               // 48 float4s per row at most: 12 per lane quarter
 constexpr int TILE = 128;                // rows (nodes) per image tile
 constexpr int PLANE = TILE * 128;        // 16 KB: one fp16 plane of one k-block (64 features) of one tile
 constexpr int KBLOCK = 2 * PLANE;        // hi plane then lo plane
@@ -100,43 +99,85 @@ inline size_t zimg_bytes(int64_t n_rows, const Dims& d) { return size_t((n_rows 
 namespace gnnfd {
 namespace in {
 
+// ---- lane geometry of the edge kernels ------------------------------------------------------------------------------
+// lane = (head h = lane >> 2, quarter q = lane & 3).  A staged x row is KP floats = n4 float4s; lane (h, q) owns the
+// float4s 4*i + q (i = 0, 1, ...) of the row for ITS head: 44 accumulators (forward) / 44 Gd values (backward) for
+// K = 166.  Per edge and lane: ceil(n4/4) conflict-free 128-bit shared loads (the four q-lanes read 64 contiguous bytes,
+// the eight heads read the same addresses = broadcast) and 4 FMAs per load; the backward's dot product is finished by
+// TWO shuffles over the lane's quad; everything per-head (softmax state, weights, scales) is a scalar per lane.
+// N4 > 0: compile-time row width (no per-load predicate except the tail); N4 = 0: run-time n4 <= 48.
+template <int N4>
+struct RowGeo {
+    static constexpr int NI = N4 > 0 ? (N4 + 3) / 4 : MAX_K / 16;
+    __device__ static __forceinline__ bool valid(int i, int q, int n4) { return N4 > 0 ? (4 * i + q < N4) : (4 * i + q < n4); }
+};
+
 // ---- per-warp ring of staged x rows ------------------------------------------------------------------------------
-// Row j starts at x + j*ldx, which is only 4- or 8-byte aligned (K = 166: 664-byte stride).  cp.async.bulk needs
-// 16-byte aligned source and size, so lane 0 fetches the enclosing 16-byte aligned span into the slot and the consumer
-// adds (address & 15).  Sizes are run-time (they depend on K); per-warp layout:
-//   [R slots][p_s: 2 x 32 x H floats][j_s: 2 x 32 ints][R+1 mbarriers][extra]
+// Rows must be 16-byte aligned and zero-padded to KP floats (ldx % 4 == 0, ldx >= KP: gnnfd_in_pad_x builds such a copy
+// of an unaligned x): lane 0 hands a whole row to the bulk-copy engine (cp.async.bulk global->shared, mbarrier
+// complete_tx).  Per-warp layout:  [R slots of KP*4 bytes][p_s: 2 x 32 x H floats][j_s: 2 x 32 ints][R+1 mbarriers][extra]
 constexpr int IN_WARPS = 4;
 constexpr int IN_THREADS = IN_WARPS * 32;
-constexpr int IN_R = 10;                                   // ring slots per warp
+constexpr int IN_R = 8, IN_LOG_R = 3;                      // ring slots per warp (power of two)
 constexpr int IN_P_BYTES = 2 * 32 * H * 4, IN_J_BYTES = 2 * 32 * 4, IN_BAR_BYTES = ((IN_R + 1) * 8 + 15) / 16 * 16;
 
-__host__ __device__ inline int in_slot_bytes(int K) { return (K * 4 + 12 + 15) / 16 * 16; }
-__host__ __device__ inline int in_warp_bytes(int K, int extra)
+__host__ __device__ inline int in_warp_bytes(int KP, int extra)
 {
-    return (IN_R * in_slot_bytes(K) + IN_P_BYTES + IN_J_BYTES + IN_BAR_BYTES + extra + 127) / 128 * 128;
+    return (IN_R * KP * 4 + IN_P_BYTES + IN_J_BYTES + IN_BAR_BYTES + extra + 127) / 128 * 128;
+}
+
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity)
+{
+    uint32_t done = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1u << 26)) __trap();   // a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+                 "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
 }
 
 struct InRing {
-    uint8_t* ring;
+    uint32_t ring_u32, full_u32, slot;   // shared-space addresses / bytes per slot
     uint8_t* extra;
     float* p_s;      // [2][32*H]
     int* j_s;        // [2][32]
-    uint64_t* full;  // [IN_R] + one spare barrier (index IN_R) for kernel-specific use
-    int slot, issued = 0, consumed = 0;
-    uint64_t xaddr;
-    uint32_t ldxb, rowb;
+    int issued = 0, consumed = 0;
+    const float* x;
+    int64_t ldx;
 
-    __device__ __forceinline__ void init(uint8_t* base, const float* x, int64_t ldx, int K, int lane)
+    __device__ __forceinline__ void init(uint8_t* base, const float* x_, int64_t ldx_, int KP, int lane)
     {
-        slot = in_slot_bytes(K);
-        ring = base;
+        slot = uint32_t(KP) * 4u;
+        ring_u32 = st_smem_u32(base);
         p_s = reinterpret_cast<float*>(base + IN_R * slot);
         j_s = reinterpret_cast<int*>(base + IN_R * slot + IN_P_BYTES);
-        full = reinterpret_cast<uint64_t*>(base + IN_R * slot + IN_P_BYTES + IN_J_BYTES);
+        uint64_t* full = reinterpret_cast<uint64_t*>(base + IN_R * slot + IN_P_BYTES + IN_J_BYTES);
+        full_u32 = st_smem_u32(full);
         extra = base + IN_R * slot + IN_P_BYTES + IN_J_BYTES + IN_BAR_BYTES;
-        xaddr = reinterpret_cast<uint64_t>(x);
-        ldxb = uint32_t(ldx) * 4u;
-        rowb = uint32_t(K) * 4u;
+        x = x_;
+        ldx = ldx_;
         if (lane == 0) {
 #pragma unroll
             for (int i = 0; i <= IN_R; ++i) st_mbar_init(&full[i], 1);
@@ -144,26 +185,24 @@ struct InRing {
         }
         __syncwarp();
     }
+    __device__ __forceinline__ uint32_t spare_bar() const { return full_u32 + 8u * IN_R; }   // for kernel-specific use
     __device__ __forceinline__ bool has_room() const { return issued - consumed < IN_R; }
     __device__ __forceinline__ void issue(int j, int lane)
     {
         if (lane == 0) {
-            const int s = issued % IN_R;
-            const uint64_t a = xaddr + uint64_t(uint32_t(j)) * ldxb;
-            const uint64_t a0 = a & ~uint64_t(15);
-            const uint32_t bytes = uint32_t(((a + rowb + 15) & ~uint64_t(15)) - a0);
-            st_mbar_expect_tx(&full[s], bytes);
-            st_bulk_g2s(ring + s * slot, reinterpret_cast<const void*>(a0), bytes, &full[s]);
+            const uint32_t s = uint32_t(issued) & (IN_R - 1);
+            const uint32_t bar = full_u32 + 8u * s;
+            mbar_expect_tx_u32(bar, slot);
+            bulk_g2s_u32(ring_u32 + s * slot, x + int64_t(j) * ldx, slot, bar);
         }
         ++issued;
     }
-    // wait for the oldest in-flight row (source id j); returns the address of its first element
-    __device__ __forceinline__ const float* front(int j)
+    // wait for the oldest in-flight row; returns its shared-space address
+    __device__ __forceinline__ uint32_t front()
     {
-        const int s = consumed % IN_R;
-        st_mbar_wait(&full[s], (consumed / IN_R) & 1);
-        const uint32_t off = uint32_t(xaddr + uint64_t(uint32_t(j)) * ldxb) & 15u;
-        return reinterpret_cast<const float*>(ring + s * slot + off);
+        const uint32_t s = uint32_t(consumed) & (IN_R - 1);
+        mbar_wait_u32(full_u32 + 8u * s, uint32_t(consumed >> IN_LOG_R) & 1u);
+        return ring_u32 + s * slot;
     }
     __device__ __forceinline__ void pop()
     {
@@ -172,20 +211,13 @@ struct InRing {
     }
 };
 
-// the features of one staged row owned by this lane: pairs (64r + 2*lane, +1), zero beyond K
-template <bool VEC2>
-__device__ __forceinline__ void load_xrow(const float* __restrict__ row, int lane, int K, float2 (&v)[NSLOT])
+// arr[h] with a run-time h, without dynamic register indexing
+__device__ __forceinline__ float pick_head(const float (&arr)[H], int h)
 {
+    float r = arr[0];
 #pragma unroll
-    for (int r = 0; r < NSLOT; ++r) {
-        const int f = 64 * r + 2 * lane;
-        if (VEC2) {   // K even, rows 8-byte aligned: a pair is inside the row or outside
-            v[r] = (f < K) ? *reinterpret_cast<const float2*>(row + f) : make_float2(0.f, 0.f);
-        } else {
-            v[r].x = (f < K) ? row[f] : 0.f;
-            v[r].y = (f + 1 < K) ? row[f + 1] : 0.f;
-        }
-    }
+    for (int k = 1; k < H; ++k) r = (h == k) ? arr[k] : r;
+    return r;
 }
 
 }  // namespace in

@@ -170,9 +170,24 @@ def in_supported(K: int, H: int, C_: int, concat: bool) -> bool:
 
 
 def in_sizes(n_dst: int, K: int):
-    pb, zb, ld = C.c_size_t(), C.c_size_t(), C.c_int64()
-    _abi.check(_abi.lib().gnnfd_in_sizes(int(n_dst), int(K), C.byref(pb), C.byref(zb), C.byref(ld)))
-    return pb.value, zb.value, ld.value
+    """(prep bytes, image bytes, leading dimension of Gd, leading dimension of the padded x)."""
+    pb, zb, ld, xld = C.c_size_t(), C.c_size_t(), C.c_int64(), C.c_int64()
+    _abi.check(_abi.lib().gnnfd_in_sizes(int(n_dst), int(K), C.byref(pb), C.byref(zb), C.byref(ld), C.byref(xld)))
+    return pb.value, zb.value, ld.value, xld.value
+
+
+def in_pad_x(x: torch.Tensor) -> torch.Tensor:
+    """x [N,K] -> view [N,K] of a zero-padded [N, round_up(K,8)] copy (16-byte aligned rows for the bulk-copy gathers);
+    returns ``x`` itself when it already has that layout."""
+    N, K = x.shape
+    xld = in_sizes(0, K)[3]
+    if x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.stride(0) >= xld and x.data_ptr() % 16 == 0:
+        return x
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    x16 = torch.empty(N, xld, dtype=torch.float32, device=x.device)
+    _abi.check(_abi.lib().gnnfd_in_pad_x(x.data_ptr(), x.stride(0), N, K, x16.data_ptr(), _stream()))
+    return x16[:, :K]
 
 
 def in_logits(x, W, att_src, att_dst, prep, xmax, n_rows=None):
@@ -194,7 +209,7 @@ def in_fwd(g: GraphCSR, x, a_src, a_dst, negative_slope, prep, keep_mask=None, p
     """Aggregation in input space -> (zimg, rowmax, rowsum)."""
     L = _abi.lib()
     dev, K = x.device, x.size(1)
-    _, zb, _ = in_sizes(g.n_dst, K)
+    zb = in_sizes(g.n_dst, K)[1]
     zimg = _aligned_u8(zb, dev)
     rowmax = torch.empty(g.n_dst, 8, dtype=torch.float32, device=dev)
     rowsum = torch.empty(g.n_dst, 8, dtype=torch.float32, device=dev)
@@ -223,7 +238,7 @@ def in_bwd_edges(g: GraphCSR, x, a_src, a_dst, rowmax, rowsum, d_out, prep, nega
     """Gd GEMM + backward edge pass, in blocks of destination rows.  Returns dz [E',H] (source-major) and da_dst."""
     L = _abi.lib()
     dev, K = x.device, x.size(1)
-    _, _, F = in_sizes(g.n_dst, K)
+    F = in_sizes(g.n_dst, K)[2]
     dz = torch.empty(g.n_edges, 8, dtype=torch.float32, device=dev)
     da_dst = torch.empty(g.n_dst, 8, dtype=torch.float32, device=dev)
     nb = C.c_size_t()
@@ -280,13 +295,12 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
             raise ValueError(f"x must be [N,{W.size(1)}], got {tuple(x.shape)}")
         if x.size(0) != g.n_src:
             raise ValueError(f"x has {x.size(0)} rows but the graph has {g.n_src} source nodes")
-        if x.stride(1) != 1:
-            x = x.contiguous()
         W = W.contiguous()
         a_s, a_d = att_src.contiguous().view(-1), att_dst.contiguous().view(-1)
         K = x.size(1)
         with torch.cuda.device(x.device):
-            pb, _, _ = in_sizes(g.n_dst, K)
+            pb = in_sizes(g.n_dst, K)[0]
+            x = in_pad_x(x)
             prep = _aligned_u8(pb, x.device)
             xmax = torch.zeros(16, dtype=torch.float32, device=x.device)
             a_src, a_dst = in_logits(x, W, a_s, a_d, prep, xmax)

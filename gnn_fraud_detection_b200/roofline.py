@@ -38,3 +38,29 @@ def stage_flops(N: int, Ep: int, K: int, H: int = 8, C: int = 64, need_dx: bool 
         "gat_fwd": Ep * H * (2 * C + 10),
         "gat_bwd": Ep * H * (4 * C + 20),
     }
+
+
+def stage_bytes_input_space(N: int, Ep: int, K: int, H: int = 8, C: int = 64, n_src: int | None = None) -> dict:
+    """Algorithmic bytes of the input-space formulation of the first layer (csrc/in_common.cuh): per-edge gathers are
+    x rows (K*4 B) instead of projected rows (H*C*4 B); the aggregated input Z [N, H*KP] (fp16 pair = 4 B/element) is
+    written once and read by the two tensor-core GEMMs; Gd [N, H*KP] fp32 is written and read once.  Same charging
+    rules as ``stage_bytes`` (gathers per edge, no credit for cache reuse)."""
+    i = 4
+    KP = (K + 7) // 8 * 8
+    F = H * KP
+    Ns = N if n_src is None else n_src
+    b = {}
+    b["in_logits"] = N * (K * 4 + 8 * H)
+    # per edge: x[src] row, col, a_src[src]; per row: a_dst, (max,sum), rowptr, Z row
+    b["in_fwd_edges"] = Ep * (K * 4 + i + 4 * H) + N * (4 * H + 8 * H + i + F * 4)
+    b["in_out_gemm"] = N * (F * 4 + 4 * C) + F * C * 4
+    b["in_bwd_gd"] = N * (4 * C + F * 4)
+    # per edge: x[src] row, col, a_src[src], csr2csc, dz write; per row: Gd row, (a_dst,max,sum), da_dst, rowptr
+    b["in_bwd_edges"] = Ep * (K * 4 + i + 4 * H + i + 4 * H) + N * (F * 4 + 12 * H + 4 * H + i)
+    b["in_bwd_dasrc"] = Ep * 4 * H + Ns * (4 * H + i)
+    # dW GEMM reads Z and dOut; da^T x reads x and the logit gradients; dbias reads dOut
+    b["in_bwd_params"] = N * (F * 4 + 4 * C + K * 4 + 8 * H + 4 * C) + 2 * K * H * C * 4
+    b["fwd"] = b["in_logits"] + b["in_fwd_edges"] + b["in_out_gemm"]
+    b["bwd"] = b["in_bwd_gd"] + b["in_bwd_edges"] + b["in_bwd_dasrc"] + b["in_bwd_params"]
+    b["total"] = b["fwd"] + b["bwd"]
+    return b

@@ -233,9 +233,15 @@ int gnnfd_project_bwd(const float* x, int64_t ldx, const float* W, const float* 
  *           gnnfd_in_logits (u) + gnnfd_in_prepare (scales, images); valid until W / att / max|x| change
  *   zimg  : gnnfd_in_sizes().zimg_bytes for n_dst rows, 1024-byte aligned; written by gnnfd_in_fwd, read by gnnfd_in_out
  *           and gnnfd_in_bwd_params
- *   gd    : [rows, gd_ld] fp32, gd_ld = gnnfd_in_sizes().gd_ld */
+ *   gd    : [rows, gd_ld] fp32, gd_ld = gnnfd_in_sizes().gd_ld
+ *   x     : in every call below the PADDED layout (see gnnfd_in_pad_x) */
 int gnnfd_in_supported(int64_t K, int H, int C, int concat);
-int gnnfd_in_sizes(int64_t n_dst, int64_t K, size_t* prep_bytes, size_t* zimg_bytes, int64_t* gd_ld);
+int gnnfd_in_sizes(int64_t n_dst, int64_t K, size_t* prep_bytes, size_t* zimg_bytes, int64_t* gd_ld, int64_t* x_ld);
+/* The edge kernels hand whole x rows to the bulk-copy engine, so x must have 16-byte aligned rows of x_ld = round_up(K, 8)
+ * floats, zero beyond K (leading dimension % 4 == 0 and >= x_ld).  gnnfd_in_pad_x builds such a copy x16 [N, x_ld] of an
+ * arbitrary x (the reference's K = 166 / 165 rows are only 8- / 4-byte aligned); for a static first-layer input it is
+ * built once, like the CSR. */
+int gnnfd_in_pad_x(const float* x, int64_t ldx, int64_t N, int64_t K, float* x16, gnnfd_stream_t stream);
 /* a_src / a_dst [N,H] of rows [0,N) of x; xmax[0] = max(xmax[0], max|x|) (zero it before the first call; across GPUs
  * max-reduce it before gnnfd_in_prepare). */
 int gnnfd_in_logits(const float* x, int64_t ldx, int64_t N, int64_t K, const float* W, const float* att_src,

@@ -68,10 +68,10 @@ def case(name, N, K, ei, seed=0, n_blocks=None, keep=None, p=0.0):
     o2.backward(d_out.double())
     # ---- device
     g = build_csr(ei.to(dev), N)
-    xg, Wg = x.to(dev), W.to(dev)
+    xg, Wg = Fn.in_pad_x(x.to(dev)), W.to(dev)
     asg, adg, bg = a_s.to(dev).view(-1).contiguous(), a_d.to(dev).view(-1).contiguous(), b.to(dev)
     keep_g = None if keep is None else keep.to(dev).to(torch.uint8).contiguous()
-    pb, zb, F = Fn.in_sizes(N, K)
+    pb, zb, F, _ = Fn.in_sizes(N, K)
     prep = Fn._aligned_u8(pb, dev)
     xmax = torch.zeros(16, device=dev)
     a_src, a_dst = Fn.in_logits(xg, Wg, asg, adg, prep, xmax)
