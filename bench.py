@@ -231,24 +231,30 @@ def run_gpu_arm(args):
         d_out = torch.full((N, C), 1.0 / N, device=dev)      # timing only; parity runs use randn/N
         n_local, part = N, None
     else:
-        Part = partition.ReplicatedInputPartition if args.mgpu == "replicate" else partition.DstRangePartition
+        Part = {"input": partition.InputSpacePartition, "replicate": partition.ReplicatedInputPartition,
+                "allgather": partition.DstRangePartition}[args.mgpu]
         part = Part.build(ei, N, rank, world, dev)
         del ei
         g, Ep, n_local = part.graph, part.graph.n_edges, part.n_local
         csr_ms = part.build_ms
-        if args.mgpu == "replicate":   # the layer input is resident on every GPU (same seed => identical copies)
+        if args.mgpu == "input":       # replicated input in the padded-row layout of the input-space kernels
+            x = torch.zeros(part.n_pos, Fn.in_sizes(0, K)[3], device=dev)
+            x[:, :K] = torch.randn(part.n_pos, K, device=dev, generator=gen)
+            x = x[:, :K]
+        elif args.mgpu == "replicate":   # the layer input is resident on every GPU (same seed => identical copies)
             x = torch.randn(part.n_pos, K, device=dev, generator=gen)
         else:                          # this rank's rows of x
             x = torch.randn(part.rows_padded, K, device=dev, generator=gen)
         d_out = torch.full((n_local, C), 1.0 / N, device=dev)
     gen_s = time.perf_counter() - t_gen
 
-    input_space = args.algo == _abi.GEMM_INPUT
+    input_space = (args.algo == _abi.GEMM_INPUT) if world == 1 else (args.mgpu == "input")
     if input_space:
         stages = ["in_logits", "in_fwd_edges", "in_out_gemm", "in_bwd_gd_edges", "in_bwd_dasrc", "in_bwd_params"]
-        in_prep = Fn._aligned_u8(Fn.in_sizes(n_local, K)[0], dev)
-        x = Fn.in_pad_x(x)            # static first-layer input: padded once, like the CSR
-        in_xmax = torch.zeros(16, device=dev)
+        if world == 1:
+            in_prep = Fn._aligned_u8(Fn.in_sizes(n_local, K)[0], dev)
+            x = Fn.in_pad_x(x)            # static first-layer input: padded once, like the CSR
+            in_xmax = torch.zeros(16, device=dev)
     else:
         stages = ["project_fwd", "gat_fwd", "gat_bwd_dst_src", "project_bwd"]
     ev = {}
@@ -413,10 +419,14 @@ def run_gpu_arm(args):
             "config": {"workload": workload, "nodes": N, "edges": E_total, "edges_after_self_loop_rewrite": Ep_total,
                        "in_features": K, "heads": H, "out_channels": C, "concat": False,
                        "l2": "inputs larger than L2 (xw %.1f GB per pass)" % (N * H * C * s_bytes / 1e9),
-                       "parallelism": "1 GPU" if world == 1 else (
-                           f"dst-range x{world}: replicated input + redundant projection, all-to-all of per-edge grads, "
-                           f"all-gather of dOut" if args.mgpu == "replicate" else
-                           f"dst-range x{world}: NCCL all-gather of projected features, reduce-scatter of dxw"),
+                       "parallelism": "1 GPU" if world == 1 else {
+                           "input": f"dst-range x{world}: replicated input, input-space aggregation, all-gather / "
+                                    f"reduce-scatter of [N,H] logit vectors only",
+                           "replicate": f"dst-range x{world}: replicated input + redundant projection, all-to-all of "
+                                        f"per-edge grads, all-gather of dOut",
+                           "allgather": f"dst-range x{world}: NCCL all-gather of projected features, reduce-scatter of dxw",
+                       }[args.mgpu],
+                       "formulation": "input-space" if input_space else "projected-feature",
                        "csr_build_ms": csr_ms, "setup_s": gen_s, "gemm_algo": args.algo, "note": note},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
@@ -484,7 +494,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--mgpu", default="replicate", choices=["replicate", "allgather"],
+    ap.add_argument("--mgpu", default="input", choices=["input", "replicate", "allgather"],
                     help="multi-GPU variant of the destination-range partition (see partition.py)")
     args = ap.parse_args()
     if args.impl == "reference":

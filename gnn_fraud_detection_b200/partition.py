@@ -395,3 +395,139 @@ class ReplicatedInputPartition(DstRangePartition):
                 "d2h_bytes_per_step": d2h * self.world, "steps": steps, "ms_per_step": dt * 1e3,
                 "includes": "per rank: H2D of x + own edge list, CSR/CSC + exchange-index rebuild, fwd+bwd with "
                             "all-to-all/all-gather/all-reduce, D2H of grads"}
+
+
+class InputSpacePartition(DstRangePartition):
+    """Destination-range partition of the FIRST layer in the input-space formulation (csrc/in_common.cuh).
+
+    The layer input x (static for layer 1, ``K*4`` bytes per row) is resident on every GPU in padded position space;
+    each GPU aggregates INPUT rows for its destination range, so nothing is projected redundantly and no per-edge
+    quantity crosses NVLink.  Per step the ranks exchange only per-node logit vectors:
+      forward   all-gather of ``a_src [N,H]`` (32 B per node) and a max-reduce of one scalar (the fp16-pair scale);
+      backward  reduce-scatter of the partial ``da_src [N,H]`` and the all-reduce of the weight gradients.
+    ~64 B per node over NVLink instead of ~2 x 2 KB (all-gather of projected features) or 64 B per EDGE plus 256 B per node
+    (the replicated-input variant above).
+    """
+
+    @classmethod
+    def build(cls, edge_index, num_nodes, rank, world, device):
+        plan = DstRangePlan.build(edge_index, num_nodes, world)
+        self = cls(plan, rank, device)
+        self.local_ei = plan.local_edges(edge_index, rank)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        self.graph = self.build_graph(self.local_ei)
+        torch.cuda.synchronize()
+        self.build_ms = (time.perf_counter() - t0) * 1e3
+        return self
+
+    def prepare_buffers(self, K):
+        from . import functional as Fn
+        self.prep = Fn._aligned_u8(Fn.in_sizes(self.n_local, K)[0], self.device)
+        self.xmax = torch.zeros(16, dtype=torch.float32, device=self.device)
+
+    def layer_fwd_bwd(self, x_full, W, a_s, a_d, bias, d_out, H, C, xw_dtype=None, algo=None, marks=None, graph=None):
+        """``x_full``: the replicated input in padded position space ``[world*rows_padded, K]`` with 16-byte aligned,
+        zero-padded rows (``functional.in_pad_x`` layout).  Returns ``(out [n_local, C], (dW, datt_src, datt_dst, dbias))``
+        with the weight gradients all-reduced."""
+        from . import functional as Fn
+        g = graph or self.graph
+        P, dev, n, K = self.rows_padded, self.device, self.n_local, x_full.size(1)
+        lo = self.rank * P
+        if getattr(self, "prep", None) is None:
+            self.prepare_buffers(K)
+        prep, xmax = self.prep, self.xmax
+        if marks: marks[0].record()
+        # forward: logits of the own rows, gathered from every rank; softmax / aggregation / output GEMM are local
+        xmax.zero_()
+        x_own = x_full[lo:lo + P]
+        a_src_own, a_dst_own = Fn.in_logits(x_own, W, a_s, a_d, prep, xmax)
+        if self.world > 1:
+            a_src_full = torch.empty(self.n_pos, H, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(a_src_full, a_src_own)
+            dist.all_reduce(xmax, op=dist.ReduceOp.MAX)
+        else:
+            a_src_full = a_src_own
+        Fn.in_prepare(W, K, xmax, prep)
+        if marks: marks[1].record()
+        zimg, rowmax, rowsum = Fn.in_fwd(g, x_full, a_src_full, a_dst_own, 0.2, prep)
+        if marks: marks[2].record()
+        out = Fn.in_out(zimg, n, K, prep, bias)
+        if marks: marks[3].record()
+        # backward: edge pass is local; the partial da_src over ALL source positions is reduce-scattered to the owners
+        dz, da_dst = Fn.in_bwd_edges(g, x_full, a_src_full, a_dst_own, rowmax, rowsum, d_out, prep, 0.2)
+        if marks: marks[4].record()
+        da_src_part = Fn.in_dasrc(g, dz)
+        if self.world > 1:
+            da_src = torch.empty(P, H, dtype=torch.float32, device=dev)
+            dist.reduce_scatter_tensor(da_src, da_src_part)
+        else:
+            da_src = da_src_part
+        if marks: marks[5].record()
+        dW, datt_s, datt_d, dbias = Fn.in_bwd_params(zimg, d_out, x_own[:n], W, a_s, a_d, da_src[:n], da_dst, prep)
+        if self.world > 1:
+            D = H * C
+            flat = torch.cat([dW.reshape(-1), datt_s, datt_d, dbias])
+            dist.all_reduce(flat)
+            k = dW.numel()
+            dW, datt_s, datt_d, dbias = flat[:k].view_as(dW), flat[k:k + D], flat[k + D:k + 2 * D], flat[k + 2 * D:]
+        if marks: marks[6].record()
+        return out, (dW, datt_s, datt_d, dbias)
+
+    def e2e(self, args, conv, x_full, N, E_total, K, dev):
+        """End-to-end with HOST buffers: per step every rank copies ITS OWN rows of the input and its destination-range
+        edge list host->device, the input rows are all-gathered over NVLink (instead of every rank pulling the whole
+        input through PCIe), CSR/CSC are rebuilt, forward + backward run with the collectives, and the all-reduced weight
+        gradients are read back."""
+        from . import functional as Fn
+        H, C = conv.heads, conv.out_channels
+        P, lo = self.rows_padded, self.rank * self.rows_padded
+        ld = x_full.stride(0)
+        rows = x_full.as_strided((self.n_pos, ld), (ld, 1))          # the whole padded rows (pad columns included)
+        x_own_host = torch.empty((P, ld), dtype=x_full.dtype, pin_memory=True).copy_(rows[lo:lo + P])
+        ei_host = torch.empty(self.local_ei.shape, dtype=self.local_ei.dtype, pin_memory=True).copy_(self.local_ei)
+        del rows
+        W = conv.lin_src.weight.detach()
+        a_s, a_d = conv.att_src.detach().view(-1).contiguous(), conv.att_dst.detach().view(-1).contiguous()
+        bias = conv.bias.detach()
+        d_out = torch.full((self.n_local, C), 1.0 / N, device=dev)
+        steps = max(1, min(args.steps, args.e2e_steps))
+        self.graph = None
+        del x_full
+        torch.cuda.empty_cache()
+        copy_stream = torch.cuda.Stream(device=dev)
+
+        def one():
+            main = torch.cuda.current_stream()
+            ed = ei_host.to(dev, non_blocking=True)
+            copy_stream.wait_stream(main)
+            with torch.cuda.stream(copy_stream):       # feature copy overlaps the index build below
+                xo = x_own_host.to(dev, non_blocking=True)
+            g = self.build_graph(ed)
+            main.wait_stream(copy_stream)
+            xo.record_stream(main)
+            xf = torch.empty(self.n_pos, ld, dtype=torch.float32, device=dev)
+            if self.world > 1:
+                dist.all_gather_into_tensor(xf, xo)
+            else:
+                xf.copy_(xo)
+            out, grads = self.layer_fwd_bwd(xf[:, :K], W, a_s, a_d, bias, d_out, H, C, graph=g)
+            return [t.cpu() for t in grads] + [out[:1].cpu()]
+
+        one()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = one()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / steps], device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        h2d = x_own_host.numel() * x_own_host.element_size() + ei_host.numel() * ei_host.element_size()
+        d2h = sum(t.numel() * t.element_size() for t in res)
+        return {"value": E_total / dt, "unit": "edges/s", "h2d_bytes_per_step": h2d * self.world,
+                "d2h_bytes_per_step": d2h * self.world, "steps": steps, "ms_per_step": dt * 1e3,
+                "includes": "per rank: H2D of own x rows + own edge list, all-gather of x over NVLink, CSR/CSC rebuild, "
+                            "fwd+bwd with all-gather/reduce-scatter of [N,H] logits, all-reduce of grads, D2H of grads"}

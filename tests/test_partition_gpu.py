@@ -17,7 +17,8 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from gnn_fraud_detection_b200 import _abi, build_csr, functional as Fn, synth
-        from gnn_fraud_detection_b200.partition import DstRangePartition, ReplicatedInputPartition, snapshot_batches
+        from gnn_fraud_detection_b200.partition import (DstRangePartition, InputSpacePartition, ReplicatedInputPartition,
+                                                         snapshot_batches)
         from gnn_fraud_detection_b200 import GATConv
         H, C, K, N, E = 8, 64, 166, 200_000, 2_000_000
         ei = synth.powerlaw_graph(N, E, seed=5, device=dev)
@@ -52,6 +53,34 @@ def _worker(rank, world, port, ret):
         errs += [float((o3 - out[lo:hi]).abs().max()), float((dW3 - dW).abs().max()), float((ds3 - datt_s).abs().max()),
                  float((dd3 - datt_d).abs().max()), float((db3 - dbias).abs().max())]
         rel_dw = max(rel_dw, float((dW3 - dW).norm() / dW.norm()))
+        # input-space formulation (x replicated, only [N,H] logit vectors cross NVLink)
+        part3 = InputSpacePartition.build(ei, N, rank, world, dev)
+        x16 = torch.zeros(part3.n_pos, Fn.in_sizes(0, K)[3], device=dev)
+        x16[part3.plan.to_pos(torch.arange(N, device=dev)), :K] = x
+        o4, (dW4, ds4, dd4, db4) = part3.layer_fwd_bwd(x16[:, :K], W, a_s, a_d, bias, d_out[lo:hi].contiguous(), H, C)
+        errs += [float((o4 - out[lo:hi]).abs().max()), float((dW4 - dW).abs().max()), float((ds4 - datt_s).abs().max()),
+                 float((dd4 - datt_d).abs().max()), float((db4 - dbias).abs().max())]
+        rel_dw = max(rel_dw, float((dW4 - dW).norm() / dW.norm()))
+        # ... and directly against the fp64 CPU oracle on a graph it can hold
+        from oracle import pyg_gatconv as O
+        N2, E2 = 20_000, 200_000
+        ei2 = synth.powerlaw_graph(N2, E2, seed=6, device=dev)
+        x2 = torch.randn(N2, K, device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+        d2 = torch.randn(N2, C, device=dev, generator=torch.Generator(device=dev).manual_seed(4)) / N2
+        p5 = InputSpacePartition.build(ei2, N2, rank, world, dev)
+        lo2, hi2 = int(p5.plan.start[rank]), int(p5.plan.start[rank + 1])
+        x2p = torch.zeros(p5.n_pos, Fn.in_sizes(0, K)[3], device=dev)
+        x2p[p5.plan.to_pos(torch.arange(N2, device=dev)), :K] = x2
+        o5, (dW5, ds5, dd5, db5) = p5.layer_fwd_bwd(x2p[:, :K], W, a_s, a_d, bias, d2[lo2:hi2].contiguous(), H, C)
+        torch.set_num_threads(4)
+        Wc, asc, adc, bc = W.double().cpu(), conv.att_src.detach().double().cpu(), conv.att_dst.detach().double().cpu(), bias.double().cpu()
+        ro, _ = O.gatconv_forward(x2.double().cpu(), ei2.cpu(), Wc, asc, adc, bc, H, C, False)
+        cf = O.gatconv_backward_closed_form(x2.double().cpu(), ei2.cpu(), Wc, asc, adc, H, C, d2.double().cpu(), False, need_dx=False)
+        errs += [float((o5.double().cpu() - ro[lo2:hi2]).abs().max()), float((dW5.double().cpu() - cf["dW"]).abs().max()),
+                 float((ds5.double().cpu() - cf["datt_src"].view(-1)).abs().max()),
+                 float((dd5.double().cpu() - cf["datt_dst"].view(-1)).abs().max()),
+                 float((db5.double().cpu() - cf["dbias"]).abs().max())]
+        rel_dw = max(rel_dw, float((dW5.double().cpu() - cf["dW"]).norm() / cf["dW"].norm()))
         # time-step sharding: a rank's block-diagonal batch reproduces the full-graph rows it owns
         xs, es, ts = synth.elliptic_synth(num_nodes=40_000, num_edges=46_000, num_feats=K, seed=0, device=dev)
         full = conv.eval()(xs, es)
