@@ -278,10 +278,12 @@ in_out_gemm(const uint8_t* __restrict__ zimg, const uint8_t* __restrict__ wimg, 
 constexpr int G3_THREADS = 192;
 constexpr uint32_t G3_A = 2 * KBLOCK;              // 64 KB: two consecutive k-blocks (128 features), hi + lo each
 constexpr uint32_t G3_B = 2 * PLANE;               // 32 KB: dO tile, hi + lo planes
-constexpr int G3_FLUSH = 2;   // node tiles per accumulation chain: 2 x 8 k-steps x 3 MMAs (measured: rel. error 1e-6; 8 tiles drifted to 1e-5)
+#ifndef GNNFD_G3_FLUSH
+#define GNNFD_G3_FLUSH 4
+#endif
+constexpr int G3_FLUSH = GNNFD_G3_FLUSH;   // node tiles per accumulation chain (chain = G3_FLUSH x 8 k-steps x 3 MMAs)
 constexpr int G3_STG_LD = 33;
 constexpr size_t G3_SMEM = 2 * size_t(G3_A) + 2 * size_t(G3_B) + 4 * 32 * G3_STG_LD * 4 + 1024;
-constexpr int G3_MAX_MT = 6;
 
 __global__ void __launch_bounds__(G3_THREADS, 1)
 in_dw_gemm(const uint8_t* __restrict__ zimg, const float* __restrict__ d_out, const float* __restrict__ dmax, int64_t n,

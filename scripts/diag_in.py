@@ -119,8 +119,47 @@ def case(name, N, K, ei, seed=0, n_blocks=None, keep=None, p=0.0):
     return max(r)
 
 
+def big_case(N=200_000, E=2_000_000, K=166):
+    """dW / datt accuracy at a size where the node-reduction chains are long: fp64 reference evaluated on the GPU."""
+    print(f"== big: N={N} E={E}")
+    dev = torch.device("cuda")
+    W, a_s, a_d, b = seeded_params(K, H, C, False, seed=1)
+    ei = synth.powerlaw_graph(N, E, seed=5, device=dev)
+    x = torch.randn(N, K, device=dev, generator=torch.Generator(device=dev).manual_seed(0))
+    d_out = torch.randn(N, C, device=dev, generator=torch.Generator(device=dev).manual_seed(2)) / N
+    with torch.device("cuda"):
+        cf = O.gatconv_backward_closed_form(x.double(), ei, W.double().cuda(), a_s.double().cuda(), a_d.double().cuda(), H, C,
+                                            d_out.double(), False, need_dx=False)
+        ro, _ = O.gatconv_forward(x.double(), ei, W.double().cuda(), a_s.double().cuda(), a_d.double().cuda(), b.double().cuda(), H, C, False)
+    g = build_csr(ei, N)
+    xg, Wg = Fn.in_pad_x(x), W.to(dev)
+    asg, adg, bg = a_s.to(dev).view(-1).contiguous(), a_d.to(dev).view(-1).contiguous(), b.to(dev)
+    prep = Fn._aligned_u8(Fn.in_sizes(N, K)[0], dev)
+    xmax = torch.zeros(16, device=dev)
+    a_src, a_dst = Fn.in_logits(xg, Wg, asg, adg, prep, xmax)
+    Fn.in_prepare(Wg, K, xmax, prep)
+    zimg, rowmax, rowsum = Fn.in_fwd(g, xg, a_src, a_dst, 0.2, prep)
+    out = Fn.in_out(zimg, N, K, prep, bg)
+    err("out", out, ro)
+    dz, da_dst = Fn.in_bwd_edges(g, xg, a_src, a_dst, rowmax, rowsum, d_out, prep, 0.2)
+    da_src = Fn.in_dasrc(g, dz)
+    err("da_src", da_src, cf["da_src"]); err("da_dst", da_dst, cf["da_dst"])
+    dW, ds, dd, db = Fn.in_bwd_params(zimg, d_out, xg, Wg, asg, adg, da_src, da_dst, prep)
+    err("dW", dW, cf["dW"]); err("datt_src", ds, cf["datt_src"].view(-1)); err("datt_dst", dd, cf["datt_dst"].view(-1)); err("dbias", db, cf["dbias"])
+    # the projected-feature path on the same inputs
+    xw, a_src2, a_dst2 = Fn.project_fwd(x, Wg, asg, adg, H, C)
+    out2, rm2, rs2 = Fn.gat_fwd(g, xw, a_src2, a_dst2, bg, H, C, 0.2, False)
+    dxw, das2, dad2 = Fn.gat_bwd(g, xw, a_src2, a_dst2, rm2, rs2, d_out, asg, adg, H, C, 0.2, False)
+    dW2, ds2, dd2, db2, _ = Fn.project_bwd(x, Wg, dxw, xw, das2, dad2, d_out, H, C, C, False)
+    print("  projected-feature path:")
+    err("out", out2, ro); err("dW", dW2, cf["dW"]); err("datt_src", ds2, cf["datt_src"].view(-1)); err("dbias", db2, cf["dbias"])
+
+
 def main():
     torch.manual_seed(0)
+    if os.environ.get("DIAG_BIG"):
+        big_case()
+        return
     worst = 0.0
     worst = max(worst, case("tiny", 3, 5, torch.tensor([[0, 1, 2, 2], [1, 2, 0, 2]])))
     worst = max(worst, case("small", 300, 166, synth.random_graph(300, 1500, seed=2)))

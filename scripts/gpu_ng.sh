@@ -1,8 +1,11 @@
 #!/bin/bash
-# usage: gpu_ng.sh G   -- one scaling point of the default bench (replicate variant), without the e2e leg
+# scaling point at G GPUs (run under gpurun --gpus G): parity test (first 4 GPUs) + headline workload
+G=${1:-4}
 mkdir -p gpurun_out
-G=$1
-timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 2951$G bench.py --gpus $G --steps 5 --warmup 3 --no-e2e > gpurun_out/bench_scale_${G}.log 2>&1
-echo "G=$G exit $?"; tail -1 gpurun_out/bench_scale_${G}.log | python -c "
+if [ "${2:-test}" = "test" ]; then
+timeout 400 python -m pytest tests/test_partition_gpu.py -x -q -p no:cacheprovider > gpurun_out/pytest_mgpu_${G}g.log 2>&1; echo "pytest exit $?"; tail -3 gpurun_out/pytest_mgpu_${G}g.log
+fi
+GNNFD_BENCH_DEBUG=1 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $G --steps 10 --warmup 3 > gpurun_out/bench_scale_${G}.log 2> gpurun_out/bench_scale_${G}.err
+echo "G=$G exit $?"; grep "stages_ms" gpurun_out/bench_scale_${G}.err | head -8; tail -1 gpurun_out/bench_scale_${G}.log | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['roofline'].get('stages_ms'))"
+d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'], d['roofline']['stages_ms'], d['e2e'], d['config']['csr_build_ms'])"
