@@ -10,6 +10,10 @@
 #include "in_common.cuh"
 #include "gat_phase_bwd.cuh"
 
+#ifndef GNNFD_IN_UNROLL_BWD
+#define GNNFD_IN_UNROLL_BWD 4
+#endif
+
 #include <atomic>
 #include <climits>
 #include <cstdlib>
@@ -19,6 +23,7 @@ extern std::atomic<long long> g_launches;
 int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who);
 
 namespace in {
+constexpr int IN_UNROLL_BWD = GNNFD_IN_UNROLL_BWD;
 bool in_x_ok(const float* x, int64_t ldx, int KP);   // gat_in_fwd.cu
 
 
@@ -126,7 +131,10 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
     while (true) {
         const int* j0 = ring.j_s + b0 * 32;
         const int* j1 = ring.j_s + (b0 ^ 1) * 32;
-        while (ring.has_room() && issued0 < c0.n) ring.issue(j0[issued0++], lane);
+        {
+            const int kk = min(ring.room(), c0.n - issued0);
+            if (kk > 0) { ring.issue_many(j0 + issued0, kk, lane); issued0 += kk; }
+        }
         kind1 = next(c1, k1);
         issued1 = 0;
         if (kind1) {
@@ -141,31 +149,46 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
         }
         int rows_done = 0;
         const int* bits0 = bits_s + b0 * 32;
-        // phase B: dot products of the staged x rows with this row's Gd (lane = head, quarter)
-        for (int t = 0; t < c0.n; ++t) {
-            const uint32_t a = ring.front() + uint32_t(q) * 16u;
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;     // four independent FMA chains
+        // packs: lanes (= staged edges) that end a row
+        const unsigned lastmask = (PACK && kind0 == 2) ? __ballot_sync(FULL, (bits0[lane] >> 26) & 1) : 0u;
+        // phase B: dot products of the staged x rows with this row's Gd (lane = head, quarter); edges in groups of four:
+        // one warp barrier and one (multi-lane) refill per group
+        for (int t0 = 0; t0 < c0.n; t0 += 4) {
+            const int cnt = min(4, c0.n - t0);
+#pragma unroll IN_UNROLL_BWD
+            for (int r = 0; r < 4; ++r) {
+                if (r < cnt) {
+                    const int t = t0 + r;
+                    const uint32_t a = ring.front_at(r) + uint32_t(q) * 16u;
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;     // four independent FMA chains
 #pragma unroll
-            for (int i = 0; i < RG::NI; ++i)
-                if (RG::valid(i, q, n4)) {
-                    const float4 v = lds128(a + uint32_t(i) * 64u);
-                    d0 = fmaf(g[i].x, v.x, d0); d1 = fmaf(g[i].y, v.y, d1);
-                    d2 = fmaf(g[i].z, v.z, d2); d3 = fmaf(g[i].w, v.w, d3);
+                    for (int i = 0; i < RG::NI; ++i)
+                        if (RG::valid(i, q, n4)) {
+                            const float4 v = lds128(a + uint32_t(i) * 64u);
+                            d0 = fmaf(g[i].x, v.x, d0); d1 = fmaf(g[i].y, v.y, d1);
+                            d2 = fmaf(g[i].z, v.z, d2); d3 = fmaf(g[i].w, v.w, d3);
+                        }
+                    float d = (d0 + d1) + (d2 + d3);
+                    d += __shfl_xor_sync(FULL, d, 1);
+                    d += __shfl_xor_sync(FULL, d, 2);
+                    if (q == 0) dal_s[t * H + h] = d;
+                    gdb.flush(lane);             // every lane has consumed g in the FMAs above (the shuffles are the meeting point)
+                    if (PACK && t + 1 < c0.n && ((lastmask >> t) & 1u)) {
+                        // row boundary inside the pack: switch to the next row's Gd, prefetch the one after it
+                        ++rows_done;
+                        gdb.take(c0.row + rows_done, lane, g);
+                        if (rows_done + 1 < k0) gdb.want_later(c0.row + rows_done + 1);
+                        else if (kind1 && c1.first) gdb.want_later(c1.row);
+                    }
                 }
-            float d = (d0 + d1) + (d2 + d3);
-            d += __shfl_xor_sync(FULL, d, 1);
-            d += __shfl_xor_sync(FULL, d, 2);
-            if (q == 0) dal_s[t * H + h] = d;
-            ring.pop();
-            gdb.flush(lane);                 // every lane has consumed g in the FMAs above
-            if (issued0 < c0.n) ring.issue(j0[issued0++], lane);
-            else if (kind1 && issued1 < c1.n) ring.issue(j1[issued1++], lane);
-            if (PACK && kind0 == 2 && t + 1 < c0.n && ((bits0[t] >> 26) & 1)) {
-                // row boundary inside the pack: switch to the next row's Gd, prefetch the one after it
-                ++rows_done;
-                gdb.take(c0.row + rows_done, lane, g);
-                if (rows_done + 1 < k0) gdb.want_later(c0.row + rows_done + 1);
-                else if (kind1 && c1.first) gdb.want_later(c1.row);
+            }
+            ring.pop_many(cnt);
+            int free_slots = cnt;
+            const int kk = min(free_slots, c0.n - issued0);
+            if (kk > 0) { ring.issue_many(j0 + issued0, kk, lane); issued0 += kk; free_slots -= kk; }
+            if (kind1 && free_slots > 0) {
+                const int kn = min(free_slots, c1.n - issued1);
+                if (kn > 0) { ring.issue_many(j1 + issued1, kn, lane); issued1 += kn; }
             }
         }
         __syncwarp();

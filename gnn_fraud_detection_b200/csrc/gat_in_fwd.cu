@@ -12,6 +12,10 @@
 #include "in_common.cuh"
 #include "gat_phase_fwd.cuh"
 
+#ifndef GNNFD_IN_UNROLL_FWD
+#define GNNFD_IN_UNROLL_FWD 1     // the row epilogue (image write) sits inside the edge loop: unrolling it 4x thrashes the i-cache
+#endif
+
 #include <atomic>
 #include <climits>
 #include <cstdlib>
@@ -22,6 +26,7 @@ int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who);
 int in_build_gd_image(const float* W, int K, void* prep, cudaStream_t st);   // project_tc.cu
 
 namespace in {
+constexpr int IN_UNROLL_FWD = GNNFD_IN_UNROLL_FWD;
 
 // ---- u = W_h^T att  ([2H][KP]) --------------------------------------------------------------------------------------
 __global__ void in_u_kernel(const float* __restrict__ W, const float* __restrict__ att_src, const float* __restrict__ att_dst,
@@ -282,7 +287,10 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
     while (true) {
         const int* j0 = ring.j_s + b0 * 32;
         const int* j1 = ring.j_s + (b0 ^ 1) * 32;
-        while (ring.has_room() && issued0 < c0.n) ring.issue(j0[issued0++], lane);
+        {
+            const int k0 = min(ring.room(), c0.n - issued0);
+            if (k0 > 0) { ring.issue_many(j0 + issued0, k0, lane); issued0 += k0; }
+        }
         kind1 = next(c1);
         issued1 = 0;
         if (kind1) phase_a(c1, kind1, b0 ^ 1);
@@ -292,7 +300,10 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
             acc_zero(acc);
         }
         float fch = 1.f;
-        if (!(PACK && kind0 == 2)) {
+        unsigned lastmask = 0;                          // packs: lanes (= staged edges) that end a row
+        if (PACK && kind0 == 2) {
+            lastmask = __ballot_sync(FULL, r_all[b0 * 32 + lane] < 0);
+        } else {
             const float cm = pick_head(c0.cm, h), cs = pick_head(c0.cs, h);
             const float mn = fmaxf(m, cm);
             const float fold = expf(m - mn);            // 0 on the first chunk (m = -inf)
@@ -305,26 +316,35 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
             }
         }
         const float* p0 = ring.p_s + b0 * 32 * H + h;
-        const int* r0 = r_all + b0 * 32;
-        for (int t = 0; t < c0.n; ++t) {
-            const uint32_t a = ring.front() + uint32_t(q) * 16u;
-            const float w = p0[t * H] * fch;
+        // edges in groups of four: one warp barrier and one (multi-lane) refill per group
+        for (int t0 = 0; t0 < c0.n; t0 += 4) {
+            const int cnt = min(4, c0.n - t0);
+#pragma unroll IN_UNROLL_FWD
+            for (int r = 0; r < 4; ++r) {
+                if (r < cnt) {
+                    const int t = t0 + r;
+                    const uint32_t a = ring.front_at(r) + uint32_t(q) * 16u;
+                    const float w = p0[t * H] * fch;
 #pragma unroll
-            for (int i = 0; i < RG::NI; ++i)
-                if (RG::valid(i, q, n4)) {
-                    const float4 v = lds128(a + uint32_t(i) * 64u);
-                    acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y);
-                    acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
+                    for (int i = 0; i < RG::NI; ++i)
+                        if (RG::valid(i, q, n4)) {
+                            const float4 v = lds128(a + uint32_t(i) * 64u);
+                            acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y);
+                            acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
+                        }
+                    if (PACK && ((lastmask >> t) & 1u)) {     // last edge of a packed row (weights already normalised)
+                        sink.finish_norm(c0.row + __popc(lastmask & ((1u << t) - 1u)), acc, lane);
+                        acc_zero(acc);
+                    }
                 }
-            ring.pop();
-            if (issued0 < c0.n) ring.issue(j0[issued0++], lane);
-            else if (kind1 && issued1 < c1.n) ring.issue(j1[issued1++], lane);
-            if (PACK && kind0 == 2) {
-                const int rs = r0[t];
-                if (rs < 0) {                                   // last edge of a packed row (weights already normalised)
-                    sink.finish_norm(rs & 0x7fffffff, acc, lane);
-                    acc_zero(acc);
-                }
+            }
+            ring.pop_many(cnt);
+            int free_slots = cnt;
+            const int k0 = min(free_slots, c0.n - issued0);
+            if (k0 > 0) { ring.issue_many(j0 + issued0, k0, lane); issued0 += k0; free_slots -= k0; }
+            if (kind1 && free_slots > 0) {
+                const int k1 = min(free_slots, c1.n - issued1);
+                if (k1 > 0) { ring.issue_many(j1 + issued1, k1, lane); issued1 += k1; }
             }
         }
         if (kind0 == 1 && c0.last) sink.finish(c0.row, m, s, acc, lane);

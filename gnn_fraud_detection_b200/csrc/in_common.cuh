@@ -197,11 +197,26 @@ struct InRing {
         }
         ++issued;
     }
-    // wait for the oldest in-flight row; returns its shared-space address
-    __device__ __forceinline__ uint32_t front()
+    // rows j[0..cnt) in ONE divergent block: lane r < cnt hands row j[r] to the copy engine (cnt <= IN_R)
+    __device__ __forceinline__ void issue_many(const int* j, int cnt, int lane)
     {
-        const uint32_t s = uint32_t(consumed) & (IN_R - 1);
-        mbar_wait_u32(full_u32 + 8u * s, uint32_t(consumed >> IN_LOG_R) & 1u);
+        if (lane < cnt) {
+            const uint32_t n = uint32_t(issued + lane);
+            const uint32_t s = n & (IN_R - 1);
+            const uint32_t bar = full_u32 + 8u * s;
+            mbar_expect_tx_u32(bar, slot);
+            bulk_g2s_u32(ring_u32 + s * slot, x + int64_t(j[lane]) * ldx, slot, bar);
+        }
+        issued += cnt;
+    }
+    // wait for the oldest in-flight row; returns its shared-space address
+    __device__ __forceinline__ uint32_t front() { return front_at(0); }
+    // ... for the r-th oldest
+    __device__ __forceinline__ uint32_t front_at(int r)
+    {
+        const uint32_t n = uint32_t(consumed + r);
+        const uint32_t s = n & (IN_R - 1);
+        mbar_wait_u32(full_u32 + 8u * s, (n >> IN_LOG_R) & 1u);
         return ring_u32 + s * slot;
     }
     __device__ __forceinline__ void pop()
@@ -209,6 +224,13 @@ struct InRing {
         __syncwarp();
         ++consumed;
     }
+    // the cnt oldest rows have been consumed by every lane (their loads fed FMAs that have issued)
+    __device__ __forceinline__ void pop_many(int cnt)
+    {
+        __syncwarp();
+        consumed += cnt;
+    }
+    __device__ __forceinline__ int room() const { return IN_R - (issued - consumed); }
 };
 
 // arr[h] with a run-time h, without dynamic register indexing

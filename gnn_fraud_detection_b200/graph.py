@@ -8,6 +8,7 @@ epoch (``src/train.py:124``), so the CSR is built once and cached on the tensor'
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from collections import OrderedDict
 from typing import Optional
 
@@ -162,22 +163,32 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = T
 
 
 class CSRCache:
-    """Small LRU keyed on the identity of the edge_index tensor (full-batch training reuses it)."""
+    """Small LRU keyed on the identity of the edge_index tensor (full-batch training reuses it).
+
+    The key is ``(data_ptr, shape, strides, _version, device, num_nodes, add_self_loops)``.  An entry does NOT keep the
+    tensor alive: it holds a weak reference and a finalizer drops the entry when the tensor dies, so a one-shot
+    ``edge_index`` (the reference's train loop moves a fresh batch to the device every step, ``src/train.py:105``) does not
+    pin its CSR/CSC in HBM, and a recycled ``data_ptr`` cannot hit a stale entry.  Inference tensors carry no version
+    counter and are built uncached.  For streaming use, build the graph once with ``build_csr`` and pass the ``GraphCSR``.
+    """
 
     def __init__(self, capacity: int = 8):
         self.capacity = capacity
         self._d: "OrderedDict[tuple, tuple]" = OrderedDict()
 
     def get(self, edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool, build_csc: bool) -> GraphCSR:
-        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_index._version, edge_index.device.index,
-               int(num_nodes), bool(add_self_loops))
+        if edge_index.is_inference():
+            return build_csr(edge_index, num_nodes, add_self_loops, build_csc)
+        key = (edge_index.data_ptr(), tuple(edge_index.shape), tuple(edge_index.stride()), edge_index._version,
+               edge_index.device.index, int(num_nodes), bool(add_self_loops))
         hit = self._d.get(key)
-        if hit is not None and (hit[0].has_csc or not build_csc):
+        if hit is not None and hit[1]() is edge_index and (hit[0].has_csc or not build_csc):
             self._d.move_to_end(key)
             return hit[0]
         g = build_csr(edge_index, num_nodes, add_self_loops, build_csc)
-        # keep a reference to the tensor so its storage (and therefore data_ptr) cannot be recycled
-        self._d[key] = (g, edge_index)
+        ref = weakref.ref(edge_index)
+        weakref.finalize(edge_index, self._d.pop, key, None)
+        self._d[key] = (g, ref)
         self._d.move_to_end(key)
         while len(self._d) > self.capacity:
             self._d.popitem(last=False)

@@ -81,6 +81,25 @@ class GATConv(nn.Module):
         need_csc = torch.is_grad_enabled()
         return GLOBAL_CSR_CACHE.get(edge_index, num_nodes, self.add_self_loops, need_csc)
 
+    def _check_inputs(self, x: torch.Tensor, g: GraphCSR, residual: Optional[torch.Tensor] = None):
+        """Shape / dtype / device checks shared by the training path and the fused inference path: the C ABI takes raw
+        pointers, so a wrong dtype or row count must be caught here."""
+        if not x.is_cuda:
+            raise RuntimeError("gnn_fraud_detection_b200.GATConv runs on CUDA only (no CPU fallback)")
+        if x.dtype != torch.float32:
+            raise TypeError(f"x must be float32, got {x.dtype}")
+        if x.dim() != 2 or x.size(1) != self.in_channels:
+            raise ValueError(f"x must be [N,{self.in_channels}], got {tuple(x.shape)}")
+        if x.size(0) != g.n_src:
+            raise ValueError(f"x has {x.size(0)} rows but the graph has {g.n_src} source nodes")
+        if g.device != x.device:
+            raise RuntimeError(f"graph lives on {g.device} but x on {x.device}")
+        if residual is not None:
+            Co = self.heads * self.out_channels if self.concat else self.out_channels
+            if tuple(residual.shape) != (g.n_dst, Co) or residual.dtype != torch.float32 or residual.device != x.device:
+                raise ValueError(f"residual must be float32 [{g.n_dst},{Co}] on {x.device}, got {residual.dtype} "
+                                 f"{tuple(residual.shape)} on {residual.device}")
+
     def forward(self, x: torch.Tensor, edge_index, edge_attr=None, size=None, return_attention_weights=None,
                 dropout_mask: Optional[torch.Tensor] = None):
         """``x [N, in_channels]`` fp32 cuda, ``edge_index [2,E]`` int64 cuda -> ``[N, out_channels]``.
@@ -93,13 +112,22 @@ class GATConv(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("gnn_fraud_detection_b200.GATConv runs on CUDA only (no CPU fallback)")
         g = self._graph(edge_index, x.size(0))
+        self._check_inputs(x, g)
         H, C = self.heads, self.out_channels
         p = self.dropout if self.training else 0.0
         keep = None
         if dropout_mask is not None:
+            if not self.dropout > 0.0:
+                raise ValueError("dropout_mask was given but this layer has dropout=0: the mask would be ignored")
             keep = dropout_mask.to(device=x.device, dtype=torch.uint8).contiguous()
             p = self.dropout
-        elif p > 0.0:
+        if p >= 1.0:
+            # F.dropout(alpha, p=1) zeroes every attention coefficient: the aggregation vanishes, the bias remains
+            if return_attention_weights:
+                raise NotImplementedError("return_attention_weights with dropout >= 1")
+            out = x.new_zeros(g.n_dst, H * C if self.concat else C)
+            return out + self.bias if self.bias is not None else out
+        if keep is None and p > 0.0:
             keep = (torch.rand(g.n_edges, H, device=x.device) >= p).to(torch.uint8)
         if keep is not None and tuple(keep.shape) != (g.n_edges, H):
             raise ValueError(f"dropout_mask must be [{g.n_edges},{H}], got {tuple(keep.shape)}")
@@ -109,16 +137,17 @@ class GATConv(nn.Module):
         if not return_attention_weights:
             return res
         out, a_src, a_dst, rowmax, rowsum = res
-        alpha_csr = gat_alpha(g, a_src, a_dst, rowmax, rowsum, H, self.negative_slope)
-        # PyG returns (edge_index', alpha) in edge_index' order: un-permute the CSR-ordered alpha
-        perm = g.perm.long()
-        alpha = torch.empty_like(alpha_csr)
-        alpha[perm] = alpha_csr
-        dst_sorted = torch.repeat_interleave(torch.arange(g.n_dst, device=x.device),
-                                             (g.rowptr[1:] - g.rowptr[:-1]).long())
-        ei = torch.empty(2, g.n_edges, dtype=torch.int64, device=x.device)
-        ei[0, perm] = g.col.long()
-        ei[1, perm] = dst_sorted
+        with torch.cuda.device(x.device):
+            alpha_csr = gat_alpha(g, a_src, a_dst, rowmax, rowsum, H, self.negative_slope)
+            # PyG returns (edge_index', alpha) in edge_index' order: un-permute the CSR-ordered alpha
+            perm = g.perm.long()
+            alpha = torch.empty_like(alpha_csr)
+            alpha[perm] = alpha_csr
+            dst_sorted = torch.repeat_interleave(torch.arange(g.n_dst, device=x.device),
+                                                 (g.rowptr[1:] - g.rowptr[:-1]).long())
+            ei = torch.empty(2, g.n_edges, dtype=torch.int64, device=x.device)
+            ei[0, perm] = g.col.long()
+            ei[1, perm] = dst_sorted
         return out, (ei, alpha)
 
     @torch.no_grad()
@@ -126,11 +155,13 @@ class GATConv(nn.Module):
                            relu: bool = True, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Inference-only fast path for the reference's layer loop (``src/models/gat.py:80-91``):
         ``residual + relu(batch_norm_eval(gat(x, edge_index)))`` with the BatchNorm (running statistics folded to
-        a per-channel affine), the ReLU and the residual add fused into the aggregation kernel's row epilogue."""
+        a per-channel affine), the ReLU and the residual add fused into the aggregation kernel's row epilogue (or, for a
+        ``gemm_algo=GEMM_INPUT`` first layer, into the epilogue of the output GEMM)."""
         from . import functional as Fn
         if not x.is_cuda:
             raise RuntimeError("gnn_fraud_detection_b200.GATConv runs on CUDA only (no CPU fallback)")
         g = self._graph(edge_index, x.size(0))
+        self._check_inputs(x, g, residual)
         H, C = self.heads, self.out_channels
         scale = shift = None
         if batch_norm is not None:
@@ -139,13 +170,24 @@ class GATConv(nn.Module):
             b = batch_norm.bias if batch_norm.bias is not None else torch.zeros_like(inv)
             scale = (w * inv).contiguous()
             shift = (b - batch_norm.running_mean * w * inv).contiguous()
-        x = x if x.stride(1) == 1 else x.contiguous()
+        act = _abi.ACT_RELU if relu else _abi.ACT_NONE
+        res = None if residual is None else residual.contiguous()
+        W = self.lin_src.weight.contiguous()
+        a_s, a_d = self.att_src.reshape(-1), self.att_dst.reshape(-1)
         with torch.cuda.device(x.device):
-            xw, a_src, a_dst = Fn.project_fwd(x, self.lin_src.weight.contiguous(), self.att_src.reshape(-1),
-                                              self.att_dst.reshape(-1), H, C, self.feature_dtype, self.gemm_algo)
-            out, _, _ = Fn.gat_fwd(g, xw, a_src, a_dst, self.bias, H, C, self.negative_slope, self.concat,
-                                   _abi.ACT_RELU if relu else _abi.ACT_NONE, None, 0.0, scale, shift,
-                                   None if residual is None else residual.contiguous())
+            if self.gemm_algo == _abi.GEMM_INPUT and Fn.in_supported(x.size(1), H, C, self.concat):
+                K = x.size(1)
+                x16 = Fn.in_pad_x(x)
+                prep = Fn._aligned_u8(Fn.in_sizes(g.n_dst, K)[0], x.device)
+                xmax = torch.zeros(16, dtype=torch.float32, device=x.device)
+                a_src, a_dst = Fn.in_logits(x16, W, a_s, a_d, prep, xmax)
+                Fn.in_prepare(W, K, xmax, prep)
+                zimg, _, _ = Fn.in_fwd(g, x16, a_src, a_dst, self.negative_slope, prep)
+                return Fn.in_out(zimg, g.n_dst, K, prep, self.bias, act, scale, shift, res)
+            x = x if x.stride(1) == 1 else x.contiguous()
+            xw, a_src, a_dst = Fn.project_fwd(x, W, a_s, a_d, H, C, self.feature_dtype, self.gemm_algo)
+            out, _, _ = Fn.gat_fwd(g, xw, a_src, a_dst, self.bias, H, C, self.negative_slope, self.concat, act, None, 0.0,
+                                   scale, shift, res)
         return out
 
     def extra_repr(self):

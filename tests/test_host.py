@@ -116,3 +116,43 @@ def test_snapshot_builder_has_no_cpu_fallback_and_validates_arguments():
     assert torch.equal(ids, torch.tensor([0, 1, 2])) and torch.equal(el, ei) and torch.equal(xl, x)
     xo, eo, ido = O.temporal_subgraph_oracle(x, ei, ts, 1)
     assert ido.tolist() == [0, 1] and eo.tolist() == [[0], [1]]
+
+
+# ---- CSR cache: key, lifetime, inference tensors -----------------------------------------------------
+class _FakeGraph:
+    has_csc = True
+
+
+def test_csr_cache_key_lifetime_and_inference_tensors(monkeypatch):
+    import gc
+    from gnn_fraud_detection_b200 import graph
+    built = []
+
+    def fake_build(edge_index, num_nodes, add_self_loops=True, build_csc=True, **kw):
+        built.append((edge_index.data_ptr(), tuple(edge_index.shape), tuple(edge_index.stride())))
+        return _FakeGraph()
+
+    monkeypatch.setattr(graph, "build_csr", fake_build)
+    cache = graph.CSRCache(capacity=4)
+    base = torch.arange(24, dtype=torch.int64).view(2, 12)
+    a = base[:, :3]                                     # same data_ptr / shape / version, different strides
+    b = base.view(-1)[:6].view(2, 3)
+    ga, gb = cache.get(a, 5, True, True), cache.get(b, 5, True, True)
+    assert ga is not gb and len(built) == 2
+    assert cache.get(a, 5, True, True) is ga and len(built) == 2          # hit
+    base[0, 0] = 7                                                        # in-place edit bumps _version: rebuilt
+    assert cache.get(a, 5, True, True) is not ga and len(built) == 3
+    # an entry does not keep its tensor alive, and dies with it
+    t = torch.zeros(2, 4, dtype=torch.int64)
+    cache.get(t, 9, True, True)
+    n = len(cache._d)
+    del t
+    gc.collect()
+    assert len(cache._d) == n - 1
+    # inference tensors have no version counter: built uncached instead of raising
+    with torch.inference_mode():
+        u = torch.zeros(2, 4, dtype=torch.int64)
+        n_built, n_entries = len(built), len(cache._d)
+        cache.get(u, 9, True, True)
+        cache.get(u, 9, True, True)
+    assert len(built) == n_built + 2 and len(cache._d) == n_entries
