@@ -39,7 +39,7 @@ WORKLOADS = {
     "elliptic": (203_769, 234_355, 166),
     "skew": (1_000_000, 5_000_000 + 16 * 131_072 + 64_000, 166),
 }
-CPU_SAMPLE = (50_000, 500_000, 166)   # 1/400-scale power-law graph for the CPU arm (bounded sample)
+CPU_SAMPLE = (200_000, 2_000_000, 166)   # 1/100-scale power-law graph for the CPU arm (bounded sample)
 
 
 def env_int(name, default):
@@ -115,13 +115,30 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm (reference formulation = oracle port)
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step_fn(N, E, K, threads):
-    """Returns (step_fn, description).  Only bench.py's cpu_baseline / --impl reference legs use the oracle."""
+def cpu_sample_for(workload: str):
+    """(N, E, K, same_config): the Elliptic-shaped workload runs at FULL size on the host (BASELINE.json configs[0]/[1]);
+    the power-law / skew workloads cannot (PyG's [E',8,64] message tensor alone is 450 GB at 200M edges), so the CPU arm
+    runs the 1/100-scale graph of the same family."""
+    if workload == "elliptic":
+        return WORKLOADS["elliptic"] + (True,)
+    return CPU_SAMPLE + (False,)
+
+
+def cpu_reference_step_fn(workload, threads):
+    """Returns (step_fn, kind, description, E, same_config).  Only bench.py's cpu_baseline / --impl reference legs use the
+    oracle."""
     from gnn_fraud_detection_b200 import synth
     from oracle import pyg_gatconv as O
     torch.set_num_threads(threads)
     kind = "port"
-    ei = synth.powerlaw_graph(N, E, seed=1234, device="cpu")
+    N, E, K, same = cpu_sample_for(workload)
+    if workload == "elliptic":
+        ei = synth.elliptic_synth(N, E, 1, seed=0, device="cpu")[1]
+        what = f"Elliptic-shaped graph N={N} E={E} K={K} at FULL size (same config as the GPU arm)"
+    else:
+        ei = synth.powerlaw_graph(N, E, seed=1234, device="cpu")
+        what = f"power-law graph N={N} E={E} K={K} (1/{200_000_000 // E}-scale powerlaw_200m)"
+    E = ei.size(1)
     x = torch.randn(N, K, generator=torch.Generator().manual_seed(0))
     torch.manual_seed(1)
     conv = O.OracleGATConv(K, C, heads=H, concat=False, dropout=0.0)
@@ -138,7 +155,7 @@ def cpu_reference_step_fn(N, E, K, threads):
         out.backward(d_out)
         return float(out[0, 0].detach())
 
-    return step, kind, f"power-law graph N={N} E={E} K={K} (1/{200_000_000 // E}-scale powerlaw_200m), one GATConv fwd+bwd"
+    return step, kind, what + ", one GATConv fwd+bwd", E, same
 
 
 def run_reference_arm(args):
@@ -146,8 +163,8 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    N, E, K = CPU_SAMPLE
-    step, kind, sample = cpu_reference_step_fn(N, E, K, threads)
+    step, kind, sample, E, same = cpu_reference_step_fn(args.workload, threads)
+    K = WORKLOADS[args.workload][2]
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.perf_counter()
@@ -159,7 +176,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": max(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "reference_sample": sample, "H": H, "C": C, "K": K,
+        "config": {"workload": args.workload, "reference_sample": sample, "same_config": same, "H": H, "C": C, "K": K,
                    "note": "reference = PyG GATConv formulation on host cores; torch_geometric is absent from "
                            "this image so the CPU oracle port (oracle/pyg_gatconv.py) is what runs"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
@@ -400,15 +417,14 @@ def run_gpu_arm(args):
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        cn, ce, ck = CPU_SAMPLE
-        cstep, kind, sample = cpu_reference_step_fn(cn, ce, ck, threads)
+        cstep, kind, sample, ce, same = cpu_reference_step_fn(workload, threads)
         cstep()
         t0 = time.perf_counter()
         reps = 2
         for _ in range(reps):
             cstep()
         cdt = (time.perf_counter() - t0) / reps
-        cpu = {"value": ce / cdt, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+        cpu = {"value": ce / cdt, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample, "same_config": same,
                "ms_per_step": cdt * 1e3}
 
     if rank == 0:

@@ -92,3 +92,39 @@ def test_fused_eval_epilogue_matches_unfused_and_oracle(golden_dir):
         got = conv.forward_fused_eval(h, ei, bn, relu=True, residual=h)
         assert maxabs(got, ref) <= 1e-5
         assert maxabs(conv.forward_fused_eval(h, ei, None, relu=False), conv(h, ei)) <= 1e-6
+
+
+def test_models_match_the_reference_wrappers_own_outputs(golden_dir):
+    """reference_models_golden.npz = the reference's unmodified GAT / TemporalGNN classes (layer := CPU oracle) with the
+    reference's checkpoints: eval logits, and one full training step (train-mode BatchNorm, masked BCE(pos_weight=50),
+    dropout 0) in fp64 -- loss, logits and every parameter gradient."""
+    gold = np.load(os.path.join(golden_dir, "reference_models_golden.npz"))
+    small = np.load(os.path.join(golden_dir, "golden_small.npz"))
+    x, ei = torch.from_numpy(small["x"]).cuda(), torch.from_numpy(small["edge_index"]).cuda()
+    y = torch.from_numpy(gold["train_y"]).cuda()
+    mask = y != -1
+    crit = torch.nn.BCEWithLogitsLoss(pos_weight=torch.tensor(50.0, device="cuda"))
+    for name, cls, ck in (("gat", GAT, "gat_ckpt.npz"), ("tgn", TemporalGNN, "tgn_ckpt.npz")):
+        m = load_ckpt(cls(x.size(1), 64, 1, num_layers=3), os.path.join(golden_dir, ck)).cuda().eval()
+        with torch.no_grad():
+            r = m(x, ei)
+        lg = r[0] if name == "tgn" else r
+        assert np.abs(lg.cpu().numpy() - gold[f"{name}_logits_f64"]).max() <= 1e-4
+        if name == "tgn":
+            assert np.abs(r[1].cpu().numpy() - gold["tgn_hidden_f64"]).max() <= 1e-4
+        # training step
+        m = load_ckpt(cls(x.size(1), 64, 1, num_layers=3, dropout=0.0), os.path.join(golden_dir, ck)).cuda().train()
+        r = m(x, ei)
+        lg = r[0] if name == "tgn" else r
+        loss = crit(lg[mask].squeeze(1), y[mask].float())
+        loss.backward()
+        assert abs(float(loss) - float(gold[f"train_{name}_loss"])) <= 1e-4 * float(gold[f"train_{name}_loss"])
+        assert relerr(lg, torch.from_numpy(gold[f"train_{name}_logits"])) <= 1e-5
+        for pn, p in m.named_parameters():
+            if "lin_dst" in pn:
+                continue
+            ref = torch.from_numpy(gold[f"train_{name}_grad.{pn}"])
+            if float(ref.norm()) > 1e-9:        # (conv biases feed a train-mode BatchNorm: their true gradient is zero)
+                assert relerr(p.grad, ref) <= 2e-4, (name, pn, relerr(p.grad, ref))
+            else:
+                assert maxabs(p.grad, ref) <= 1e-5, (name, pn)
