@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_INPUT = 0, 1, 2, 3
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -41,7 +41,7 @@ class Graph(C.Structure):
 
 
 # name -> (restype, argtypes); every symbol include/gnnfd_b200.h declares
-_vp, _sz, _i64, _i, _f = C.c_void_p, C.c_size_t, C.c_int64, C.c_int, C.c_float
+_vp, _sz, _i64, _i, _f, _u64 = C.c_void_p, C.c_size_t, C.c_int64, C.c_int, C.c_float, C.c_uint64
 _szp, _i64p, _gp = C.POINTER(C.c_size_t), C.POINTER(C.c_int64), C.POINTER(Graph)
 SIGNATURES = {
     "gnnfd_last_error": (C.c_char_p, []),
@@ -62,12 +62,13 @@ SIGNATURES = {
     "gnnfd_project_workspace_bytes": (_i, [_i64, _i64, _i, _i, _i, _szp]),
     "gnnfd_project_fwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gnnfd_gat_fwd_workspace_bytes": (_i, [_gp, _i, _i, _szp]),
-    "gnnfd_gat_fwd": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "gnnfd_gat_fwd_fused": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
-                                 _vp, _sz, _vp]),
+    "gnnfd_dropout_mask": (_i, [_u64, _f, _i64, _i, _vp, C.POINTER(C.c_float), _vp]),
+    "gnnfd_gat_fwd": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _f, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gnnfd_gat_fwd_fused": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _f, _u64, _vp, _vp, _vp, _vp, _vp,
+                                 _vp, _vp, _sz, _vp]),
     "gnnfd_gat_alpha": (_i, [_gp, _vp, _vp, _vp, _vp, _i, _f, _vp, _vp]),
     "gnnfd_gat_bwd_workspace_bytes": (_i, [_gp, _i, _i, _szp]),
-    "gnnfd_gat_bwd_dst": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _f, _vp, _vp, _vp, _vp,
+    "gnnfd_gat_bwd_dst": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _f, _u64, _vp, _vp, _vp, _vp,
                                _sz, _vp]),
     "gnnfd_gat_bwd_src": (_i, [_gp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "gnnfd_project_bwd_workspace_bytes": (_i, [_i64, _i64, _i, _i, _i, _szp]),
@@ -80,12 +81,12 @@ SIGNATURES = {
     "gnnfd_in_logits": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "gnnfd_in_prepare": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "gnnfd_in_fwd_workspace_bytes": (_i, [_gp, _szp]),
-    "gnnfd_in_fwd": (_i, [_gp, _vp, _i64, _i64, _vp, _vp, _f, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gnnfd_in_fwd": (_i, [_gp, _vp, _i64, _i64, _vp, _vp, _f, _vp, _f, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gnnfd_in_out": (_i, [_vp, _i64, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
     "gnnfd_in_bwd_gd": (_i, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "gnnfd_in_bwd_edges_workspace_bytes": (_i, [_gp, _szp]),
     "gnnfd_in_bwd_edges": (_i, [_gp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f, _vp, _f,
-                                _vp, _vp, _vp, _sz, _i, _vp]),
+                                _u64, _vp, _vp, _vp, _sz, _i, _vp]),
     "gnnfd_in_bwd_dasrc": (_i, [_gp, _vp, _vp, _vp]),
     "gnnfd_in_bwd_params_workspace_bytes": (_i, [_i64, _i64, _szp]),
     "gnnfd_in_bwd_params": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,

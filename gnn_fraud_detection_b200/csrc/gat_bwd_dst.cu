@@ -55,7 +55,7 @@ __device__ __forceinline__ void bwd_dst_stream(ChunkCursor& cur, WarpRing<GE, bw
                                                const float* __restrict__ a_src, const float* __restrict__ a_dst,
                                                const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                                                const float* __restrict__ d_out, float slope,
-                                               const uint8_t* __restrict__ keep, float keep_scale,
+                                               KeepMask keep, float keep_scale,
                                                float* __restrict__ alpha_used, float* __restrict__ dz, int64_t eg_ld,
                                                float* __restrict__ da_dst, float* __restrict__ part_t, int chunk_id,
                                                int lane)
@@ -213,7 +213,7 @@ gat_bwd_dst_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict_
                   const int32_t* __restrict__ csr2csc, const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                   const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                   const float* __restrict__ d_out, gnnfd_item_plan_t items, int hub_threshold, float slope,
-                  const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
+                  KeepMask keep, float keep_scale, float* __restrict__ alpha_used,
                   float* __restrict__ dz, int64_t eg_ld, float* __restrict__ da_dst)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -237,7 +237,7 @@ __device__ __forceinline__ void bwd_dst_stream_pack(ChunkCursor& cur, WarpRing<G
                                                     const float* __restrict__ a_src, const float* __restrict__ a_dst,
                                                     const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                                                     const float* __restrict__ d_out, float slope,
-                                                    const uint8_t* __restrict__ keep, float keep_scale,
+                                                    KeepMask keep, float keep_scale,
                                                     float* __restrict__ alpha_used, float* __restrict__ dz, int64_t eg_ld,
                                                     float* __restrict__ da_dst, int lane)
 {
@@ -427,7 +427,7 @@ gat_bwd_dst_items_pack(const int32_t* __restrict__ rowptr, const int32_t* __rest
                        const int32_t* __restrict__ csr2csc, const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                        const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                        const float* __restrict__ d_out, gnnfd_item_plan_t items, int hub_threshold, float slope,
-                       const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
+                       KeepMask keep, float keep_scale, float* __restrict__ alpha_used,
                        float* __restrict__ dz, int64_t eg_ld, float* __restrict__ da_dst)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -449,7 +449,7 @@ gat_bwd_dst_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
                  const int32_t* __restrict__ csr2csc, const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                  const float* __restrict__ a_dst, const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                  const float* __restrict__ d_out, gnnfd_hub_plan_t plan, float slope,
-                 const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ alpha_used,
+                 KeepMask keep, float keep_scale, float* __restrict__ alpha_used,
                  float* __restrict__ dz, int64_t eg_ld, float* __restrict__ part_t)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -478,7 +478,7 @@ static int set_smem_bwd(K kernel, int bytes)
 template <class GE>
 static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* a_src, const float* a_dst,
                           const float* rowmax, const float* rowsum, const float* d_out, float slope, int concat,
-                          const uint8_t* keep, float p_drop, float* alpha_used, float* dz, float* da_dst, void* ws,
+                          const uint8_t* keep_mask, float p_drop, uint64_t seed, float* alpha_used, float* dz, float* da_dst, void* ws,
                           size_t ws_bytes, cudaStream_t st)
 {
     using XT = typename GE::XT;
@@ -488,8 +488,9 @@ static int launch_bwd_dst(const gnnfd_graph_t* g, const void* xw_, const float* 
     if (n == 0) return GNNFD_OK;
     GNNFD_REQUIRE(g->items_dst.n_items > 0 && g->items_dst.item_start, GNNFD_ERR_ARG,
                   "gat_bwd_dst: the graph has no work-item plan over rowptr (gnnfd_item_plan)");
-    const bool drop = keep != nullptr && p_drop > 0.f;
-    const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
+    const bool drop = p_drop > 0.f;              // explicit mask, or (mask == NULL) the counter-based RNG keyed on seed
+    float ks = 1.f;
+    const KeepMask keep = make_keep(keep_mask, p_drop, seed, &ks);
     const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
     const unsigned grid = (unsigned)((g->items_dst.n_items + ST_WARPS - 1) / ST_WARPS);
     // two dense [E',H] arrays, or the halves of one interleaved [E',2H] buffer (dz == alpha_used + H)
@@ -558,7 +559,7 @@ extern "C" {
 
 int gnnfd_gat_bwd_dst(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src, const float* a_dst,
                       const float* rowmax, const float* rowsum, const float* d_out, int H, int C,
-                      float negative_slope, int concat, const uint8_t* keep_mask, float p_drop, float* alpha_used,
+                      float negative_slope, int concat, const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed, float* alpha_used,
                       float* dz, float* da_dst, void* ws, size_t ws_bytes, gnnfd_stream_t stream)
 {
     int rc = check_graph(g, false, "gat_bwd_dst");
@@ -572,13 +573,13 @@ int gnnfd_gat_bwd_dst(const gnnfd_graph_t* g, const void* xw, int xw_dtype, cons
     cudaStream_t st = (cudaStream_t)stream;
     if (H == 8 && C == 64 && xw_dtype == GNNFD_F32)
         return launch_bwd_dst<Geo<8, 64, float>>(g, xw, a_src, a_dst, rowmax, rowsum, d_out, negative_slope, concat,
-                                                 keep_mask, p_drop, alpha_used, dz, da_dst, ws, ws_bytes, st);
+                                                 keep_mask, p_drop, dropout_seed, alpha_used, dz, da_dst, ws, ws_bytes, st);
     if (H == 8 && C == 64 && xw_dtype == GNNFD_BF16)
         return launch_bwd_dst<Geo<8, 64, __nv_bfloat16>>(g, xw, a_src, a_dst, rowmax, rowsum, d_out, negative_slope,
-                                                         concat, keep_mask, p_drop, alpha_used, dz, da_dst, ws, ws_bytes, st);
+                                                         concat, keep_mask, p_drop, dropout_seed, alpha_used, dz, da_dst, ws, ws_bytes, st);
     if (H == 4 && C == 32 && xw_dtype == GNNFD_F32)
         return launch_bwd_dst<Geo<4, 32, float>>(g, xw, a_src, a_dst, rowmax, rowsum, d_out, negative_slope, concat,
-                                                 keep_mask, p_drop, alpha_used, dz, da_dst, ws, ws_bytes, st);
+                                                 keep_mask, p_drop, dropout_seed, alpha_used, dz, da_dst, ws, ws_bytes, st);
     GNNFD_REQUIRE(false, GNNFD_ERR_UNSUPPORTED, "gat_bwd_dst: (heads=%d, out_channels=%d, dtype=%d) is not built", H, C,
                   xw_dtype);
     return GNNFD_ERR_UNSUPPORTED;

@@ -66,6 +66,52 @@ __device__ __forceinline__ void load_slot(const __nv_bfloat16* __restrict__ row,
     v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
 }
 
+// Attention dropout (GATConv(..., dropout=p), src/models/gat.py:39): which (edge, head) coefficients survive.
+// Either an explicit keep-mask [E',H] in edge_index' (PyG) order -- parity tests inject one -- or, in training, a
+// counter-based RNG keyed on (seed, position in edge_index', head): stateless, so the forward and the backward kernels
+// re-derive the SAME bits with no [E',H] tensor and no extra pass.  16 random bits per (edge, head): keep iff bits >= thr,
+// thr = floor(p * 65536); the survivors are scaled by 65536 / (65536 - thr) (the exact keep probability).
+struct KeepMask {
+    const uint8_t* mask;
+    uint64_t seed;
+    uint32_t thr;
+    __host__ __device__ KeepMask(const uint8_t* m = nullptr, uint64_t s = 0, uint32_t t = 0) : mask(m), seed(s), thr(t) {}
+    __host__ __device__ static uint64_t mix(uint64_t z)            // splitmix64 finaliser
+    {
+        z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
+        z ^= z >> 27; z *= 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return z;
+    }
+    // bit h = coefficient (edge at position pos of edge_index', head h) is kept; H <= 8
+    __host__ __device__ unsigned bits(int64_t pos, int H) const
+    {
+        unsigned r = 0;
+        if (mask) {
+            const uint8_t* kb = mask + pos * H;
+            for (int h = 0; h < H; ++h) r |= unsigned(kb[h] != 0) << h;
+            return r;
+        }
+        const uint64_t c = seed + 0x9E3779B97F4A7C15ull * uint64_t(2 * pos + 1);
+        const uint64_t w0 = mix(c), w1 = mix(c ^ 0xD1B54A32D192ED03ull);
+        for (int h = 0; h < H; ++h) {
+            const uint32_t v = uint32_t(((h < 4 ? w0 : w1) >> (16 * (h & 3))) & 0xffffu);
+            r |= unsigned(v >= thr) << h;
+        }
+        return r;
+    }
+};
+// host side: the KeepMask and the survivor scale for (explicit mask or NULL, p, seed)
+inline KeepMask make_keep(const uint8_t* mask, float p_drop, uint64_t seed, float* scale)
+{
+    if (!(p_drop > 0.f)) { *scale = 1.f; return KeepMask(); }
+    if (mask) { *scale = 1.f / (1.f - p_drop); return KeepMask(mask, 0, 0); }
+    uint32_t thr = uint32_t(double(p_drop) * 65536.0);
+    if (thr > 65535u) thr = 65535u;
+    *scale = 65536.f / float(65536u - thr);
+    return KeepMask(nullptr, seed, thr);
+}
+
 constexpr int ROW_WARPS = 8;                 // warps (rows) per CTA
 constexpr int ROW_THREADS = ROW_WARPS * 32;
 

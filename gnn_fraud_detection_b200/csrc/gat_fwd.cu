@@ -165,7 +165,7 @@ __device__ __forceinline__ void fwd_stream(ChunkCursor& cur, WarpRing<GE>& ring,
                                            const int32_t* __restrict__ perm,
                                            const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                                            const float* __restrict__ a_dst, float slope,
-                                           const uint8_t* __restrict__ keep, float keep_scale, int lane)
+                                           KeepMask keep, float keep_scale, int lane)
 {
     constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP;
     const int sub = lane / GE::G;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4)
 gat_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
               const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
               const float* __restrict__ a_dst, EpiParams ep, gnnfd_item_plan_t items,
-              int hub_threshold, float slope, const uint8_t* __restrict__ keep, float keep_scale,
+              int hub_threshold, float slope, KeepMask keep, float keep_scale,
               float* __restrict__ out, float* __restrict__ rowmax, float* __restrict__ rowsum)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -273,7 +273,7 @@ __device__ __forceinline__ void fwd_stream_pack(ChunkCursor& cur, WarpRing<GE, 2
                                                 const int32_t* __restrict__ perm,
                                                 const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                                                 const float* __restrict__ a_dst, float slope,
-                                                const uint8_t* __restrict__ keep, float keep_scale, int lane)
+                                                KeepMask keep, float keep_scale, int lane)
 {
     constexpr int H = GE::H, NS = GE::NS, VW = GE::VW, HP = GE::HP;
     const int sub = lane / GE::G;
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4)
 gat_fwd_items_pack(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                    const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                    const float* __restrict__ a_dst, EpiParams ep, gnnfd_item_plan_t items,
-                   int hub_threshold, float slope, const uint8_t* __restrict__ keep, float keep_scale,
+                   int hub_threshold, float slope, KeepMask keep, float keep_scale,
                    float* __restrict__ out, float* __restrict__ rowmax, float* __restrict__ rowsum)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(ST_THREADS, 4)
 gat_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                    const typename GE::XT* __restrict__ xw, const float* __restrict__ a_src,
                    const float* __restrict__ a_dst, gnnfd_hub_plan_t plan, float slope,
-                   const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ part_ms,
+                   KeepMask keep, float keep_scale, float* __restrict__ part_ms,
                    float* __restrict__ part_acc)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -523,7 +523,7 @@ static int set_smem(K kernel, int bytes)
 
 template <class GE>
 static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_src, const float* a_dst,
-                      EpiParams ep, float slope, int concat, const uint8_t* keep, float p_drop,
+                      EpiParams ep, float slope, int concat, const uint8_t* keep_mask, float p_drop, uint64_t seed,
                       float* out, float* rowmax, float* rowsum, void* ws, size_t ws_bytes, cudaStream_t st)
 {
     using XT = typename GE::XT;
@@ -533,8 +533,9 @@ static int launch_fwd(const gnnfd_graph_t* g, const void* xw_, const float* a_sr
     if (n == 0) return GNNFD_OK;
     GNNFD_REQUIRE(g->items_dst.n_items > 0 && g->items_dst.item_start, GNNFD_ERR_ARG,
                   "gat_fwd: the graph has no work-item plan over rowptr (gnnfd_item_plan)");
-    const bool drop = keep != nullptr && p_drop > 0.f;
-    const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
+    const bool drop = p_drop > 0.f;              // explicit mask, or (mask == NULL) the counter-based RNG keyed on seed
+    float ks = 1.f;
+    const KeepMask keep = make_keep(keep_mask, p_drop, seed, &ks);
     const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
     const unsigned grid = (unsigned)((g->items_dst.n_items + ST_WARPS - 1) / ST_WARPS);
     int rc = GNNFD_OK;
@@ -607,11 +608,39 @@ int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who)
     return GNNFD_OK;
 }
 
+
+// the keep bits of the counter-based attention-dropout RNG, written out as a [E',H] uint8 mask in edge_index' order
+// (test / debugging hook: the kernels themselves never materialise it)
+__global__ void dropout_mask_kernel(KeepMask km, int64_t n_edges, int H, uint8_t* __restrict__ out)
+{
+    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < n_edges; e += int64_t(gridDim.x) * blockDim.x) {
+        const unsigned b = km.bits(e, H);
+        for (int h = 0; h < H; ++h) out[e * H + h] = uint8_t((b >> h) & 1u);
+    }
+}
+
 }  // namespace gnnfd
 
 using namespace gnnfd;
 
 extern "C" {
+
+int gnnfd_dropout_mask(uint64_t dropout_seed, float p_drop, int64_t n_edges, int H, uint8_t* keep_mask, float* scale_host,
+                       gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(p_drop > 0.f && p_drop < 1.f && H >= 1 && H <= 8 && n_edges >= 0, GNNFD_ERR_ARG, "dropout_mask: bad argument");
+    float ks = 1.f;
+    const KeepMask km = make_keep(nullptr, p_drop, dropout_seed, &ks);
+    if (scale_host) *scale_host = ks;
+    if (n_edges == 0) return GNNFD_OK;
+    GNNFD_REQUIRE(keep_mask, GNNFD_ERR_ARG, "dropout_mask: keep_mask is NULL");
+    int64_t blocks = (n_edges + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    dropout_mask_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(km, n_edges, H, keep_mask);
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
 
 int gnnfd_gat_fwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* bytes)
 {
@@ -623,7 +652,7 @@ int gnnfd_gat_fwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* 
 
 int gnnfd_gat_fwd_fused(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src, const float* a_dst,
                         const float* bias, int H, int C, float negative_slope, int concat, int act,
-                        const uint8_t* keep_mask, float p_drop, const float* post_scale, const float* post_shift,
+                        const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed, const float* post_scale, const float* post_shift,
                         const float* residual, float* out, float* rowmax, float* rowsum, void* ws, size_t ws_bytes,
                         gnnfd_stream_t stream)
 {
@@ -632,6 +661,7 @@ int gnnfd_gat_fwd_fused(const gnnfd_graph_t* g, const void* xw, int xw_dtype, co
     GNNFD_REQUIRE(g->n_dst == 0 || (xw && a_src && a_dst && out && rowmax && rowsum), GNNFD_ERR_ARG,
                   "gat_fwd: NULL tensor");
     GNNFD_REQUIRE(p_drop >= 0.f && p_drop < 1.f, GNNFD_ERR_ARG, "gat_fwd: dropout p must be in [0,1)");
+    GNNFD_REQUIRE(p_drop == 0.f || g->n_edges == 0 || g->perm, GNNFD_ERR_ARG, "gat_fwd: attention dropout needs perm");
     GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(xw) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                   GNNFD_ERR_ARG, "gat_fwd: xw/out must be 16-byte aligned");
     GNNFD_REQUIRE((post_scale == nullptr) == (post_shift == nullptr), GNNFD_ERR_ARG,
@@ -639,13 +669,13 @@ int gnnfd_gat_fwd_fused(const gnnfd_graph_t* g, const void* xw, int xw_dtype, co
     cudaStream_t st = (cudaStream_t)stream;
     const EpiParams ep{bias, post_scale, post_shift, residual, act};
     if (H == 8 && C == 64 && xw_dtype == GNNFD_F32)
-        return launch_fwd<Geo<8, 64, float>>(g, xw, a_src, a_dst, ep, negative_slope, concat, keep_mask, p_drop, out, rowmax,
+        return launch_fwd<Geo<8, 64, float>>(g, xw, a_src, a_dst, ep, negative_slope, concat, keep_mask, p_drop, dropout_seed, out, rowmax,
                                              rowsum, ws, ws_bytes, st);
     if (H == 8 && C == 64 && xw_dtype == GNNFD_BF16)
-        return launch_fwd<Geo<8, 64, __nv_bfloat16>>(g, xw, a_src, a_dst, ep, negative_slope, concat, keep_mask, p_drop, out,
+        return launch_fwd<Geo<8, 64, __nv_bfloat16>>(g, xw, a_src, a_dst, ep, negative_slope, concat, keep_mask, p_drop, dropout_seed, out,
                                                      rowmax, rowsum, ws, ws_bytes, st);
     if (H == 4 && C == 32 && xw_dtype == GNNFD_F32)
-        return launch_fwd<Geo<4, 32, float>>(g, xw, a_src, a_dst, ep, negative_slope, concat, keep_mask, p_drop, out, rowmax,
+        return launch_fwd<Geo<4, 32, float>>(g, xw, a_src, a_dst, ep, negative_slope, concat, keep_mask, p_drop, dropout_seed, out, rowmax,
                                              rowsum, ws, ws_bytes, st);
     GNNFD_REQUIRE(false, GNNFD_ERR_UNSUPPORTED, "gat_fwd: (heads=%d, out_channels=%d, dtype=%d) is not built; "
                   "available: (8,64,f32), (8,64,bf16), (4,32,f32)", H, C, xw_dtype);
@@ -654,10 +684,10 @@ int gnnfd_gat_fwd_fused(const gnnfd_graph_t* g, const void* xw, int xw_dtype, co
 
 int gnnfd_gat_fwd(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src, const float* a_dst,
                   const float* bias, int H, int C, float negative_slope, int concat, int act,
-                  const uint8_t* keep_mask, float p_drop, float* out, float* rowmax, float* rowsum, void* ws,
+                  const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed, float* out, float* rowmax, float* rowsum, void* ws,
                   size_t ws_bytes, gnnfd_stream_t stream)
 {
-    return gnnfd_gat_fwd_fused(g, xw, xw_dtype, a_src, a_dst, bias, H, C, negative_slope, concat, act, keep_mask, p_drop,
+    return gnnfd_gat_fwd_fused(g, xw, xw_dtype, a_src, a_dst, bias, H, C, negative_slope, concat, act, keep_mask, p_drop, dropout_seed,
                                nullptr, nullptr, nullptr, out, rowmax, rowsum, ws, ws_bytes, stream);
 }
 

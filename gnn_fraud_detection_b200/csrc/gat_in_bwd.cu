@@ -90,7 +90,7 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
                                               const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                                               const int32_t* __restrict__ csr2csc, const float* __restrict__ a_src,
                                               const float* __restrict__ a_dst, const float* __restrict__ rowmax,
-                                              const float* __restrict__ rowsum, float slope, const uint8_t* __restrict__ keep,
+                                              const float* __restrict__ rowsum, float slope, KeepMask keep,
                                               float keep_scale, float* __restrict__ dz, float* __restrict__ da_dst,
                                               float* __restrict__ part_t, int chunk_id, int lane)
 {
@@ -291,7 +291,7 @@ gat_in_bwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
                  const int32_t* __restrict__ csr2csc, const float* __restrict__ x, int64_t ldx, int KP,
                  const float* __restrict__ a_src, const float* __restrict__ a_dst, const float* __restrict__ rowmax,
                  const float* __restrict__ rowsum, const float* __restrict__ gd, gnnfd_item_plan_t items, int item_lo,
-                 int item_hi, int hub_threshold, float slope, const uint8_t* __restrict__ keep, float keep_scale,
+                 int item_hi, int hub_threshold, float slope, KeepMask keep, float keep_scale,
                  float* __restrict__ dz, float* __restrict__ da_dst)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -316,7 +316,7 @@ gat_in_bwd_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
                 const int32_t* __restrict__ csr2csc, const float* __restrict__ x, int64_t ldx, int KP,
                 const float* __restrict__ a_src, const float* __restrict__ a_dst, const float* __restrict__ rowmax,
                 const float* __restrict__ rowsum, const float* __restrict__ gd, gnnfd_hub_plan_t plan, int row_lo, int row_hi,
-                float slope, const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ dz,
+                float slope, KeepMask keep, float keep_scale, float* __restrict__ dz,
                 float* __restrict__ part_t)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -368,7 +368,7 @@ int gnnfd_in_bwd_edges_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes)
 int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src,
                        const float* a_dst, const float* rowmax, const float* rowsum, const float* gd, int64_t gd_row0,
                        int64_t item_lo, int64_t item_hi, int64_t row_lo, int64_t row_hi, float negative_slope,
-                       const uint8_t* keep_mask, float p_drop, float* dz, float* da_dst, void* ws, size_t ws_bytes,
+                       const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed, float* dz, float* da_dst, void* ws, size_t ws_bytes,
                        int phase, gnnfd_stream_t stream)
 {
     int rc = check_graph(g, true, "in_bwd_edges");
@@ -385,8 +385,9 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
     GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(gd) & 15) == 0, GNNFD_ERR_ARG, "in_bwd_edges: gd must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const Dims d((int)K);
-    const bool drop = keep_mask != nullptr && p_drop > 0.f;
-    const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
+    const bool drop = p_drop > 0.f;              // explicit mask, or (mask == NULL) the counter-based RNG keyed on seed
+    float ks = 1.f;
+    const KeepMask keep = make_keep(keep_mask, p_drop, dropout_seed, &ks);
     const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
     GNNFD_REQUIRE(in_x_ok(x, ldx, d.KP), GNNFD_ERR_ARG,
                   "in_bwd_edges: x rows must be 16-byte aligned and zero-padded to %d floats (gnnfd_in_pad_x)", d.KP);
@@ -415,13 +416,13 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
     if (rc) return rc;                                                                                                 \
     gat_in_bwd_items<NN, DD, PP><<<grid, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, x, ldx, d.KP, a_src, \
                                                                  a_dst, rowmax, rowsum, gd0, g->items_dst, (int)item_lo,   \
-                                                                 (int)item_hi, thr, negative_slope, keep_mask, ks, dz, da_dst)
+                                                                 (int)item_hi, thr, negative_slope, keep, ks, dz, da_dst)
 #define GNNFD_IN_HUB1(NN, DD)                                                                                          \
     rc = in_set_smem_bwd(gat_in_bwd_hub1<NN, DD>, smem);                                                               \
     if (rc) return rc;                                                                                                 \
     gat_in_bwd_hub1<NN, DD><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, x, ldx, d.KP, a_src, a_dst, \
                                                           rowmax, rowsum, gd0, pl, (int)row_lo, (int)row_hi, negative_slope, \
-                                                          keep_mask, ks, dz, part_t)
+                                                          keep, ks, dz, part_t)
 #define GNNFD_IN_BWD_ALL(NN)                                                                                           \
     if (pack) { if (drop) { GNNFD_IN_BWD(NN, true, true); } else { GNNFD_IN_BWD(NN, false, true); } }                  \
     else      { if (drop) { GNNFD_IN_BWD(NN, true, false); } else { GNNFD_IN_BWD(NN, false, false); } }                \

@@ -255,7 +255,7 @@ template <int N4, bool DROPOUT, bool PACK, class Sink>
 __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, const Sink& sink, float* rowmax, float* rowsum,
                                               const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
                                               const int32_t* __restrict__ perm, int n4, const float* __restrict__ a_src,
-                                              const float* __restrict__ a_dst, float slope, const uint8_t* __restrict__ keep,
+                                              const float* __restrict__ a_dst, float slope, KeepMask keep,
                                               float keep_scale, int lane)
 {
     using RG = RowGeo<N4>;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(IN_THREADS, 4)
 gat_in_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                  const float* __restrict__ x, int64_t ldx, const float* __restrict__ a_src,
                  const float* __restrict__ a_dst, gnnfd_item_plan_t items, int hub_threshold, float slope,
-                 const uint8_t* __restrict__ keep, float keep_scale, ZSink<N4> sink)
+                 KeepMask keep, float keep_scale, ZSink<N4> sink)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(IN_THREADS, 4)
 gat_in_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                       const float* __restrict__ x, int64_t ldx, int KP, const float* __restrict__ a_src,
                       const float* __restrict__ a_dst, gnnfd_hub_plan_t plan, float slope,
-                      const uint8_t* __restrict__ keep, float keep_scale, float* __restrict__ part_ms,
+                      KeepMask keep, float keep_scale, float* __restrict__ part_ms,
                       float* __restrict__ part_acc)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -462,11 +462,12 @@ bool in_x_ok(const float* x, int64_t ldx, int KP) { return (reinterpret_cast<uin
 
 template <int N4>
 static int launch_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, const Dims& d, const float* a_src, const float* a_dst,
-                         float slope, const uint8_t* keep, float p_drop, const float* scal, void* zimg, float* rowmax,
+                         float slope, const uint8_t* keep_mask, float p_drop, uint64_t seed, const float* scal, void* zimg, float* rowmax,
                          float* rowsum, void* ws, size_t ws_bytes, cudaStream_t st)
 {
-    const bool drop = keep != nullptr && p_drop > 0.f;
-    const float ks = drop ? 1.f / (1.f - p_drop) : 1.f;
+    const bool drop = p_drop > 0.f;              // explicit mask, or (mask == NULL) the counter-based RNG keyed on seed
+    float ks = 1.f;
+    const KeepMask keep = make_keep(keep_mask, p_drop, seed, &ks);
     const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
     const int smem = IN_WARPS * in_warp_bytes(d.KP, FWD_EXTRA);
     const unsigned grid = (unsigned)((g->items_dst.n_items + IN_WARPS - 1) / IN_WARPS);
@@ -622,7 +623,7 @@ int gnnfd_in_fwd_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes)
 
 /* Aggregation in input space: zimg (fp16-pair image of Z, rows = destinations), rowmax / rowsum [n_dst,H]. */
 int gnnfd_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src, const float* a_dst,
-                 float negative_slope, const uint8_t* keep_mask, float p_drop, const void* prep, void* zimg,
+                 float negative_slope, const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed, const void* prep, void* zimg,
                  float* rowmax, float* rowsum, void* ws, size_t ws_bytes, gnnfd_stream_t stream)
 {
     int rc = check_graph(g, false, "in_fwd");
@@ -645,10 +646,10 @@ int gnnfd_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K,
         GNNFD_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(zimg) + last, 0, size_t(d.NKB) * KBLOCK, st));
     }
     if (d.KP == 168)
-        return launch_in_fwd<42>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
+        return launch_in_fwd<42>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, dropout_seed, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
     if (d.KP == 64)
-        return launch_in_fwd<16>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
-    return launch_in_fwd<0>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
+        return launch_in_fwd<16>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, dropout_seed, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
+    return launch_in_fwd<0>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, dropout_seed, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
 }
 
 }  // extern "C"

@@ -36,7 +36,7 @@ __device__ __forceinline__ void bwd_phase_a(const BwdChunk& c, const int32_t* __
                                             const int32_t* __restrict__ perm, const float* __restrict__ a_src,
                                             const float* __restrict__ a_dst, const float* __restrict__ rowmax,
                                             const float* __restrict__ rowsum, float slope,
-                                            const uint8_t* __restrict__ keep, float* p_s, int* j_s, int* bits_s, int lane)
+                                            KeepMask keep, float* p_s, int* j_s, int* bits_s, int lane)
 {
     constexpr int H = GE::H;
     RowStat<H> r;
@@ -55,9 +55,7 @@ __device__ __forceinline__ void bwd_phase_a(const BwdChunk& c, const int32_t* __
             alpha[h] = expf((pos ? z : z * slope) - r.m[h]) * r.inv[h];
         }
         if (DROPOUT) {
-            const uint8_t* kb = keep + int64_t(perm[c.beg + lane]) * H;
-#pragma unroll
-            for (int h = 0; h < H; ++h) bits |= int(kb[h] != 0) << (8 + h);
+            bits |= int(keep.bits(perm[c.beg + lane], H)) << 8;
         } else {
             bits |= 0xff00;
         }
@@ -108,7 +106,7 @@ __device__ __forceinline__ void bwd_phase_a_pack(int row0, int beg, int n, int k
                                                  const float* __restrict__ a_src, const float* __restrict__ a_dst,
                                                  const float* __restrict__ rowmax, const float* __restrict__ rowsum,
                                                  const float* __restrict__ d_out, float slope,
-                                                 const uint8_t* __restrict__ keep, float* p_s, int* j_s, int* bits_s, int lane)
+                                                 KeepMask keep, float* p_s, int* j_s, int* bits_s, int lane)
 {
     constexpr int H = GE::H;
     const bool act = lane < n;
@@ -145,9 +143,7 @@ __device__ __forceinline__ void bwd_phase_a_pack(int row0, int beg, int n, int k
             alpha[h] = expf((pos ? z : z * slope) - r.m[h]) * r.inv[h];
         }
         if (DROPOUT) {
-            const uint8_t* kb = keep + int64_t(perm[e_id]) * H;
-#pragma unroll
-            for (int h = 0; h < H; ++h) bits |= int(kb[h] != 0) << (8 + h);
+            bits |= int(keep.bits(perm[e_id], H)) << 8;
         } else {
             bits |= 0xff00;
         }

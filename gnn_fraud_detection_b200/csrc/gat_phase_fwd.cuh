@@ -20,7 +20,7 @@ template <class GE, bool DROPOUT>
 __device__ __forceinline__ void fwd_phase_a(ChunkStat<GE::H>& c, int beg, const int32_t* __restrict__ col,
                                             const int32_t* __restrict__ perm, const float* __restrict__ a_src,
                                             const float* __restrict__ a_dst, float slope,
-                                            const uint8_t* __restrict__ keep, float keep_scale, float* p_s, int* j_s,
+                                            KeepMask keep, float keep_scale, float* p_s, int* j_s,
                                             int lane)
 {
     constexpr int H = GE::H;
@@ -34,9 +34,9 @@ __device__ __forceinline__ void fwd_phase_a(ChunkStat<GE::H>& c, int beg, const 
 #pragma unroll
         for (int h = 0; h < H; ++h) e[h] = leaky(as[h] + adst[h], slope);
         if (DROPOUT) {
-            const uint8_t* kb = keep + int64_t(perm[beg + lane]) * H;
+            const unsigned kbits = keep.bits(perm[beg + lane], H);
 #pragma unroll
-            for (int h = 0; h < H; ++h) kp[h] = kb[h] ? keep_scale : 0.f;
+            for (int h = 0; h < H; ++h) kp[h] = (kbits >> h) & 1u ? keep_scale : 0.f;
         }
     } else {
 #pragma unroll
@@ -62,7 +62,7 @@ template <class GE, bool DROPOUT>
 __device__ __forceinline__ void fwd_phase_a_pack(int row0, int beg, int n, int k, int lane_a, int lane_b,
                                                  const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                                                  const float* __restrict__ a_src, const float* __restrict__ a_dst,
-                                                 float slope, const uint8_t* __restrict__ keep, float keep_scale,
+                                                 float slope, KeepMask keep, float keep_scale,
                                                  float* __restrict__ rowmax, float* __restrict__ rowsum, float* p_s,
                                                  int* j_s, int* r_s, int lane)
 {
@@ -90,9 +90,9 @@ __device__ __forceinline__ void fwd_phase_a_pack(int row0, int beg, int n, int k
 #pragma unroll
         for (int h = 0; h < H; ++h) e[h] = leaky(as[h] + adst[h], slope);
         if (DROPOUT) {
-            const uint8_t* kb = keep + int64_t(perm[e_id]) * H;
+            const unsigned kbits = keep.bits(perm[e_id], H);
 #pragma unroll
-            for (int h = 0; h < H; ++h) kp[h] = kb[h] ? keep_scale : 0.f;
+            for (int h = 0; h < H; ++h) kp[h] = (kbits >> h) & 1u ? keep_scale : 0.f;
         }
     } else {
 #pragma unroll

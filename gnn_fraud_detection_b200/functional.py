@@ -54,7 +54,7 @@ def project_fwd(x, W, att_src, att_dst, H, C_, xw_dtype=torch.float32, algo=_abi
 
 
 def gat_fwd(g: GraphCSR, xw, a_src, a_dst, bias, H, C_, negative_slope, concat, act=_abi.ACT_NONE, keep_mask=None,
-            p_drop=0.0, post_scale=None, post_shift=None, residual=None):
+            p_drop=0.0, post_scale=None, post_shift=None, residual=None, seed=0):
     """Fused softmax/aggregation.  ``post_scale``/``post_shift`` [Co] (folded eval-mode BatchNorm), ``act`` and
     ``residual`` [n_dst,Co] are applied in the row epilogue: ``act((mean+bias)*scale+shift) + residual``."""
     L = _abi.lib()
@@ -68,10 +68,21 @@ def gat_fwd(g: GraphCSR, xw, a_src, a_dst, bias, H, C_, negative_slope, concat, 
     ws = _ws(nb.value, dev)
     _abi.check(L.gnnfd_gat_fwd_fused(g.ref(), xw.data_ptr(), _DT[xw.dtype], a_src.data_ptr(), a_dst.data_ptr(),
                                      _abi.ptr(bias), H, C_, float(negative_slope), int(concat), int(act),
-                                     _abi.ptr(keep_mask), float(p_drop), _abi.ptr(post_scale), _abi.ptr(post_shift),
+                                     _abi.ptr(keep_mask), float(p_drop), int(seed), _abi.ptr(post_scale), _abi.ptr(post_shift),
                                      _abi.ptr(residual), out.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(),
                                      ws.data_ptr(), ws.numel(), _stream()))
     return out, rowmax, rowsum
+
+
+def dropout_mask(seed: int, p_drop: float, n_edges: int, H: int, device):
+    """The keep bits the kernels derive from ``seed`` (counter-based RNG), as a [E',H] uint8 mask in edge_index' order,
+    and the survivor scale.  Test hook: the kernels never materialise this tensor."""
+    keep = torch.empty(n_edges, H, dtype=torch.uint8, device=device)
+    scale = C.c_float()
+    with torch.cuda.device(device):
+        _abi.check(_abi.lib().gnnfd_dropout_mask(int(seed), float(p_drop), int(n_edges), int(H), keep.data_ptr(),
+                                                 C.byref(scale), _stream()))
+    return keep, scale.value
 
 
 def gat_alpha(g: GraphCSR, a_src, a_dst, rowmax, rowsum, H, negative_slope):
@@ -84,13 +95,13 @@ def gat_alpha(g: GraphCSR, a_src, a_dst, rowmax, rowsum, H, negative_slope):
 
 
 def gat_bwd(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, att_src, att_dst, H, C_, negative_slope, concat,
-            keep_mask=None, p_drop=0.0, da_dst_full="same", da_dst_view=None):
+            keep_mask=None, p_drop=0.0, da_dst_full="same", da_dst_view=None, seed=0):
     """dst-major + src-major backward passes.  Returns dxw [n_src,H*C], da_src [n_src,H], da_dst [n_dst,H].
 
     For a destination-range partition ``da_dst_full`` is a zero ``[n_src,H]`` buffer in source-position space
     and ``da_dst_view=(lo, n)`` says where this rank's ``da_dst`` rows belong in it."""
     alpha_used, dz, da_dst = gat_bwd_dst(g, xw, a_src, a_dst, rowmax, rowsum, d_out, H, C_, negative_slope, concat,
-                                         keep_mask, p_drop)
+                                         keep_mask, p_drop, seed)
     full = da_dst if isinstance(da_dst_full, str) else da_dst_full
     if da_dst_view is not None:
         lo, n = da_dst_view
@@ -100,7 +111,7 @@ def gat_bwd(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, att_src, att_d
 
 
 def gat_bwd_dst(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, H, C_, negative_slope, concat, keep_mask=None,
-                p_drop=0.0):
+                p_drop=0.0, seed=0):
     """dst-major pass: alpha_used [E',H], dz [E',H] (views of one interleaved [E',2H] buffer, rows in source-major
     order) and da_dst [n_dst,H]."""
     L = _abi.lib()
@@ -115,7 +126,7 @@ def gat_bwd_dst(g: GraphCSR, xw, a_src, a_dst, rowmax, rowsum, d_out, H, C_, neg
     ws = _ws(nb.value, dev)
     _abi.check(L.gnnfd_gat_bwd_dst(g.ref(), xw.data_ptr(), _DT[xw.dtype], a_src.data_ptr(), a_dst.data_ptr(),
                                    rowmax.data_ptr(), rowsum.data_ptr(), d_out.data_ptr(), H, C_,
-                                   float(negative_slope), int(concat), _abi.ptr(keep_mask), float(p_drop),
+                                   float(negative_slope), int(concat), _abi.ptr(keep_mask), float(p_drop), int(seed),
                                    alpha_used.data_ptr(), dz.data_ptr(), da_dst.data_ptr(), ws.data_ptr(),
                                    ws.numel(), _stream()))
     return alpha_used, dz, da_dst
@@ -205,7 +216,7 @@ def in_prepare(W, K, xmax, prep):
     _abi.check(_abi.lib().gnnfd_in_prepare(W.data_ptr(), int(K), xmax.data_ptr(), prep.data_ptr(), _stream()))
 
 
-def in_fwd(g: GraphCSR, x, a_src, a_dst, negative_slope, prep, keep_mask=None, p_drop=0.0):
+def in_fwd(g: GraphCSR, x, a_src, a_dst, negative_slope, prep, keep_mask=None, p_drop=0.0, seed=0):
     """Aggregation in input space -> (zimg, rowmax, rowsum)."""
     L = _abi.lib()
     dev, K = x.device, x.size(1)
@@ -217,7 +228,8 @@ def in_fwd(g: GraphCSR, x, a_src, a_dst, negative_slope, prep, keep_mask=None, p
     _abi.check(L.gnnfd_in_fwd_workspace_bytes(g.ref(), C.byref(nb)))
     ws = _ws(nb.value, dev)
     _abi.check(L.gnnfd_in_fwd(g.ref(), x.data_ptr(), x.stride(0), K, a_src.data_ptr(), a_dst.data_ptr(),
-                              float(negative_slope), _abi.ptr(keep_mask), float(p_drop), prep.data_ptr(), zimg.data_ptr(),
+                              float(negative_slope), _abi.ptr(keep_mask), float(p_drop), int(seed), prep.data_ptr(),
+                              zimg.data_ptr(),
                               rowmax.data_ptr(), rowsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
     return zimg, rowmax, rowsum
 
@@ -234,7 +246,7 @@ IN_GD_BLOCK_BYTES = 8 << 30     # upper bound of the Gd buffer of the backward e
 
 
 def in_bwd_edges(g: GraphCSR, x, a_src, a_dst, rowmax, rowsum, d_out, prep, negative_slope, keep_mask=None, p_drop=0.0,
-                 n_blocks=None):
+                 n_blocks=None, seed=0):
     """Gd GEMM + backward edge pass, in blocks of destination rows.  Returns dz [E',H] (source-major) and da_dst."""
     L = _abi.lib()
     dev, K = x.device, x.size(1)
@@ -254,7 +266,7 @@ def in_bwd_edges(g: GraphCSR, x, a_src, a_dst, rowmax, rowsum, d_out, prep, nega
         phase = 1 | (2 if bi == len(blocks) - 1 else 0)
         _abi.check(L.gnnfd_in_bwd_edges(g.ref(), x.data_ptr(), x.stride(0), K, a_src.data_ptr(), a_dst.data_ptr(),
                                         rowmax.data_ptr(), rowsum.data_ptr(), gd.data_ptr(), r_lo, i_lo, i_hi, r_lo, r_hi,
-                                        float(negative_slope), _abi.ptr(keep_mask), float(p_drop), dz.data_ptr(),
+                                        float(negative_slope), _abi.ptr(keep_mask), float(p_drop), int(seed), dz.data_ptr(),
                                         da_dst.data_ptr(), ws.data_ptr(), ws.numel(), phase, _stream()))
     return dz, da_dst
 
@@ -288,7 +300,7 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
     """First-layer GATConv (x needs no gradient, concat=False, H=8, C=64) in the input-space formulation."""
 
     @staticmethod
-    def forward(ctx, x, W, att_src, att_dst, bias, g: GraphCSR, negative_slope, keep_mask, p_drop, want_stats):
+    def forward(ctx, x, W, att_src, att_dst, bias, g: GraphCSR, negative_slope, keep_mask, p_drop, want_stats, seed=0):
         _require_f32_cuda("x", x)
         _require_f32_cuda("lin_src.weight", W)
         if x.dim() != 2 or x.size(1) != W.size(1):
@@ -305,10 +317,10 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
             xmax = torch.zeros(16, dtype=torch.float32, device=x.device)
             a_src, a_dst = in_logits(x, W, a_s, a_d, prep, xmax)
             in_prepare(W, K, xmax, prep)
-            zimg, rowmax, rowsum = in_fwd(g, x, a_src, a_dst, negative_slope, prep, keep_mask, p_drop)
+            zimg, rowmax, rowsum = in_fwd(g, x, a_src, a_dst, negative_slope, prep, keep_mask, p_drop, seed)
             out = in_out(zimg, g.n_dst, K, prep, bias)
         ctx.save_for_backward(x, W, a_s, a_d, a_src, a_dst, rowmax, rowsum, keep_mask, zimg, prep)
-        ctx.g, ctx.slope, ctx.p = g, negative_slope, p_drop
+        ctx.g, ctx.slope, ctx.p, ctx.seed = g, negative_slope, p_drop, seed
         ctx.has_bias = bias is not None
         ctx.att_shape = att_src.shape
         if want_stats:
@@ -326,11 +338,12 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
             raise RuntimeError("the input-space formulation computes no gradient w.r.t. x (first layer only)")
         d_out = d_out.contiguous().float()
         with torch.cuda.device(x.device):
-            dz, da_dst = in_bwd_edges(g, x, a_src, a_dst, rowmax, rowsum, d_out, prep, ctx.slope, keep_mask, ctx.p)
+            dz, da_dst = in_bwd_edges(g, x, a_src, a_dst, rowmax, rowsum, d_out, prep, ctx.slope, keep_mask, ctx.p,
+                                      seed=ctx.seed)
             da_src = in_dasrc(g, dz)
             dW, datt_src, datt_dst, dbias = in_bwd_params(zimg, d_out, x, W, a_s, a_d, da_src, da_dst, prep)
         return (None, dW, datt_src.view(ctx.att_shape), datt_dst.view(ctx.att_shape), dbias if ctx.has_bias else None,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 class GATConvFunction(torch.autograd.Function):
@@ -338,7 +351,7 @@ class GATConvFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, W, att_src, att_dst, bias, g: GraphCSR, H, C_, concat, negative_slope, keep_mask, p_drop,
-                xw_dtype, algo, want_stats):
+                xw_dtype, algo, want_stats, seed=0):
         _require_f32_cuda("x", x)
         _require_f32_cuda("lin_src.weight", W)
         if x.dim() != 2 or x.size(1) != W.size(1):
@@ -352,9 +365,10 @@ class GATConvFunction(torch.autograd.Function):
         with torch.cuda.device(x.device):
             xw, a_src, a_dst = project_fwd(x, W, a_s, a_d, H, C_, xw_dtype, algo)
             out, rowmax, rowsum = gat_fwd(g, xw, a_src, a_dst, bias, H, C_, negative_slope, concat, _abi.ACT_NONE,
-                                          keep_mask, p_drop)
+                                          keep_mask, p_drop, seed=seed)
         ctx.save_for_backward(x, W, a_s, a_d, xw, a_src, a_dst, rowmax, rowsum, keep_mask)
         ctx.g, ctx.H, ctx.C, ctx.concat, ctx.slope, ctx.p, ctx.algo = g, H, C_, concat, negative_slope, p_drop, algo
+        ctx.seed = seed
         ctx.has_bias = bias is not None
         ctx.att_shape = att_src.shape
         if want_stats:
@@ -373,21 +387,22 @@ class GATConvFunction(torch.autograd.Function):
         Co = H * C_ if concat else C_
         with torch.cuda.device(x.device):
             dxw, da_src, da_dst = gat_bwd(g, xw, a_src, a_dst, rowmax, rowsum, d_out, a_s, a_d, H, C_, ctx.slope,
-                                          concat, keep_mask, ctx.p)
+                                          concat, keep_mask, ctx.p, seed=ctx.seed)
             dW, datt_src, datt_dst, dbias, dx = project_bwd(x, W, dxw, xw, da_src, da_dst, d_out, H, C_, Co, need_dx,
                                                             ctx.algo)
         return (dx, dW, datt_src.view(ctx.att_shape), datt_dst.view(ctx.att_shape),
-                dbias if ctx.has_bias else None, None, None, None, None, None, None, None, None, None, None)
+                dbias if ctx.has_bias else None, None, None, None, None, None, None, None, None, None, None, None)
 
 
 def gatconv(x, W, att_src, att_dst, bias, g: GraphCSR, heads, out_channels, concat=False, negative_slope=0.2,
-            keep_mask=None, p_drop=0.0, xw_dtype=torch.float32, algo=_abi.GEMM_AUTO, want_stats=False):
+            keep_mask=None, p_drop=0.0, xw_dtype=torch.float32, algo=_abi.GEMM_AUTO, want_stats=False, seed=0):
+    """``p_drop > 0`` with ``keep_mask=None`` selects the in-kernel counter-based dropout RNG keyed on ``seed``."""
     if algo == _abi.GEMM_INPUT:
         need_dx = x.requires_grad and torch.is_grad_enabled()
         if need_dx or xw_dtype != torch.float32 or not in_supported(x.size(1), heads, out_channels, concat) or p_drop > 0.9:
             raise _abi.GnnfdError(-5, "input-space formulation: needs x without gradient, concat=False, heads=8, "
                                       "out_channels=64, in_channels <= 192, fp32 features, dropout <= 0.9")
         return GATConvInputSpaceFunction.apply(x, W, att_src, att_dst, bias, g, negative_slope, keep_mask, p_drop,
-                                               want_stats)
+                                               want_stats, seed)
     return GATConvFunction.apply(x, W, att_src, att_dst, bias, g, heads, out_channels, concat, negative_slope,
-                                 keep_mask, p_drop, xw_dtype, algo, want_stats)
+                                 keep_mask, p_drop, xw_dtype, algo, want_stats, seed)

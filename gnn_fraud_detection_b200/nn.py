@@ -56,6 +56,7 @@ class GATConv(nn.Module):
         self.concat, self.negative_slope, self.dropout = concat, negative_slope, dropout
         self.add_self_loops = add_self_loops
         self.feature_dtype, self.gemm_algo = feature_dtype, gemm_algo
+        self.last_dropout_seed = None
         self.lin_src = _Linear(in_channels, heads * out_channels)
         self.lin_dst = self.lin_src  # same module object: state_dict() emits both keys, as PyG does
         self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
@@ -104,8 +105,10 @@ class GATConv(nn.Module):
                 dropout_mask: Optional[torch.Tensor] = None):
         """``x [N, in_channels]`` fp32 cuda, ``edge_index [2,E]`` int64 cuda -> ``[N, out_channels]``.
 
-        ``dropout_mask``: optional ``[E',H]`` keep-mask in ``edge_index'`` order for the attention dropout
-        (parity tests inject it); in training mode with ``dropout > 0`` one is drawn with ``torch.rand``.
+        Attention dropout (training mode, ``dropout > 0``): the kernels draw the keep bits themselves from a counter-based
+        RNG keyed on (seed, position in ``edge_index'``, head) -- no ``[E',H]`` mask tensor, no ``torch.rand`` pass; the
+        seed comes from torch's CPU generator (reproducible under ``torch.manual_seed``) and is kept in ``last_dropout_seed``.
+        ``dropout_mask``: optional explicit ``[E',H]`` keep-mask in ``edge_index'`` order (parity tests inject one).
         """
         if edge_attr is not None or size is not None:
             raise NotImplementedError("edge_attr / size are not part of the reference's hot path")
@@ -127,13 +130,15 @@ class GATConv(nn.Module):
                 raise NotImplementedError("return_attention_weights with dropout >= 1")
             out = x.new_zeros(g.n_dst, H * C if self.concat else C)
             return out + self.bias if self.bias is not None else out
+        seed = 0
         if keep is None and p > 0.0:
-            keep = (torch.rand(g.n_edges, H, device=x.device) >= p).to(torch.uint8)
+            seed = int(torch.randint(0, 2 ** 62, (1,), device="cpu"))
+            self.last_dropout_seed = seed
         if keep is not None and tuple(keep.shape) != (g.n_edges, H):
             raise ValueError(f"dropout_mask must be [{g.n_edges},{H}], got {tuple(keep.shape)}")
         res = gatconv(x, self.lin_src.weight, self.att_src, self.att_dst, self.bias, g, H, C, self.concat,
                       self.negative_slope, keep, p, self.feature_dtype, self.gemm_algo,
-                      want_stats=bool(return_attention_weights))
+                      want_stats=bool(return_attention_weights), seed=seed)
         if not return_attention_weights:
             return res
         out, a_src, a_dst, rowmax, rowsum = res

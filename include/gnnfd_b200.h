@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 8
+#define GNNFD_ABI_VERSION 9
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -169,22 +169,27 @@ int gnnfd_project_fwd(const float* x, int64_t ldx, const float* W, const float* 
  * Replaces: edge_update + message + aggregate + head mean/concat + bias of GATConv.forward.
  * out [n_dst, concat ? H*C : C]; rowmax/rowsum [n_dst,H] are saved for the backward (rowsum already
  * includes PyG's +1e-16).  a_dst is indexed by LOCAL destination row, a_src/xw by source id.
- * keep_mask: optional [E',H] uint8 attention-dropout keep mask in edge_index' (PyG) order, applied as
- * alpha*keep/(1-p); NULL => no dropout. */
+ * Attention dropout (GATConv(..., dropout=p) in training, src/models/gat.py:39): p_drop = 0 => none.  With p_drop > 0
+ * either keep_mask is an explicit [E',H] uint8 keep mask in edge_index' (PyG) order, applied as alpha*keep/(1-p) (parity
+ * tests inject one), or keep_mask is NULL and the kernels draw the bits from a counter-based RNG keyed on (dropout_seed,
+ * position in edge_index', head) -- no [E',H] tensor exists; forward and backward must be given the same seed.
+ * gnnfd_dropout_mask writes those bits out (test hook) and returns the survivor scale. */
+int gnnfd_dropout_mask(uint64_t dropout_seed, float p_drop, int64_t n_edges, int H, uint8_t* keep_mask,
+                       float* scale_host, gnnfd_stream_t stream);
 int gnnfd_gat_fwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* bytes);
 int gnnfd_gat_fwd(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src,
                   const float* a_dst, const float* bias, int H, int C, float negative_slope, int concat,
-                  int act, const uint8_t* keep_mask, float p_drop, float* out, float* rowmax,
-                  float* rowsum, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+                  int act, const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed, float* out,
+                  float* rowmax, float* rowsum, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 /* Same with the layer loop's eval-mode tail fused into the row epilogue (src/models/gat.py:80-91, tgn.py:94-105):
  *   v = mean/concat + bias;  v = v*post_scale[c] + post_shift[c] (BatchNorm1d with running statistics, folded);
  *   v = act(v);  v += residual[row,c].   post_scale/post_shift [Co] come together or both NULL; residual
  *   [n_dst,Co] or NULL. */
 int gnnfd_gat_fwd_fused(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src,
                         const float* a_dst, const float* bias, int H, int C, float negative_slope, int concat,
-                        int act, const uint8_t* keep_mask, float p_drop, const float* post_scale,
-                        const float* post_shift, const float* residual, float* out, float* rowmax,
-                        float* rowsum, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+                        int act, const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed,
+                        const float* post_scale, const float* post_shift, const float* residual, float* out,
+                        float* rowmax, float* rowsum, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 /* alpha [E',H] in dst-sorted (CSR) order, recomputed from the saved row statistics
  * (return_attention_weights=True; un-permute through perm to get PyG order). */
 int gnnfd_gat_alpha(const gnnfd_graph_t* g, const float* a_src, const float* a_dst, const float* rowmax,
@@ -207,8 +212,8 @@ int gnnfd_gat_bwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* 
 int gnnfd_gat_bwd_dst(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src,
                       const float* a_dst, const float* rowmax, const float* rowsum, const float* d_out,
                       int H, int C, float negative_slope, int concat, const uint8_t* keep_mask,
-                      float p_drop, float* alpha_used, float* dz, float* da_dst, void* ws,
-                      size_t ws_bytes, gnnfd_stream_t stream);
+                      float p_drop, uint64_t dropout_seed, float* alpha_used, float* dz, float* da_dst,
+                      void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 int gnnfd_gat_bwd_src(const gnnfd_graph_t* g, const float* alpha_used, const float* dz,
                       const float* d_out, const float* att_src, const float* att_dst,
                       const float* da_dst_full, int H, int C, int concat, float* dxw, float* da_src,
@@ -252,8 +257,8 @@ int gnnfd_in_fwd_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes);
 /* edge_update + message + aggregate in input space -> zimg, rowmax / rowsum [n_dst,H] (as gnnfd_gat_fwd saves them). */
 int gnnfd_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src,
                  const float* a_dst, float negative_slope, const uint8_t* keep_mask, float p_drop,
-                 const void* prep, void* zimg, float* rowmax, float* rowsum, void* ws, size_t ws_bytes,
-                 gnnfd_stream_t stream);
+                 uint64_t dropout_seed, const void* prep, void* zimg, float* rowmax, float* rowsum, void* ws,
+                 size_t ws_bytes, gnnfd_stream_t stream);
 /* out [n,C] = act((Z W_r / H + bias) * post_scale + post_shift) + residual  (epilogue as gnnfd_gat_fwd_fused). */
 int gnnfd_in_out(const void* zimg, int64_t n, int64_t K, const void* prep, const float* bias, int act,
                  const float* post_scale, const float* post_shift, const float* residual, float* out,
@@ -267,8 +272,8 @@ int gnnfd_in_bwd_edges_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes);
 int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src,
                        const float* a_dst, const float* rowmax, const float* rowsum, const float* gd,
                        int64_t gd_row0, int64_t item_lo, int64_t item_hi, int64_t row_lo, int64_t row_hi,
-                       float negative_slope, const uint8_t* keep_mask, float p_drop, float* dz, float* da_dst,
-                       void* ws, size_t ws_bytes, int phase, gnnfd_stream_t stream);
+                       float negative_slope, const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed,
+                       float* dz, float* da_dst, void* ws, size_t ws_bytes, int phase, gnnfd_stream_t stream);
 /* da_src [n_src,H] = per-source sums of dz (over g's CSC). */
 int gnnfd_in_bwd_dasrc(const gnnfd_graph_t* g, const float* dz, float* da_src, gnnfd_stream_t stream);
 int gnnfd_in_bwd_params_workspace_bytes(int64_t n, int64_t K, size_t* bytes);

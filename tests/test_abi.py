@@ -50,5 +50,5 @@ def test_host_side_argument_errors_need_no_gpu():
     assert lib.gnnfd_gat_fwd_workspace_bytes(C.byref(g), 8, 64, C.byref(nb)) == 0
     # unsupported head geometry fails loudly instead of falling back
     g.n_dst = 0
-    rc = lib.gnnfd_gat_fwd(C.byref(g), 16, _abi.F32, 16, 16, None, 3, 17, 0.2, 0, 0, None, 0.0, 16, 16, 16, None, 0, None)
+    rc = lib.gnnfd_gat_fwd(C.byref(g), 16, _abi.F32, 16, 16, None, 3, 17, 0.2, 0, 0, None, 0.0, 0, 16, 16, 16, None, 0, None)
     assert rc == -5 and b"not built" in lib.gnnfd_last_error()

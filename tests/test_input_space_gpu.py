@@ -125,3 +125,49 @@ def test_fp16_pair_scale_is_range_safe():
         out = conv(x.cuda(), ei.cuda())
         ref, _ = O.gatconv_forward(x.double(), ei, Ws.double(), a_s.double(), a_d.double(), b.double(), 8, 64)
         assert relerr(out, ref) <= 1e-5, scale
+
+
+# ---- in-kernel attention dropout (counter-based RNG) -----------------------------------------------------------------
+@pytest.mark.parametrize("algo", [_abi.GEMM_SIMT, _abi.GEMM_INPUT])
+def test_in_kernel_dropout_equals_its_exported_mask(algo):
+    """Training-mode attention dropout draws its bits inside the kernels.  gnnfd_dropout_mask exports the same bits: a run
+    with the RNG and a run with that mask injected must agree BIT FOR BIT in the output and in every gradient (so forward
+    and backward see one mask), and the injected-mask path is the one checked against the oracle above."""
+    N, E, K, H, C, p = 3000, 30000, 166, 8, 64, 0.2
+    W, a_s, a_d, b = seeded_params(K, H, C, seed=5)
+    x = torch.randn(N, K, generator=torch.Generator().manual_seed(0)).cuda()
+    ei = torch.cat([synth.random_graph(N, E, seed=1), torch.stack([torch.randint(0, N, (900,)), torch.full((900,), 7)])], 1).cuda()
+    conv = _layer(K, H, C, False, W, a_s, a_d, b, dropout=p, gemm_algo=algo).train()
+    need_dx = algo != _abi.GEMM_INPUT
+    d_out = torch.randn(N, C, generator=torch.Generator().manual_seed(3)).cuda() / N
+    torch.manual_seed(123)
+    xg = x.clone().requires_grad_(need_dx)
+    out = conv(xg, ei)
+    out.backward(d_out)
+    seed = conv.last_dropout_seed
+    grads = [p_.grad.clone() for p_ in conv.parameters()] + ([xg.grad.clone()] if need_dx else [])
+    g = conv._graph(ei, N)
+    keep, scale = Fn.dropout_mask(seed, p, g.n_edges, H, x.device)
+    rate = float(keep.float().mean())
+    assert abs(rate - (1 - p)) < 3e-3 and abs(scale * (1 - p) - 1) < 1e-4          # 264K draws: sigma = 8e-4
+    per_head = keep.float().mean(0)
+    assert float((per_head - (1 - p)).abs().max()) < 6e-3
+    # heads and consecutive edges are uncorrelated
+    kf = keep.float() - keep.float().mean()
+    assert abs(float((kf[:, 0] * kf[:, 1]).mean())) < 3e-3 and abs(float((kf[1:, 0] * kf[:-1, 0]).mean())) < 3e-3
+    conv.zero_grad()
+    xg2 = x.clone().requires_grad_(need_dx)
+    out2 = conv(xg2, ei, dropout_mask=keep)
+    out2.backward(d_out)
+    # same bits, same arithmetic; only the survivor scale differs: 65536/(65536 - thr) (the exact keep probability of the
+    # 16-bit draw, 1.249995 for p = 0.2) against the mask path's 1/(1-p) = 1.25, i.e. 3.8e-6 relative
+    assert relerr(out, out2) < 1e-5
+    for ga, pb in zip(grads, list(conv.parameters()) + ([xg2] if need_dx else [])):
+        assert relerr(ga, pb.grad) < 2e-5
+    # a different seed gives a different mask; the same torch seed reproduces the run
+    torch.manual_seed(123)
+    assert torch.equal(conv(x, ei), out.detach())
+    torch.manual_seed(124)
+    assert not torch.equal(conv(x, ei), out.detach())
+    k2, _ = Fn.dropout_mask(seed + 1, p, g.n_edges, H, x.device)
+    assert 0.25 < float((k2 != keep).float().mean()) < 0.40                        # 2 p (1-p) = 0.32
