@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import fused
 from .nn import GATConv
 
 __all__ = ["GAT", "TemporalGNN"]
@@ -36,6 +37,8 @@ class _GATStack(nn.Module):
             GATConv(k, hidden_channels, heads=_HEADS, concat=False, dropout=dropout, **conv_kwargs) for k in fan_in)
         self.batch_norms = (nn.ModuleList(nn.BatchNorm1d(hidden_channels) for _ in fan_in)
                             if use_batch_norm else None)
+        self.fused_tail = True      # train-mode BatchNorm/ReLU/dropout/residual through libgnnfd_b200 (False: torch ops)
+        self.bn_group = None        # process group whose ranks hold disjoint rows of one batch (synchronised statistics)
 
     def _encode(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
         h = x
@@ -48,10 +51,15 @@ class _GATStack(nn.Module):
             return h
         for i, conv in enumerate(self.gat_layers):
             z = conv(h, edge_index)
+            res = h if (self.residual and h.size(-1) == z.size(-1)) else None
+            if self.use_batch_norm and self.training and z.is_cuda and self.fused_tail:
+                # training: BatchNorm (batch statistics) + ReLU + feature dropout + residual in two kernels (gat.py:82-91)
+                h = fused.bn_relu_dropout_residual(z, self.batch_norms[i], self.dropout, res, group=self.bn_group)
+                continue
             if self.use_batch_norm:
                 z = self.batch_norms[i](z)
             z = F.dropout(F.relu(z), p=self.dropout, training=self.training)
-            h = h + z if (self.residual and h.size(-1) == z.size(-1)) else z
+            h = res + z if res is not None else z
         return h
 
 
@@ -77,12 +85,17 @@ class TemporalGNN(_GATStack):
                          **conv_kwargs)
         self.gru = nn.GRUCell(hidden_channels, hidden_channels)
         self.out = nn.Linear(hidden_channels, out_channels)
+        self.fused_head = True
 
     def forward(self, x: torch.Tensor, edge_index: torch.Tensor, batch: Optional[torch.Tensor] = None,
                 hidden_state: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+        h = self._encode(x, edge_index)
+        if h.is_cuda and self.fused_head and fused.gru_head_supported(self.gru, self.out):
+            # GRUCell + Linear(64 -> 1) as one kernel; hidden_state=None is the reference's zero state (tgn.py:88-89)
+            return fused.gru_head(h, self.gru, self.out, hidden_state)
         if hidden_state is None:
             hidden_state = torch.zeros(x.size(0), self.hidden_channels, device=x.device)
-        hidden_state = self.gru(self._encode(x, edge_index), hidden_state)
+        hidden_state = self.gru(h, hidden_state)
         return self.out(hidden_state), hidden_state
 
     def predict(self, x, edge_index, batch=None, hidden_state=None, apply_sigmoid: bool = True) -> torch.Tensor:

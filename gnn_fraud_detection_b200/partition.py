@@ -423,8 +423,10 @@ class InputSpacePartition(DstRangePartition):
 
     def prepare_buffers(self, K):
         from . import functional as Fn
+        import os
         self.prep = Fn._aligned_u8(Fn.in_sizes(self.n_local, K)[0], self.device)
         self.xmax = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self.redundant_logits = os.environ.get("GNNFD_LOGITS_REDUNDANT", "0") == "1"
 
     def layer_fwd_bwd(self, x_full, W, a_s, a_d, bias, d_out, H, C, xw_dtype=None, algo=None, marks=None, graph=None):
         """``x_full``: the replicated input in padded position space ``[world*rows_padded, K]`` with 16-byte aligned,
@@ -441,13 +443,18 @@ class InputSpacePartition(DstRangePartition):
         # forward: logits of the own rows, gathered from every rank; softmax / aggregation / output GEMM are local
         xmax.zero_()
         x_own = x_full[lo:lo + P]
-        a_src_own, a_dst_own = Fn.in_logits(x_own, W, a_s, a_d, prep, xmax)
-        if self.world > 1:
-            a_src_full = torch.empty(self.n_pos, H, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(a_src_full, a_src_own)
-            dist.all_reduce(xmax, op=dist.ReduceOp.MAX)
+        if self.world > 1 and self.redundant_logits:
+            # every rank holds all of x: 32 B of logits per node can also be recomputed locally instead of gathered
+            a_src_full, a_dst_full = Fn.in_logits(x_full, W, a_s, a_d, prep, xmax)
+            a_dst_own = a_dst_full[lo:lo + P]
         else:
-            a_src_full = a_src_own
+            a_src_own, a_dst_own = Fn.in_logits(x_own, W, a_s, a_d, prep, xmax)
+            if self.world > 1:
+                a_src_full = torch.empty(self.n_pos, H, dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(a_src_full, a_src_own)
+                dist.all_reduce(xmax, op=dist.ReduceOp.MAX)
+            else:
+                a_src_full = a_src_own
         Fn.in_prepare(W, K, xmax, prep)
         if marks: marks[1].record()
         zimg, rowmax, rowsum = Fn.in_fwd(g, x_full, a_src_full, a_dst_own, 0.2, prep)

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 9
+#define GNNFD_ABI_VERSION 10
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -282,6 +282,42 @@ int gnnfd_in_bwd_params(const void* zimg, const float* d_out, const float* x, in
                         const float* W, const float* att_src, const float* att_dst, const float* da_src,
                         const float* da_dst, const void* prep, float* dW, float* datt_src, float* datt_dst,
                         float* dbias, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+
+/* ---- (6) model-level fused operators around the layers ---------------------------------------------------
+ * Train-mode tail of the reference's layer loop (src/models/gat.py:82-91 == src/models/tgn.py:96-105): BatchNorm1d with batch
+ * statistics -> ReLU -> feature dropout -> residual add.  Forward: gnnfd_bn_sums (per-rank partial sums, all-reduced by the
+ * caller across GPUs) -> gnnfd_bn_finalize -> gnnfd_bn_relu_drop_res_fwd; backward: gnnfd_bn_bwd_sums (+ all-reduce) ->
+ * gnnfd_bn_bwd_apply.  Feature dropout uses the counter-based generator of the attention dropout, keyed on
+ * (dropout_seed, (row_base + n) * C + c); p_drop = 0 => none.  ws: gnnfd_model_ops_workspace_bytes. */
+int gnnfd_model_ops_workspace_bytes(int64_t N, size_t* bytes);
+int gnnfd_bn_sums(const float* z, int64_t N, int C, double* sums, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+int gnnfd_bn_finalize(const double* sums, double count, int C, float eps, float momentum, float* running_mean,
+                      float* running_var, float* mean, float* invstd, gnnfd_stream_t stream);
+int gnnfd_bn_relu_drop_res_fwd(const float* z, int64_t N, int C, const float* mean, const float* invstd,
+                               const float* gamma, const float* beta, float p_drop, uint64_t dropout_seed,
+                               int64_t row_base, const float* residual, float* out, gnnfd_stream_t stream);
+int gnnfd_bn_bwd_sums(const float* z, const float* d_out, int64_t N, int C, const float* mean, const float* invstd,
+                      const float* gamma, const float* beta, float p_drop, uint64_t dropout_seed, int64_t row_base,
+                      double* sums, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+int gnnfd_bn_bwd_apply(const float* z, const float* d_out, int64_t N, int C, const float* mean, const float* invstd,
+                       const float* gamma, const float* beta, float p_drop, uint64_t dropout_seed, int64_t row_base,
+                       const double* sums, double count, float* dz, float* dgamma, float* dbeta,
+                       gnnfd_stream_t stream);
+/* TemporalGNN head (src/models/tgn.py:60,88-89,108-111), hidden = 64: h_new [N,64] = GRUCell(x, h_prev) with h_prev NULL =
+ * the reference's zero state, out [N] = Linear(64 -> 1)(h_new).  Parameters in nn.GRUCell / nn.Linear layout. */
+int gnnfd_gru_head_fwd(const float* x, const float* h_prev, int64_t N, const float* w_ih, const float* w_hh,
+                       const float* b_ih, const float* b_hh, const float* w_out, const float* b_out, float* h_new,
+                       float* out, gnnfd_stream_t stream);
+int gnnfd_gru_head_bwd(const float* x, const float* h_prev, const float* d_out, const float* d_hnew, int64_t N,
+                       const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* w_out,
+                       const float* b_out, float* dx, float* dh_prev, float* dw_ih, float* dw_hh, float* db_ih,
+                       float* db_hh, float* dw_out, float* db_out, float* gates_ws, void* ws, size_t ws_bytes,
+                       gnnfd_stream_t stream);
+/* The reference's loss on the device (src/train.py:108-139,360-361): masked BCEWithLogitsLoss(pos_weight), mean over the
+ * labelled nodes (y != -1); d_logits = upstream * dloss/dlogits; stats (double[8], device): sum of losses, labelled count,
+ * TP, FP, TN, FN at sigmoid >= 0.5 (src/train.py:146-149) -- no host synchronisation. */
+int gnnfd_bce_masked(const float* logits, const int64_t* y, int64_t N, float pos_weight, float upstream, float* loss,
+                     float* d_logits, double* stats, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 
 #ifdef __cplusplus
 }
