@@ -1,0 +1,155 @@
+"""GPU parity of the model-level fused operators (include/gnnfd_b200.h section (6)) against the torch modules the reference
+uses for the same steps, evaluated in fp64 on the CPU:
+  * train-mode BatchNorm1d -> ReLU -> dropout -> residual   (src/models/gat.py:82-91)
+  * GRUCell + Linear(64 -> 1)                                (src/models/tgn.py:60,88-89,108-111)
+  * masked BCEWithLogitsLoss(pos_weight) + confusion counts  (src/train.py:108-149,360-361)
+and of the models that use them (train step vs the fp64 oracle, fused vs torch-op tail)."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from gnn_fraud_detection_b200 import GAT, TemporalGNN, fused, synth
+from util import maxabs, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,C,with_res", [(1000, 64, True), (257, 64, False), (5, 8, True), (30000, 128, True)])
+def test_bn_relu_residual_train_mode(N, C, with_res):
+    g = torch.Generator().manual_seed(N)
+    z = torch.randn(N, C, generator=g) * 2 + 0.5
+    res = torch.randn(N, C, generator=g) if with_res else None
+    bn = nn.BatchNorm1d(C)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5, generator=g); bn.bias.uniform_(-0.5, 0.5, generator=g)
+        bn.running_mean.normal_(generator=g); bn.running_var.uniform_(0.5, 2.0, generator=g)
+    ref_bn = copy.deepcopy(bn).double().train()
+    zr = z.double().requires_grad_(True)
+    rr = res.double().requires_grad_(True) if with_res else None
+    ref = F.relu(ref_bn(zr))
+    ref = ref + rr if with_res else ref
+    d_out = torch.randn(N, C, generator=g) / N
+    ref.backward(d_out.double())
+    ours_bn = copy.deepcopy(bn).cuda().train()
+    zg = z.cuda().requires_grad_(True)
+    rg = res.cuda().requires_grad_(True) if with_res else None
+    out = fused.bn_relu_dropout_residual(zg, ours_bn, 0.0, rg)
+    out.backward(d_out.cuda())
+    assert relerr(out, ref) <= 1e-6 and maxabs(out, ref) <= 1e-5
+    assert relerr(zg.grad, zr.grad) <= 2e-5 and maxabs(zg.grad, zr.grad) <= 1e-5
+    assert relerr(ours_bn.weight.grad, ref_bn.weight.grad) <= 1e-5 and relerr(ours_bn.bias.grad, ref_bn.bias.grad) <= 1e-5
+    if with_res:
+        assert torch.equal(rg.grad.cpu(), d_out)
+    # running statistics and the batch counter advance exactly like nn.BatchNorm1d's
+    assert relerr(ours_bn.running_mean, ref_bn.running_mean) <= 1e-6 and relerr(ours_bn.running_var, ref_bn.running_var) <= 1e-6
+    assert int(ours_bn.num_batches_tracked) == int(ref_bn.num_batches_tracked) == 1
+
+
+def test_bn_feature_dropout_is_consistent_between_forward_and_backward():
+    N, C, p = 20000, 64, 0.2
+    z = torch.randn(N, C, device="cuda")
+    bn = nn.BatchNorm1d(C).cuda().train()
+    zg = z.clone().requires_grad_(True)
+    out = fused.bn_relu_dropout_residual(zg, bn, p, None, seed=1234)
+    base = fused.bn_relu_dropout_residual(z, copy.deepcopy(bn), 0.0, None)
+    pos = base > 0
+    kept = (out != 0) & pos
+    rate = float(kept.sum()) / float(pos.sum())
+    assert abs(rate - (1 - p)) < 5e-3
+    assert torch.allclose(out[kept], base[kept] * (65536.0 / (65536 - int(p * 65536))), rtol=1e-6)
+    # the gradient of sum(out) w.r.t. z vanishes where the unit was dropped ... checked through the BN-free part: dy
+    out.sum().backward()
+    out2 = fused.bn_relu_dropout_residual(z, copy.deepcopy(bn), p, None, seed=1234)
+    assert torch.equal(out2, out.detach())                        # same seed, same mask
+    assert not torch.equal(fused.bn_relu_dropout_residual(z, copy.deepcopy(bn), p, None, seed=1235), out.detach())
+
+
+@pytest.mark.parametrize("N,with_state", [(1, False), (1000, False), (777, True), (20000, True)])
+def test_gru_head(N, with_state):
+    g = torch.Generator().manual_seed(N)
+    gru, lin = nn.GRUCell(64, 64), nn.Linear(64, 1)
+    x = torch.randn(N, 64, generator=g)
+    h0 = torch.randn(N, 64, generator=g) if with_state else None
+    rg, rl = copy.deepcopy(gru).double(), copy.deepcopy(lin).double()
+    xr = x.double().requires_grad_(True)
+    hr = h0.double().requires_grad_(True) if with_state else torch.zeros(N, 64, dtype=torch.float64)
+    h1r = rg(xr, hr)
+    outr = rl(h1r)
+    d_out, d_h = torch.randn(N, 1, generator=g) / N, torch.randn(N, 64, generator=g) / N
+    (outr * d_out.double()).sum().add((h1r * d_h.double()).sum()).backward()
+    gg, gl = copy.deepcopy(gru).cuda(), copy.deepcopy(lin).cuda()
+    xg = x.cuda().requires_grad_(True)
+    hg = h0.cuda().requires_grad_(True) if with_state else None
+    out, h1 = fused.gru_head(xg, gg, gl, hg)
+    ((out * d_out.cuda()).sum() + (h1 * d_h.cuda()).sum()).backward()
+    assert out.shape == (N, 1) and h1.shape == (N, 64)
+    assert relerr(out, outr) <= 2e-6 and relerr(h1, h1r) <= 2e-6
+    assert relerr(xg.grad, xr.grad) <= 1e-5
+    if with_state:
+        assert relerr(hg.grad, hr.grad) <= 1e-5
+    for ours, ref in ((gg.weight_ih, rg.weight_ih), (gg.bias_ih, rg.bias_ih), (gg.bias_hh, rg.bias_hh), (gl.weight, rl.weight),
+                      (gl.bias, rl.bias)):
+        assert relerr(ours.grad, ref.grad) <= 1e-5
+    if with_state:
+        assert relerr(gg.weight_hh.grad, rg.weight_hh.grad) <= 1e-5
+    else:
+        assert float(gg.weight_hh.grad.abs().max()) == 0.0            # zero state: no gradient reaches W_hh
+
+
+def test_masked_bce_matches_the_reference_loss_and_metrics():
+    N = 50_000
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(N, 1, generator=g) * 3
+    y = torch.randint(-1, 2, (N,), generator=g)
+    mask = y != -1                                                    # src/train.py:108
+    lr = logits.double().requires_grad_(True)
+    crit = nn.BCEWithLogitsLoss(pos_weight=torch.tensor(50.0, dtype=torch.float64))    # src/train.py:360-361
+    ref = crit(lr[mask].squeeze(1), y[mask].double())
+    ref.backward()
+    lg = logits.cuda().requires_grad_(True)
+    loss, stats = fused.masked_bce_with_logits(lg, y.cuda(), 50.0)
+    (loss * 2.0).backward()
+    assert abs(float(loss) - float(ref)) <= 1e-6 * abs(float(ref))
+    assert relerr(lg.grad, 2.0 * lr.grad) <= 1e-6
+    pred = (torch.sigmoid(logits[mask].squeeze(1)) >= 0.5)           # src/train.py:147
+    yt = y[mask] == 1
+    want = [float(mask.sum()), float((pred & yt).sum()), float((pred & ~yt).sum()), float((~pred & ~yt).sum()), float((~pred & yt).sum())]
+    assert stats[1:6].tolist() == want
+    # nothing labelled: zero loss, zero gradient, no NaN
+    l0, s0 = fused.masked_bce_with_logits(lg.detach(), torch.full((N,), -1, device="cuda"), 50.0)
+    assert float(l0) == 0.0 and float(s0[1]) == 0.0
+
+
+def test_models_fused_tail_and_head_equal_the_torch_op_path():
+    """GAT / TemporalGNN train step (dropout 0): the fused tail / head against the same model running torch's BatchNorm1d,
+    relu, GRUCell and Linear -- every parameter gradient."""
+    x, ei, _ = synth.elliptic_synth(num_nodes=20_000, num_edges=23_000, num_feats=166, seed=0)
+    y = (torch.rand(x.size(0), generator=torch.Generator().manual_seed(1)) < 0.1).long()
+    y[::7] = -1
+    for cls in (GAT, TemporalGNN):
+        torch.manual_seed(0)
+        a = cls(166, 64, 1, num_layers=3, dropout=0.0).cuda().train()
+        b = copy.deepcopy(a)
+        b.fused_tail = False
+        if cls is TemporalGNN:
+            b.fused_head = False
+        outs = []
+        for m in (a, b):
+            r = m(x.cuda(), ei.cuda())
+            lg = r[0] if cls is TemporalGNN else r
+            if m is a:
+                loss, _ = fused.masked_bce_with_logits(lg, y.cuda(), 50.0)
+            else:
+                mask = y.cuda() != -1
+                loss = F.binary_cross_entropy_with_logits(lg[mask].squeeze(1), y.cuda()[mask].float(), pos_weight=torch.tensor(50.0, device="cuda"))
+            loss.backward()
+            outs.append((lg.detach(), float(loss)))
+        assert relerr(outs[0][0], outs[1][0]) <= 1e-5 and abs(outs[0][1] - outs[1][1]) <= 1e-5 * abs(outs[1][1])
+        for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            if float(pb.grad.norm()) > 1e-5:      # (conv biases feed a train-mode BatchNorm: their true gradient is zero)
+                assert relerr(pa.grad, pb.grad) <= 2e-4, (cls.__name__, n, relerr(pa.grad, pb.grad))
+        for ba, bb in zip(a.batch_norms, b.batch_norms):
+            assert relerr(ba.running_var, bb.running_var) <= 1e-5 and int(ba.num_batches_tracked) == int(bb.num_batches_tracked) == 1
