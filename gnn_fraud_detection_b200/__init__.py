@@ -2,8 +2,9 @@
 
 Only the hot path lives here: the drop-in ``GATConv`` layer (``nn``), the model classes that host it
 (``models``), the CUDA-built graph structures (``graph``), the autograd glue over the C ABI
-(``functional``), multi-GPU partitioning (``partition``), the snapshot builder that feeds the temporal configuration
-(``snapshot``) and synthetic data generators (``synth``).
+(``functional``), the fused operators around the layers -- train-mode BatchNorm tail, GRU head, masked BCE -- (``fused``),
+the device-resident training step (``train_step``), multi-GPU partitioning (``partition``), the snapshot builder that
+feeds the temporal configuration (``snapshot``) and synthetic data generators (``synth``).
 Importing the package does not load the CUDA library; the first layer call does, and raises if it is
 missing (there is no CPU or PyTorch fallback).
 """

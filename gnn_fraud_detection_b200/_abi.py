@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_INPUT = 0, 1, 2, 3
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -63,6 +63,7 @@ SIGNATURES = {
     "gnnfd_project_fwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gnnfd_gat_fwd_workspace_bytes": (_i, [_gp, _i, _i, _szp]),
     "gnnfd_dropout_mask": (_i, [_u64, _f, _i64, _i, _vp, C.POINTER(C.c_float), _vp]),
+    "gnnfd_set_dropout_seed_source": (None, [_vp]),
     "gnnfd_gat_fwd": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _f, _u64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gnnfd_gat_fwd_fused": (_i, [_gp, _vp, _i, _vp, _vp, _vp, _i, _i, _f, _i, _i, _vp, _f, _u64, _vp, _vp, _vp, _vp, _vp,
                                  _vp, _vp, _sz, _vp]),

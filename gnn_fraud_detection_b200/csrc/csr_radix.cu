@@ -23,6 +23,7 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 std::atomic<long long> g_launches{0};
+const uint64_t* g_dropout_seed_src = nullptr;
 
 // ---- three-phase exclusive scan over a functor ---------------------------------------------------
 constexpr int SC_THREADS = 256;
@@ -427,6 +428,7 @@ extern "C" {
 
 const char* gnnfd_last_error(void) { return g_err; }
 int gnnfd_abi_version(void) { return GNNFD_ABI_VERSION; }
+void gnnfd_set_dropout_seed_source(const uint64_t* device_word) { gnnfd::g_dropout_seed_src = device_word; }
 size_t gnnfd_sizeof_graph(void) { return sizeof(gnnfd_graph_t); }
 size_t gnnfd_sizeof_hub_plan(void) { return sizeof(gnnfd_hub_plan_t); }
 size_t gnnfd_sizeof_item_plan(void) { return sizeof(gnnfd_item_plan_t); }

@@ -75,7 +75,10 @@ struct KeepMask {
     const uint8_t* mask;
     uint64_t seed;
     uint32_t thr;
-    __host__ __device__ KeepMask(const uint8_t* m = nullptr, uint64_t s = 0, uint32_t t = 0) : mask(m), seed(s), thr(t) {}
+    const uint64_t* seed_src;     // optional device word added to the seed (gnnfd_set_dropout_seed_source): lets a step that
+                                  // is replayed from a CUDA graph draw fresh masks -- the graph bumps the word, not the host
+    __host__ __device__ KeepMask(const uint8_t* m = nullptr, uint64_t s = 0, uint32_t t = 0, const uint64_t* src = nullptr)
+        : mask(m), seed(s), thr(t), seed_src(src) {}
     __host__ __device__ static uint64_t mix(uint64_t z)            // splitmix64 finaliser
     {
         z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;
@@ -92,7 +95,11 @@ struct KeepMask {
             for (int h = 0; h < H; ++h) r |= unsigned(kb[h] != 0) << h;
             return r;
         }
-        const uint64_t c = seed + 0x9E3779B97F4A7C15ull * uint64_t(2 * pos + 1);
+        uint64_t sd = seed;
+#ifdef __CUDA_ARCH__
+        if (seed_src) sd += __ldg(reinterpret_cast<const unsigned long long*>(seed_src));
+#endif
+        const uint64_t c = sd + 0x9E3779B97F4A7C15ull * uint64_t(2 * pos + 1);
         const uint64_t w0 = mix(c), w1 = mix(c ^ 0xD1B54A32D192ED03ull);
         for (int h = 0; h < H; ++h) {
             const uint32_t v = uint32_t(((h < 4 ? w0 : w1) >> (16 * (h & 3))) & 0xffffu);
@@ -101,6 +108,7 @@ struct KeepMask {
         return r;
     }
 };
+extern const uint64_t* g_dropout_seed_src;      // csr_radix.cu; set by gnnfd_set_dropout_seed_source
 // host side: the KeepMask and the survivor scale for (explicit mask or NULL, p, seed)
 inline KeepMask make_keep(const uint8_t* mask, float p_drop, uint64_t seed, float* scale)
 {
@@ -109,7 +117,7 @@ inline KeepMask make_keep(const uint8_t* mask, float p_drop, uint64_t seed, floa
     uint32_t thr = uint32_t(double(p_drop) * 65536.0);
     if (thr > 65535u) thr = 65535u;
     *scale = 65536.f / float(65536u - thr);
-    return KeepMask(nullptr, seed, thr);
+    return KeepMask(nullptr, seed, thr, g_dropout_seed_src);
 }
 
 constexpr int ROW_WARPS = 8;                 // warps (rows) per CTA

@@ -34,7 +34,8 @@ def _draw_seed() -> int:
 
 class _BNReluDropRes(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, z, gamma, beta, residual, running_mean, running_var, eps, momentum, p_drop, seed, row_base, group):
+    def forward(ctx, z, gamma, beta, residual, running_mean, running_var, eps, momentum, p_drop, seed, row_base, group,
+                global_rows):
         L = _abi.lib()
         z = z.contiguous()
         N, Cc = z.shape
@@ -45,10 +46,13 @@ class _BNReluDropRes(torch.autograd.Function):
             _abi.check(L.gnnfd_bn_sums(z.data_ptr(), N, Cc, sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
             count = float(N)
             if group is not None:
-                cnt = torch.tensor([count], dtype=torch.float64, device=dev)
                 dist.all_reduce(sums, group=group)
-                dist.all_reduce(cnt, group=group)
-                count = float(cnt.item())
+                if global_rows is not None:           # known batch size: no second collective, no host synchronisation
+                    count = float(global_rows)
+                else:
+                    cnt = torch.tensor([count], dtype=torch.float64, device=dev)
+                    dist.all_reduce(cnt, group=group)
+                    count = float(cnt.item())
             mean = torch.empty(Cc, dtype=torch.float32, device=dev)
             invstd = torch.empty(Cc, dtype=torch.float32, device=dev)
             _abi.check(L.gnnfd_bn_finalize(sums.data_ptr(), count, Cc, float(eps), float(momentum), _abi.ptr(running_mean),
@@ -85,16 +89,17 @@ class _BNReluDropRes(torch.autograd.Function):
                                             _abi.ptr(gamma), _abi.ptr(beta), float(ctx.p), int(ctx.seed), int(ctx.row_base),
                                             sums.data_ptr(), float(ctx.count), dz.data_ptr(), _abi.ptr(dgamma), _abi.ptr(dbeta),
                                             _stream()))
-        return dz, dgamma, dbeta, (d_out if ctx.has_res else None), None, None, None, None, None, None, None, None
+        return dz, dgamma, dbeta, (d_out if ctx.has_res else None), None, None, None, None, None, None, None, None, None
 
 
 def bn_relu_dropout_residual(z: torch.Tensor, bn: nn.BatchNorm1d, p_drop: float = 0.0,
                              residual: Optional[torch.Tensor] = None, seed: Optional[int] = None, row_base: int = 0,
-                             group=None) -> torch.Tensor:
+                             group=None, global_rows: Optional[int] = None) -> torch.Tensor:
     """``residual + dropout(relu(bn(z)))`` with ``bn`` in TRAINING mode (batch statistics, running buffers updated).
 
     ``group``: a process group whose ranks hold disjoint rows of one batch -- the statistics are then those of the whole
-    batch and ``row_base`` is this rank's first global row (it keys the dropout generator)."""
+    batch and ``row_base`` is this rank's first global row (it keys the dropout generator); ``global_rows`` = the batch size
+    over all ranks, if known (saves a collective and a host synchronisation: required under CUDA-graph capture)."""
     if not z.is_cuda or z.dtype != torch.float32 or z.dim() != 2:
         raise RuntimeError("bn_relu_dropout_residual needs a float32 CUDA tensor [N,C] (no CPU fallback)")
     if not bn.training:
@@ -108,7 +113,7 @@ def bn_relu_dropout_residual(z: torch.Tensor, bn: nn.BatchNorm1d, p_drop: float 
     if p_drop > 0.0 and seed is None:
         seed = _draw_seed()
     out = _BNReluDropRes.apply(z, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.eps, bn.momentum,
-                               float(p_drop), int(seed or 0), int(row_base), group)
+                               float(p_drop), int(seed or 0), int(row_base), group, global_rows)
     if bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return out

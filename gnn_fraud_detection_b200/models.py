@@ -39,6 +39,7 @@ class _GATStack(nn.Module):
                             if use_batch_norm else None)
         self.fused_tail = True      # train-mode BatchNorm/ReLU/dropout/residual through libgnnfd_b200 (False: torch ops)
         self.bn_group = None        # process group whose ranks hold disjoint rows of one batch (synchronised statistics)
+        self.bn_rows = None         # ... and the batch size over all its ranks, if known
 
     def _encode(self, x: torch.Tensor, edge_index: torch.Tensor) -> torch.Tensor:
         h = x
@@ -54,7 +55,8 @@ class _GATStack(nn.Module):
             res = h if (self.residual and h.size(-1) == z.size(-1)) else None
             if self.use_batch_norm and self.training and z.is_cuda and self.fused_tail:
                 # training: BatchNorm (batch statistics) + ReLU + feature dropout + residual in two kernels (gat.py:82-91)
-                h = fused.bn_relu_dropout_residual(z, self.batch_norms[i], self.dropout, res, group=self.bn_group)
+                h = fused.bn_relu_dropout_residual(z, self.batch_norms[i], self.dropout, res, group=self.bn_group,
+                                                   global_rows=self.bn_rows)
                 continue
             if self.use_batch_norm:
                 z = self.batch_norms[i](z)

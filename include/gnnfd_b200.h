@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 10
+#define GNNFD_ABI_VERSION 11
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -176,6 +176,10 @@ int gnnfd_project_fwd(const float* x, int64_t ldx, const float* W, const float* 
  * gnnfd_dropout_mask writes those bits out (test hook) and returns the survivor scale. */
 int gnnfd_dropout_mask(uint64_t dropout_seed, float p_drop, int64_t n_edges, int H, uint8_t* keep_mask,
                        float* scale_host, gnnfd_stream_t stream);
+/* Process-wide: when device_word is not NULL every kernel that draws dropout bits adds *device_word to its seed.  A training
+ * step replayed from a CUDA graph (seeds are baked into the captured launches) increments that word inside the graph and so
+ * draws a fresh mask on every replay; forward and backward of one step read the same value.  NULL (default) turns it off. */
+void gnnfd_set_dropout_seed_source(const uint64_t* device_word);
 int gnnfd_gat_fwd_workspace_bytes(const gnnfd_graph_t* g, int H, int C, size_t* bytes);
 int gnnfd_gat_fwd(const gnnfd_graph_t* g, const void* xw, int xw_dtype, const float* a_src,
                   const float* a_dst, const float* bias, int H, int C, float negative_slope, int concat,

@@ -153,3 +153,65 @@ def test_models_fused_tail_and_head_equal_the_torch_op_path():
                 assert relerr(pa.grad, pb.grad) <= 2e-4, (cls.__name__, n, relerr(pa.grad, pb.grad))
         for ba, bb in zip(a.batch_norms, b.batch_norms):
             assert relerr(ba.running_var, bb.running_var) <= 1e-5 and int(ba.num_batches_tracked) == int(bb.num_batches_tracked) == 1
+
+
+def test_device_resident_train_step_graph_replay_equals_eager_loop():
+    """DeviceTrainStep (forward + loss + backward + Adam replayed from one CUDA graph, counters on the device) against the
+    reference's loop structure written out eagerly (src/train.py:103-149) on identical models: parameters after 4 steps,
+    per-step loss, and the accumulated confusion counters."""
+    from gnn_fraud_detection_b200.train_step import DeviceTrainStep
+    x, ei, _ = synth.elliptic_synth(num_nodes=8000, num_edges=9200, num_feats=166, seed=0)
+    y = (torch.rand(x.size(0), generator=torch.Generator().manual_seed(1)) < 0.1).long()
+    y[::5] = -1
+    xg, eg, yg = x.cuda(), ei.cuda(), y.cuda()
+    for cls in (GAT, TemporalGNN):
+        torch.manual_seed(0)
+        a = cls(166, 64, 1, num_layers=2, dropout=0.0).cuda().train()
+        b = copy.deepcopy(a)
+        trainer = DeviceTrainStep(a, xg, eg, yg, pos_weight=50.0, use_cuda_graph=True)
+        # construction ran 3 warm-up steps (capturing records the 4th, it does not execute it): same state for the eager twin
+        opt = torch.optim.Adam(b.parameters(), lr=1e-3, weight_decay=5e-4)
+        crit = nn.BCEWithLogitsLoss(pos_weight=torch.tensor(50.0, device="cuda"))
+        mask = yg != -1
+
+        def eager_step():
+            opt.zero_grad()
+            r = b(xg, eg)
+            lg = r[0] if cls is TemporalGNN else r
+            loss = crit(lg[mask].squeeze(1), yg[mask].float())
+            loss.backward()
+            opt.step()
+            pred = torch.sigmoid(lg[mask].squeeze(1)) >= 0.5
+            return float(loss), int((pred & (yg[mask] == 1)).sum()), int((pred & (yg[mask] == 0)).sum())
+
+        for _ in range(3):
+            eager_step()
+        tp = fp = 0
+        for _ in range(4):
+            loss_d, _ = trainer.step()
+            le, tpe, fpe = eager_step()
+            tp, fp = tp + tpe, fp + fpe
+            assert abs(float(loss_d) - le) <= 2e-4 * abs(le)
+        m = trainer.metrics()
+        assert m["labelled"] == 4 * int(mask.sum()) and abs(m["tp"] - tp) <= 2 and abs(m["fp"] - fp) <= 2
+        for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            if n.startswith("gat_layers.") and n.endswith(".bias"):
+                continue        # feeds a train-mode BatchNorm: true gradient 0, Adam turns the 1e-8 rounding noise into +-lr steps
+            assert relerr(pa, pb) <= 1e-3, (cls.__name__, n, relerr(pa, pb))
+        trainer.close()
+
+
+def test_graph_replayed_step_draws_fresh_dropout_masks():
+    from gnn_fraud_detection_b200.train_step import DeviceTrainStep
+    x, ei, _ = synth.elliptic_synth(num_nodes=4000, num_edges=4600, num_feats=166, seed=0)
+    y = (torch.rand(x.size(0), generator=torch.Generator().manual_seed(1)) < 0.2).long()
+    torch.manual_seed(0)
+    m = GAT(166, 64, 1, num_layers=2, dropout=0.5).cuda().train()
+    # lr = 0: the weights never move, so any change of the loss between replays comes from the dropout masks alone
+    tr = DeviceTrainStep(m, x.cuda(), ei.cuda(), y.cuda(), optimizer=torch.optim.SGD(m.parameters(), lr=0.0), use_cuda_graph=True)
+    losses = [float(tr.step()[0]) for _ in range(4)]
+    assert len(set(losses)) == 4, losses
+    tr.close()
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x.cuda(), ei.cuda()), m(x.cuda(), ei.cuda()))
