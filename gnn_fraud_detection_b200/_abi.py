@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_INPUT = 0, 1, 2, 3
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -61,6 +61,9 @@ SIGNATURES = {
     "gnnfd_hub_plan": (_i, [_vp, _i64, C.c_int32, C.c_int32, _vp, _vp, _vp, _i64, _i64, _i64p, _vp, _sz, _vp]),
     "gnnfd_project_workspace_bytes": (_i, [_i64, _i64, _i, _i, _i, _szp]),
     "gnnfd_project_fwd": (_i, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "gnnfd_project_image_bytes": (_i, [_i64, _i64, _szp, _szp]),
+    "gnnfd_project_image_build": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "gnnfd_project_fwd_image": (_i, [_vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "gnnfd_gat_fwd_workspace_bytes": (_i, [_gp, _i, _i, _szp]),
     "gnnfd_dropout_mask": (_i, [_u64, _f, _i64, _i, _vp, C.POINTER(C.c_float), _vp]),
     "gnnfd_set_dropout_seed_source": (None, [_vp]),

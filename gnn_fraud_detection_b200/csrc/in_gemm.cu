@@ -268,6 +268,241 @@ in_out_gemm(const uint8_t* __restrict__ zimg, const uint8_t* __restrict__ wimg, 
 }
 
 // ======================================================================================================================
+// xw = x W^T (+ logits) for the projected-feature path, A from a CACHED fp16-pair image of x
+// ======================================================================================================================
+// The projection of project_tc.cu stages x through registers (hi/lo split by four producer warps), which is what bounds it
+// (ncu: 2.4 TB/s, tensor pipe 49 %).  For the first layer x is static across training steps, so its split image is built
+// once (gnnfd_project_image_build, like the CSR) and every step's GEMM is fed by the copy engine alone.  Each ROW carries
+// its own power-of-two scale (rows of very different magnitude keep 22 bits each); it is undone in the epilogue.
+// Per 128-row tile: A = NKBX k-blocks (96 KB for K = 166) resident in shared memory; the W image streams through a
+// 3-stage ring in (n-tile of 128 columns, k-block) order; accumulators: 2 x 128 TMEM columns (epilogue of n-tile t
+// overlaps the MMAs of t+1).  Epilogue as in project_tc_ws.cuh: thread = row, per-head logit dots from the TMEM tile,
+// coalesced stores through shared memory.
+constexpr int P1_BN = 128;                          // columns per n-tile
+constexpr int P1_NT = (H * C) / P1_BN;              // 4
+constexpr int P1_BSTAGES = 3;
+constexpr uint32_t P1_B = 2 * P1_BN * 128;          // 32 KB: hi + lo [128 rows x 128 B]
+constexpr int P1_MAX_KB = 3;                        // K <= 192
+constexpr int P1_THREADS = 192;
+constexpr size_t P1_SMEM = size_t(P1_MAX_KB) * KBLOCK + size_t(P1_BSTAGES) * P1_B + 4 * 32 * G1_STG_LD * 4 + 1024;
+
+__global__ void __launch_bounds__(P1_THREADS, 1)
+in_proj_gemm(const uint8_t* __restrict__ ximg, const float* __restrict__ row_scale, const uint8_t* __restrict__ wimg,
+             const float* __restrict__ scal, int64_t n, int NKBX, const float* __restrict__ att_src,
+             const float* __restrict__ att_dst, float* __restrict__ xw, float* __restrict__ a_src, float* __restrict__ a_dst)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;                                         // [P1_MAX_KB][KBLOCK]
+    uint8_t* sB = smem + size_t(P1_MAX_KB) * KBLOCK;            // [P1_BSTAGES][P1_B]
+    __shared__ uint64_t a_full, a_empty, b_full[P1_BSTAGES], b_empty[P1_BSTAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    if (tid == 0) {
+        st_mbar_init(&a_full, 1);
+        st_mbar_init(&a_empty, 1);
+        for (int s = 0; s < P1_BSTAGES; ++s) { st_mbar_init(&b_full[s], 1); st_mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { st_mbar_init(&acc_full[s], 1); st_mbar_init(&acc_empty[s], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ---------------- producer --------------------------------------------------------------------------------
+        int64_t j = 0, bstep = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+            if (j > 0) st_mbar_wait(&a_empty, uint32_t((j - 1) & 1));
+            if (elect_one()) {
+                st_mbar_expect_tx(&a_full, uint32_t(NKBX) * KBLOCK);
+                st_bulk_g2s(sA, ximg + size_t(t) * NKBX * KBLOCK, uint32_t(NKBX) * KBLOCK, &a_full);
+            }
+            __syncwarp();
+            for (int nt = 0; nt < P1_NT; ++nt)
+                for (int kb = 0; kb < NKBX; ++kb, ++bstep) {
+                    const int s = int(bstep % P1_BSTAGES);
+                    const int64_t u = bstep / P1_BSTAGES;
+                    if (u > 0) st_mbar_wait(&b_empty[s], uint32_t((u - 1) & 1));
+                    if (elect_one()) {
+                        st_mbar_expect_tx(&b_full[s], P1_B);
+                        st_bulk_g2s(sB + size_t(s) * P1_B, wimg + (size_t(nt) * NKBX + kb) * P1_B, P1_B, &b_full[s]);
+                    }
+                    __syncwarp();
+                }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issue --------------------------------------------------------------------------------
+        constexpr uint32_t IDESC = make_idesc_f16(128, P1_BN, 0, 0);
+        int64_t j = 0, bstep = 0, astep = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++j) {
+            st_mbar_wait(&a_full, uint32_t(j & 1));
+            for (int nt = 0; nt < P1_NT; ++nt, ++astep) {
+                const int buf = int(astep & 1);
+                if ((astep >> 1) > 0) st_mbar_wait(&acc_empty[buf], uint32_t(((astep >> 1) - 1) & 1));
+                tc_fence_after();
+                const uint32_t d = tmem_base + uint32_t(buf * P1_BN);
+                for (int kb = 0; kb < NKBX; ++kb, ++bstep) {
+                    const int s = int(bstep % P1_BSTAGES);
+                    st_mbar_wait(&b_full[s], uint32_t((bstep / P1_BSTAGES) & 1));
+                    tc_fence_after();
+                    const uint32_t a_hi = st_smem_u32(sA + size_t(kb) * KBLOCK), a_lo = a_hi + PLANE;
+                    const uint32_t b_hi = st_smem_u32(sB + size_t(s) * P1_B), b_lo = b_hi + P1_BN * 128;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint32_t ko = ks * 32;
+                            const uint64_t dah = make_desc(a_hi + ko, 16, 1024), dal = make_desc(a_lo + ko, 16, 1024);
+                            const uint64_t dbh = make_desc(b_hi + ko, 16, 1024), dbl = make_desc(b_lo + ko, 16, 1024);
+                            umma_f16(d, dah, dbh, IDESC, (kb | ks) ? 1u : 0u);
+                            umma_f16(d, dah, dbl, IDESC, 1u);
+                            umma_f16(d, dal, dbh, IDESC, 1u);
+                        }
+                        umma_commit(&b_empty[s]);
+                        if (kb == NKBX - 1) {
+                            umma_commit(&acc_full[buf]);
+                            if (nt == P1_NT - 1) umma_commit(&a_empty);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ---------------- epilogue: warps 2..5 -> TMEM lane quadrants 2,3,0,1 -----------------------------------------
+        const int quad = warp & 3;
+        float* stg = reinterpret_cast<float*>(smem + size_t(P1_MAX_KB) * KBLOCK + size_t(P1_BSTAGES) * P1_B) + (warp - 2) * (32 * G1_STG_LD);
+        const float inv_w = 1.f / scal[1];
+        int64_t astep = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+            const int64_t m0 = t * TILE + quad * 32;
+            const int64_t row = m0 + lane;
+            const float inv = row < n ? inv_w / row_scale[row] : 0.f;
+            for (int nt = 0; nt < P1_NT; ++nt, ++astep) {
+                const int buf = int(astep & 1);
+                st_mbar_wait(&acc_full[buf], uint32_t((astep >> 1) & 1));
+                tc_fence_after();
+                float ps = 0.f, pd = 0.f;
+#pragma unroll 1
+                for (int ch = 0; ch < P1_BN / 32; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(buf * P1_BN + ch * 32), v);
+                    const int col0 = nt * P1_BN + ch * 32;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4) {
+                        const float4 as4 = __ldg(reinterpret_cast<const float4*>(att_src + col0 + c));
+                        const float4 ad4 = __ldg(reinterpret_cast<const float4*>(att_dst + col0 + c));
+                        const float f0 = __uint_as_float(v[c]) * inv, f1 = __uint_as_float(v[c + 1]) * inv;
+                        const float f2 = __uint_as_float(v[c + 2]) * inv, f3 = __uint_as_float(v[c + 3]) * inv;
+                        v[c] = __float_as_uint(f0); v[c + 1] = __float_as_uint(f1); v[c + 2] = __float_as_uint(f2); v[c + 3] = __float_as_uint(f3);
+                        ps = fmaf(f0, as4.x, ps); pd = fmaf(f0, ad4.x, pd);
+                        ps = fmaf(f1, as4.y, ps); pd = fmaf(f1, ad4.y, pd);
+                        ps = fmaf(f2, as4.z, ps); pd = fmaf(f2, ad4.z, pd);
+                        ps = fmaf(f3, as4.w, ps); pd = fmaf(f3, ad4.w, pd);
+                    }
+                    if (ch & 1) {                                   // two 32-column chunks per 64-wide head
+                        if (row < n) {
+                            const int hh = col0 / 64;
+                            a_src[row * H + hh] = ps;
+                            a_dst[row * H + hh] = pd;
+                        }
+                        ps = pd = 0.f;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int c = 0; c < 32; c += 4)
+                        *reinterpret_cast<float4*>(stg + lane * G1_STG_LD + c) =
+                            make_float4(__uint_as_float(v[c]), __uint_as_float(v[c + 1]), __uint_as_float(v[c + 2]), __uint_as_float(v[c + 3]));
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = 4 * i + (lane >> 3), cq = (lane & 7) * 4;
+                        const int64_t gm = m0 + r;
+                        if (gm < n)
+                            *reinterpret_cast<float4*>(xw + gm * (H * C) + col0 + cq) = *reinterpret_cast<const float4*>(stg + r * G1_STG_LD + cq);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// x [N,K] -> fp16-pair image (NKBX k-blocks of 64 features per 128-row tile) with a per-row power-of-two scale; warp = row
+__global__ void __launch_bounds__(256)
+in_ximg_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int K, int NKBX, uint8_t* __restrict__ ximg,
+               float* __restrict__ row_scale)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t n = int64_t(blockIdx.x) * 8 + warp; n < N; n += int64_t(gridDim.x) * 8) {
+        const float* row = x + n * ldx;
+        float v[P1_MAX_KB][2];
+        float mx = 0.f;
+#pragma unroll
+        for (int kb = 0; kb < P1_MAX_KB; ++kb) {
+            const int k = kb * 64 + 2 * lane;
+            v[kb][0] = (kb < NKBX && k < K) ? row[k] : 0.f;
+            v[kb][1] = (kb < NKBX && k + 1 < K) ? row[k + 1] : 0.f;
+            mx = fmaxf(mx, fmaxf(fabsf(v[kb][0]), fabsf(v[kb][1])));
+        }
+        mx = warp_max(mx);
+        const float sc = pow2_scale(mx);
+        if (lane == 0) row_scale[n] = sc;
+        const uint32_t rr = uint32_t(n) & (TILE - 1);
+        uint8_t* base = ximg + size_t(n >> 7) * size_t(NKBX) * KBLOCK + plane_off(int(rr), 2 * lane);
+#pragma unroll
+        for (int kb = 0; kb < P1_MAX_KB; ++kb)
+            if (kb < NKBX) {
+                __half2 hi, lo;
+                split_h2(v[kb][0] * sc, v[kb][1] * sc, hi, lo);
+                *reinterpret_cast<__half2*>(base + size_t(kb) * KBLOCK) = hi;
+                *reinterpret_cast<__half2*>(base + size_t(kb) * KBLOCK + PLANE) = lo;
+            }
+    }
+}
+// W [512, K] -> B images in (n-tile of 128 output columns, k-block) order: [hi 128 x 128 B | lo], scaled by sw; also scal[1] = sw
+__global__ void in_wproj_image_kernel(const float* __restrict__ W, int K, int NKBX, float* __restrict__ scal, uint8_t* __restrict__ img)
+{
+    __shared__ float red[32];
+    __shared__ float sw_s;
+    float m = 0.f;
+    for (int i = threadIdx.x; i < H * C * K; i += blockDim.x) m = fmaxf(m, fabsf(W[i]));
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        m = warp_max(m);
+        if (threadIdx.x == 0) { sw_s = pow2_scale(m); if (blockIdx.x == 0) scal[1] = sw_s; }
+    }
+    __syncthreads();
+    const float sw = sw_s;
+    const int nt = blockIdx.x / NKBX, kb = blockIdx.x % NKBX;
+    uint8_t* dst = img + size_t(blockIdx.x) * P1_B;
+    for (int idx = threadIdx.x; idx < P1_BN * 64; idx += blockDim.x) {
+        const int r = idx >> 6, e = idx & 63, k = kb * 64 + e;
+        const float v = k < K ? W[int64_t(nt * P1_BN + r) * K + k] * sw : 0.f;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const uint32_t off = plane_off(r, e);
+        *reinterpret_cast<__half*>(dst + off) = hi;
+        *reinterpret_cast<__half*>(dst + P1_BN * 128 + off) = lo;
+    }
+}
+
+// ======================================================================================================================
 // dWr partials:  P[slab][f][c] = sum_{i in slab} Z[i,f] * dO[i,c]   (both operands MN-major, reduction over nodes)
 // ======================================================================================================================
 // A CTA owns a slab of node tiles and HALF of the feature M-tiles (TMEM holds 6 accumulators of 128 x 64).  Per node
@@ -610,6 +845,58 @@ int gnnfd_in_bwd_params(const void* zimg, const float* d_out, const float* x, in
                                                              reinterpret_cast<const float*>(dmax), Gm, att_src, att_dst, d.K,
                                                              d.KP, dW);
     g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+
+/* Cached-image projection (projected-feature path, first layer): gnnfd_project_image_build splits x once into the fp16-pair
+ * tensor-core image (+ one power-of-two scale per row); gnnfd_project_fwd_image then computes xw = x W^T and the per-head
+ * logits exactly like gnnfd_project_fwd, fed by the copy engine alone.  H = 8, C = 64, K <= 192.
+ * ximg: gnnfd_project_image_bytes, 1024-byte aligned; row_scale [N]; ws >= 512 KB + 1 KB, 1024-byte aligned. */
+int gnnfd_project_image_bytes(int64_t N, int64_t K, size_t* ximg_bytes, size_t* ws_bytes)
+{
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && N >= 0, GNNFD_ERR_ARG, "project_image_bytes: K must be in [1,%d]", MAX_K);
+    const int nkbx = int((K + 63) / 64);
+    if (ximg_bytes) *ximg_bytes = size_t((N + TILE - 1) / TILE) * nkbx * KBLOCK + 1024;
+    if (ws_bytes) *ws_bytes = size_t(P1_NT) * nkbx * P1_B + 2048;
+    return GNNFD_OK;
+}
+int gnnfd_project_image_build(const float* x, int64_t ldx, int64_t N, int64_t K, void* ximg, float* row_scale, gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && ldx >= K && N >= 0, GNNFD_ERR_ARG, "project_image_build: bad shape");
+    if (N == 0) return GNNFD_OK;
+    GNNFD_REQUIRE(x && ximg && row_scale && (reinterpret_cast<uintptr_t>(ximg) & 1023) == 0, GNNFD_ERR_ARG,
+                  "project_image_build: NULL tensor or ximg not 1024-byte aligned");
+    const int nkbx = int((K + 63) / 64);
+    int64_t blocks = (N + 7) / 8;
+    if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
+    in_ximg_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, N, (int)K, nkbx, reinterpret_cast<uint8_t*>(ximg), row_scale);
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+int gnnfd_project_fwd_image(const void* ximg, const float* row_scale, int64_t N, int64_t K, const float* W, const float* att_src,
+                            const float* att_dst, float* xw, float* a_src, float* a_dst, void* ws, size_t ws_bytes,
+                            gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && N >= 0 && W && att_src && att_dst, GNNFD_ERR_ARG, "project_fwd_image: bad argument");
+    if (N == 0) return GNNFD_OK;
+    size_t need = 0;
+    gnnfd_project_image_bytes(N, K, nullptr, &need);
+    GNNFD_REQUIRE(ximg && row_scale && xw && a_src && a_dst && ws && ws_bytes >= need && (reinterpret_cast<uintptr_t>(ws) & 1023) == 0,
+                  GNNFD_ERR_WORKSPACE, "project_fwd_image: NULL tensor, or workspace too small / not 1024-byte aligned");
+    GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(xw) & 15) == 0, GNNFD_ERR_ARG, "project_fwd_image: xw must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nkbx = int((K + 63) / 64);
+    float* scal = reinterpret_cast<float*>(ws);
+    uint8_t* wimg = reinterpret_cast<uint8_t*>(ws) + 1024;
+    in_wproj_image_kernel<<<P1_NT * nkbx, 512, 0, st>>>(W, (int)K, nkbx, scal, wimg);
+    const int64_t n_tiles = (N + TILE - 1) / TILE;
+    const unsigned grid = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());
+    GNNFD_CUDA(cudaFuncSetAttribute(in_proj_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1_SMEM));
+    in_proj_gemm<<<grid, P1_THREADS, P1_SMEM, st>>>(reinterpret_cast<const uint8_t*>(ximg), row_scale, wimg, scal, N, nkbx, att_src, att_dst,
+                                                    xw, a_src, a_dst);
+    g_launches += 2;
     GNNFD_LAUNCH_CHECK();
     return GNNFD_OK;
 }

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 11
+#define GNNFD_ABI_VERSION 12
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -164,6 +164,17 @@ int gnnfd_project_fwd(const float* x, int64_t ldx, const float* W, const float* 
                       const float* att_dst, int64_t N, int64_t K, int H, int C, int xw_dtype, int algo,
                       void* xw, float* a_src, float* a_dst, void* ws, size_t ws_bytes,
                       gnnfd_stream_t stream);
+
+/* Cached-image projection for a STATIC layer input (the first layer's x does not change between training steps): x is split
+ * once into the fp16-pair tensor-core image (power-of-two scale per row; csrc/in_common.cuh layout) and gnnfd_project_fwd_image
+ * then computes exactly what gnnfd_project_fwd computes (xw fp32 + per-head logits), with both operands delivered by the bulk
+ * copy engine instead of staging warps.  H = 8, C = 64, K <= 192.  ximg 1024-byte aligned; ws 1024-byte aligned. */
+int gnnfd_project_image_bytes(int64_t N, int64_t K, size_t* ximg_bytes, size_t* ws_bytes);
+int gnnfd_project_image_build(const float* x, int64_t ldx, int64_t N, int64_t K, void* ximg, float* row_scale,
+                              gnnfd_stream_t stream);
+int gnnfd_project_fwd_image(const void* ximg, const float* row_scale, int64_t N, int64_t K, const float* W,
+                            const float* att_src, const float* att_dst, float* xw, float* a_src, float* a_dst,
+                            void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 
 /* ---- (3) fused LeakyReLU + online segment softmax + weighted neighbour gather-sum ------------
  * Replaces: edge_update + message + aggregate + head mean/concat + bias of GATConv.forward.

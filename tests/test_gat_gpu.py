@@ -292,3 +292,32 @@ def test_headline_config_properties_200m_edges():
     assert torch.allclose(dbias.double(), d_out.double().sum(0), rtol=1e-4, atol=1e-9)
     assert float(dW.abs().max()) == 0.0                                              # dxw = 0 => dW = 0 exactly
     GLOBAL_CSR_CACHE.clear()
+
+
+@pytest.mark.parametrize("N,K", [(1, 70), (1000, 166), (777, 165), (4100, 100), (130, 192), (20000, 166)])
+def test_projection_from_cached_image(N, K):
+    """gnnfd_project_fwd_image (fp16-pair image of x built once, both operands via the copy engine) against the fp64 product
+    and against the register-staged tensor-core projection; rows of very different magnitude keep their relative accuracy
+    (per-row scale)."""
+    H, C = 8, 64
+    W, a_s, a_d, _ = seeded_params(K, H, C, seed=3)
+    x = torch.randn(N, K, generator=torch.Generator().manual_seed(N + K))
+    x[::3] *= 1e-4
+    x[1::3] *= 3e3
+    xg, Wg, asg, adg = x.cuda(), W.cuda(), a_s.cuda().view(-1), a_d.cuda().view(-1)
+    img = Fn.XImage(xg)
+    xw_i, as_i, ad_i = Fn.project_fwd_image(img, Wg, asg, adg)
+    ref = x.double() @ W.double().t()
+    ra = (ref.view(N, H, C) * a_s.double()).sum(-1)
+    rd = (ref.view(N, H, C) * a_d.double()).sum(-1)
+    rowmag = ref.abs().amax(1, keepdim=True).clamp_min(1e-30)
+    assert float(((xw_i.double().cpu() - ref).abs() / rowmag).max()) <= 2e-6          # per row: relative to the row's size
+    assert float(((as_i.double().cpu() - ra).abs() / rowmag).max()) <= 4e-6 and float(((ad_i.double().cpu() - rd).abs() / rowmag).max()) <= 4e-6
+    xw_t, as_t, _ = Fn.project_fwd(xg, Wg, asg, adg, H, C, torch.float32, _abi.GEMM_TC)
+    assert float(((xw_i - xw_t).double().cpu().abs() / rowmag).max()) <= 4e-6
+    # the cache hands back the same image for the same tensor and a new one after an in-place edit
+    c = Fn.XImageCache()
+    i1 = c.get(xg)
+    assert c.get(xg) is i1
+    xg.mul_(2.0)
+    assert c.get(xg) is not i1
