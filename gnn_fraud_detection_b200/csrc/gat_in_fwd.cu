@@ -23,7 +23,7 @@
 namespace gnnfd {
 extern std::atomic<long long> g_launches;
 int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who);
-int in_build_gd_image(const float* W, int K, void* prep, cudaStream_t st);   // project_tc.cu
+int in_build_gd_image(const float* W, int K, void* prep, cudaStream_t st);   // in_gemm.cu
 
 namespace in {
 constexpr int IN_UNROLL_FWD = GNNFD_IN_UNROLL_FWD;

@@ -77,14 +77,11 @@ __device__ __forceinline__ void split_h2(float v0, float v1, __half2& hi, __half
 // Device-resident per-call constants and operand images ("prep" buffer), built by gnnfd_in_prepare:
 //   float scal[8]      : [0] sx (scale of x / Z), [1] sw (scale of W), [2] 1/(sx*sw*H), [3] 1/sx
 //   W image for out = Z W_r   : NKB k-blocks x (hi [64 rows x 128 B] | lo), rows = c, K-major, scaled by sw
-//   W image for Gd = dO W_r^T : tf32 hi/lo images of gemm_tc_ws (rows = feature f, reduction over c), scaled by 1/H
+//   W image for Gd = dO W_r^T : fp16 hi/lo, n-tiles of 128 features x 64 c (K-major in c), scaled by sw (1/H in the epilogue)
 //   u [2H][KP]         : W_h^T att_src[h] (rows 0..H-1) and W_h^T att_dst[h] (rows H..2H-1)
 constexpr size_t PREP_SCAL_BYTES = 256;
 __host__ __device__ inline size_t prep_wout_bytes(const Dims& d) { return size_t(d.NKB) * 16384; }
-__host__ __device__ inline size_t prep_wgd_bytes(const Dims& d)
-{
-    return size_t((d.F + 255) / 256) * 2 /*k-blocks of 32 c*/ * 2 /*hi, lo*/ * (256 * 32) * sizeof(float);
-}
+__host__ __device__ inline size_t prep_wgd_bytes(const Dims& d) { return size_t((d.F + 127) / 128) * 2 /*hi, lo*/ * (128 * 128); }
 __host__ __device__ inline size_t prep_u_bytes(const Dims& d) { return size_t(2 * H) * d.KP * sizeof(float); }
 __host__ __device__ inline size_t prep_off_wout(const Dims&) { return 1024; }
 __host__ __device__ inline size_t prep_off_wgd(const Dims& d) { return 1024 + ((prep_wout_bytes(d) + 1023) & ~size_t(1023)); }

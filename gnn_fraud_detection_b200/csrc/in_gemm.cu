@@ -19,7 +19,6 @@
 namespace gnnfd {
 extern std::atomic<long long> g_launches;
 int check_graph(const gnnfd_graph_t* g, bool need_csc, const char* who);
-int in_gd_gemm(const float* d_out, int64_t n, int K, const void* prep, float* gd, cudaStream_t st);                 // project_tc.cu
 size_t in_param_ws_bytes(int64_t N, int64_t K);                                                                     // project_simt.cu
 int in_param_grads_simt(const float* x, int64_t ldx, const float* W, const float* da_src, const float* da_dst,
                         const float* d_out, int64_t N, int64_t K, float* datt_src, float* datt_dst, float* dbias,
@@ -279,17 +278,22 @@ in_out_gemm(const uint8_t* __restrict__ zimg, const uint8_t* __restrict__ wimg, 
 // overlaps the MMAs of t+1).  Epilogue as in project_tc_ws.cuh: thread = row, per-head logit dots from the TMEM tile,
 // coalesced stores through shared memory.
 constexpr int P1_BN = 128;                          // columns per n-tile
-constexpr int P1_NT = (H * C) / P1_BN;              // 4
-constexpr int P1_BSTAGES = 3;
+constexpr int P1_NT_PROJ = (H * C) / P1_BN;         // 4
+constexpr int P1_BSTAGES = 2;
 constexpr uint32_t P1_B = 2 * P1_BN * 128;          // 32 KB: hi + lo [128 rows x 128 B]
 constexpr int P1_MAX_KB = 3;                        // K <= 192
-constexpr int P1_THREADS = 192;
-constexpr size_t P1_SMEM = size_t(P1_MAX_KB) * KBLOCK + size_t(P1_BSTAGES) * P1_B + 4 * 32 * G1_STG_LD * 4 + 1024;
+constexpr int P1_EPI_WARPS = 8;                     // two per TMEM lane quadrant: each takes 64 of the 128 columns (= one head)
+constexpr int P1_THREADS = 64 + 32 * P1_EPI_WARPS;
+constexpr size_t P1_SMEM = size_t(P1_MAX_KB) * KBLOCK + size_t(P1_BSTAGES) * P1_B + P1_EPI_WARPS * 32 * G1_STG_LD * 4 + 1024;
 
+// LOGITS: the projection (n_nt = 4 n-tiles of 128 = the 8 heads; per-head logit dots).  !LOGITS: plain C = A B^T with n_nt
+// n-tiles, the first n_valid columns stored (n_valid % 32 == 0) -- used for Gd = dO W_r^T (K = 64, 1344 columns).
+template <bool LOGITS>
 __global__ void __launch_bounds__(P1_THREADS, 1)
 in_proj_gemm(const uint8_t* __restrict__ ximg, const float* __restrict__ row_scale, const uint8_t* __restrict__ wimg,
-             const float* __restrict__ scal, int64_t n, int NKBX, const float* __restrict__ att_src,
-             const float* __restrict__ att_dst, float* __restrict__ xw, float* __restrict__ a_src, float* __restrict__ a_dst)
+             const float* __restrict__ scal, int64_t n, int NKBX, int n_nt, int ld_out, int n_valid, float out_scale,
+             const float* __restrict__ att_src, const float* __restrict__ att_dst, float* __restrict__ xw,
+             float* __restrict__ a_src, float* __restrict__ a_dst)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -304,7 +308,7 @@ in_proj_gemm(const uint8_t* __restrict__ ximg, const float* __restrict__ row_sca
         st_mbar_init(&a_full, 1);
         st_mbar_init(&a_empty, 1);
         for (int s = 0; s < P1_BSTAGES; ++s) { st_mbar_init(&b_full[s], 1); st_mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { st_mbar_init(&acc_full[s], 1); st_mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < 2; ++s) { st_mbar_init(&acc_full[s], 1); st_mbar_init(&acc_empty[s], P1_EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, 256);
@@ -312,6 +316,7 @@ in_proj_gemm(const uint8_t* __restrict__ ximg, const float* __restrict__ row_sca
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    const int P1_NT = n_nt;
 
     if (warp == 0) {
         // ---------------- producer --------------------------------------------------------------------------------
@@ -373,10 +378,10 @@ in_proj_gemm(const uint8_t* __restrict__ ximg, const float* __restrict__ row_sca
             }
         }
     } else {
-        // ---------------- epilogue: warps 2..5 -> TMEM lane quadrants 2,3,0,1 -----------------------------------------
-        const int quad = warp & 3;
+        // ---------------- epilogue: warps 2..9 -> TMEM lane quadrant warp & 3, column half (warp - 2) >> 2 ------------------
+        const int quad = warp & 3, half = (warp - 2) >> 2;
         float* stg = reinterpret_cast<float*>(smem + size_t(P1_MAX_KB) * KBLOCK + size_t(P1_BSTAGES) * P1_B) + (warp - 2) * (32 * G1_STG_LD);
-        const float inv_w = 1.f / scal[1];
+        const float inv_w = out_scale / scal[1];
         int64_t astep = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const int64_t m0 = t * TILE + quad * 32;
@@ -388,29 +393,30 @@ in_proj_gemm(const uint8_t* __restrict__ ximg, const float* __restrict__ row_sca
                 tc_fence_after();
                 float ps = 0.f, pd = 0.f;
 #pragma unroll 1
-                for (int ch = 0; ch < P1_BN / 32; ++ch) {
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int ch = 2 * half + cc;
+                    const int col0 = nt * P1_BN + ch * 32;
+                    if (col0 >= n_valid) break;
                     uint32_t v[32];
                     tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(buf * P1_BN + ch * 32), v);
-                    const int col0 = nt * P1_BN + ch * 32;
 #pragma unroll
                     for (int c = 0; c < 32; c += 4) {
-                        const float4 as4 = __ldg(reinterpret_cast<const float4*>(att_src + col0 + c));
-                        const float4 ad4 = __ldg(reinterpret_cast<const float4*>(att_dst + col0 + c));
                         const float f0 = __uint_as_float(v[c]) * inv, f1 = __uint_as_float(v[c + 1]) * inv;
                         const float f2 = __uint_as_float(v[c + 2]) * inv, f3 = __uint_as_float(v[c + 3]) * inv;
                         v[c] = __float_as_uint(f0); v[c + 1] = __float_as_uint(f1); v[c + 2] = __float_as_uint(f2); v[c + 3] = __float_as_uint(f3);
-                        ps = fmaf(f0, as4.x, ps); pd = fmaf(f0, ad4.x, pd);
-                        ps = fmaf(f1, as4.y, ps); pd = fmaf(f1, ad4.y, pd);
-                        ps = fmaf(f2, as4.z, ps); pd = fmaf(f2, ad4.z, pd);
-                        ps = fmaf(f3, as4.w, ps); pd = fmaf(f3, ad4.w, pd);
-                    }
-                    if (ch & 1) {                                   // two 32-column chunks per 64-wide head
-                        if (row < n) {
-                            const int hh = col0 / 64;
-                            a_src[row * H + hh] = ps;
-                            a_dst[row * H + hh] = pd;
+                        if (LOGITS) {
+                            const float4 as4 = __ldg(reinterpret_cast<const float4*>(att_src + col0 + c));
+                            const float4 ad4 = __ldg(reinterpret_cast<const float4*>(att_dst + col0 + c));
+                            ps = fmaf(f0, as4.x, ps); pd = fmaf(f0, ad4.x, pd);
+                            ps = fmaf(f1, as4.y, ps); pd = fmaf(f1, ad4.y, pd);
+                            ps = fmaf(f2, as4.z, ps); pd = fmaf(f2, ad4.z, pd);
+                            ps = fmaf(f3, as4.w, ps); pd = fmaf(f3, ad4.w, pd);
                         }
-                        ps = pd = 0.f;
+                    }
+                    if (LOGITS && cc == 1 && row < n) {             // this warp's two chunks are one 64-wide head
+                        const int hh = col0 / 64;
+                        a_src[row * H + hh] = ps;
+                        a_dst[row * H + hh] = pd;
                     }
                     __syncwarp();
 #pragma unroll
@@ -423,7 +429,7 @@ in_proj_gemm(const uint8_t* __restrict__ ximg, const float* __restrict__ row_sca
                         const int r = 4 * i + (lane >> 3), cq = (lane & 7) * 4;
                         const int64_t gm = m0 + r;
                         if (gm < n)
-                            *reinterpret_cast<float4*>(xw + gm * (H * C) + col0 + cq) = *reinterpret_cast<const float4*>(stg + r * G1_STG_LD + cq);
+                            *reinterpret_cast<float4*>(xw + gm * ld_out + col0 + cq) = *reinterpret_cast<const float4*>(stg + r * G1_STG_LD + cq);
                     }
                 }
                 tc_fence_before();
@@ -501,6 +507,41 @@ __global__ void in_wproj_image_kernel(const float* __restrict__ W, int K, int NK
         *reinterpret_cast<__half*>(dst + P1_BN * 128 + off) = lo;
     }
 }
+
+// W image of Gd = dO W_r^T: n-tile nt = features [128 nt, 128 nt + 128), rows = feature f = h*KP + k, 64 columns = c;
+// element = W[(h*C + c)*K + k] * sw  (fp16 hi | lo, K-major in c)
+__global__ void in_wgd_image_kernel(const float* __restrict__ W, int K, int KP, int F, const float* __restrict__ scal,
+                                    uint8_t* __restrict__ img)
+{
+    const int nt = blockIdx.x;
+    const float sw = scal[1];
+    uint8_t* dst = img + size_t(nt) * P1_B;
+    for (int idx = threadIdx.x; idx < P1_BN * 64; idx += blockDim.x) {
+        const int r = idx >> 6, c = idx & 63, f = nt * P1_BN + r;
+        float v = 0.f;
+        if (f < F) {
+            const int h = f / KP, k = f - h * KP;
+            if (k < K) v = W[int64_t(h * C + c) * K + k] * sw;
+        }
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        const uint32_t off = plane_off(r, c);
+        *reinterpret_cast<__half*>(dst + off) = hi;
+        *reinterpret_cast<__half*>(dst + P1_BN * 128 + off) = lo;
+    }
+}
+}  // namespace in
+int in_build_gd_image(const float* W, int K, void* prep, cudaStream_t st)
+{
+    const in::Dims d(K);
+    char* p = reinterpret_cast<char*>(prep);
+    in::in_wgd_image_kernel<<<(d.F + 127) / 128, 256, 0, st>>>(W, d.K, d.KP, d.F, reinterpret_cast<const float*>(p),
+                                                              reinterpret_cast<uint8_t*>(p + in::prep_off_wgd(d)));
+    g_launches += 1;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+namespace in {
 
 // ======================================================================================================================
 // dWr partials:  P[slab][f][c] = sum_{i in slab} Z[i,f] * dO[i,c]   (both operands MN-major, reduction over nodes)
@@ -769,14 +810,41 @@ int gnnfd_in_out(const void* zimg, int64_t n, int64_t K, const void* prep, const
 }
 
 /* gd [n, F] = d_out [n, C] @ W_r^T / H  (F = gnnfd_in_sizes' gd_ld): the per-destination vectors whose dot product with
- * x[j] is d_alpha.  Row-range agnostic: call it on a block of rows to bound the size of gd. */
-int gnnfd_in_bwd_gd(const float* d_out, int64_t n, int64_t K, const void* prep, float* gd, gnnfd_stream_t stream)
+ * x[j] is d_alpha.  Row-range agnostic: call it on a block of rows to bound the size of gd.  d_out is first split into its
+ * fp16-pair image (per-row scale) so that the GEMM is fed by the copy engine; ws: gnnfd_in_bwd_gd_workspace_bytes(n). */
+int gnnfd_in_bwd_gd_workspace_bytes(int64_t n, size_t* bytes)
+{
+    GNNFD_REQUIRE(bytes && n >= 0, GNNFD_ERR_ARG, "in_bwd_gd_workspace_bytes: bad argument");
+    *bytes = size_t((n + TILE - 1) / TILE) * KBLOCK + carve_bytes(size_t(n > 0 ? n : 1), 4) + 2048;
+    return GNNFD_OK;
+}
+int gnnfd_in_bwd_gd(const float* d_out, int64_t n, int64_t K, const void* prep, float* gd, void* ws, size_t ws_bytes,
+                    gnnfd_stream_t stream)
 {
     GNNFD_REQUIRE(K >= 1 && K <= MAX_K && n >= 0, GNNFD_ERR_ARG, "in_bwd_gd: bad shape");
     if (n == 0) return GNNFD_OK;
-    GNNFD_REQUIRE(d_out && prep && gd, GNNFD_ERR_ARG, "in_bwd_gd: NULL tensor");
+    size_t need = 0;
+    gnnfd_in_bwd_gd_workspace_bytes(n, &need);
+    GNNFD_REQUIRE(d_out && prep && gd && ws && ws_bytes >= need && (reinterpret_cast<uintptr_t>(ws) & 1023) == 0, GNNFD_ERR_WORKSPACE,
+                  "in_bwd_gd: NULL tensor, or workspace too small / not 1024-byte aligned");
     GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(gd) & 15) == 0, GNNFD_ERR_ARG, "in_bwd_gd: gd must be 16-byte aligned");
-    return in_gd_gemm(d_out, n, (int)K, prep, gd, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Dims d((int)K);
+    const int64_t n_tiles = (n + TILE - 1) / TILE;
+    uint8_t* dimg = reinterpret_cast<uint8_t*>(ws);
+    float* row_scale = reinterpret_cast<float*>(dimg + size_t(n_tiles) * KBLOCK);
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > int64_t(sm_count()) * 16) blocks = int64_t(sm_count()) * 16;
+    in_ximg_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_out, C, n, C, 1, dimg, row_scale);
+    const char* p = reinterpret_cast<const char*>(prep);
+    const unsigned grid = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());
+    GNNFD_CUDA(cudaFuncSetAttribute(in_proj_gemm<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1_SMEM));
+    in_proj_gemm<false><<<grid, P1_THREADS, P1_SMEM, st>>>(dimg, row_scale, reinterpret_cast<const uint8_t*>(p + prep_off_wgd(d)),
+                                                           reinterpret_cast<const float*>(p), n, 1, (d.F + 127) / 128, d.F, d.F,
+                                                           1.f / float(H), nullptr, nullptr, gd, nullptr, nullptr);
+    g_launches += 2;
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
 }
 
 /* da_src [n_src, H] = per-source sums of dz (source-major order, as gnnfd_in_bwd_edges writes it); needs the CSC twin. */
@@ -858,7 +926,7 @@ int gnnfd_project_image_bytes(int64_t N, int64_t K, size_t* ximg_bytes, size_t* 
     GNNFD_REQUIRE(K >= 1 && K <= MAX_K && N >= 0, GNNFD_ERR_ARG, "project_image_bytes: K must be in [1,%d]", MAX_K);
     const int nkbx = int((K + 63) / 64);
     if (ximg_bytes) *ximg_bytes = size_t((N + TILE - 1) / TILE) * nkbx * KBLOCK + 1024;
-    if (ws_bytes) *ws_bytes = size_t(P1_NT) * nkbx * P1_B + 2048;
+    if (ws_bytes) *ws_bytes = size_t(P1_NT_PROJ) * nkbx * P1_B + 2048;
     return GNNFD_OK;
 }
 int gnnfd_project_image_build(const float* x, int64_t ldx, int64_t N, int64_t K, void* ximg, float* row_scale, gnnfd_stream_t stream)
@@ -890,12 +958,12 @@ int gnnfd_project_fwd_image(const void* ximg, const float* row_scale, int64_t N,
     const int nkbx = int((K + 63) / 64);
     float* scal = reinterpret_cast<float*>(ws);
     uint8_t* wimg = reinterpret_cast<uint8_t*>(ws) + 1024;
-    in_wproj_image_kernel<<<P1_NT * nkbx, 512, 0, st>>>(W, (int)K, nkbx, scal, wimg);
+    in_wproj_image_kernel<<<P1_NT_PROJ * nkbx, 512, 0, st>>>(W, (int)K, nkbx, scal, wimg);
     const int64_t n_tiles = (N + TILE - 1) / TILE;
     const unsigned grid = (unsigned)(n_tiles < sm_count() ? n_tiles : sm_count());
-    GNNFD_CUDA(cudaFuncSetAttribute(in_proj_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1_SMEM));
-    in_proj_gemm<<<grid, P1_THREADS, P1_SMEM, st>>>(reinterpret_cast<const uint8_t*>(ximg), row_scale, wimg, scal, N, nkbx, att_src, att_dst,
-                                                    xw, a_src, a_dst);
+    GNNFD_CUDA(cudaFuncSetAttribute(in_proj_gemm<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P1_SMEM));
+    in_proj_gemm<true><<<grid, P1_THREADS, P1_SMEM, st>>>(reinterpret_cast<const uint8_t*>(ximg), row_scale, wimg, scal, N, nkbx, P1_NT_PROJ,
+                                                          H * C, H * C, 1.f, att_src, att_dst, xw, a_src, a_dst);
     g_launches += 2;
     GNNFD_LAUNCH_CHECK();
     return GNNFD_OK;

@@ -20,7 +20,6 @@
 //     row so the 64-wide logit dot products need no shuffles; the tile is staged through shared memory
 //     and written with coalesced 128-bit stores.
 #include "common.cuh"
-#include "in_common.cuh"
 
 #include <atomic>
 #include <cstdlib>
@@ -697,60 +696,6 @@ int project_bwd_dx_tc(const float* dxw, const float* W, int64_t N, int64_t K, in
     tc::gemm_tc<BN, 0, false><<<grid, tc::THREADS, smem, st>>>(dxw, D, N, D, img, n_kb, dx, nullptr, lddx, (int)K, nullptr,
                                                               nullptr, nullptr, nullptr, 0);
     g_launches += 2;
-    GNNFD_LAUNCH_CHECK();
-    return GNNFD_OK;
-}
-
-// ---- input-space path (in_common.cuh): Gd[n, F] = dO[n, C] @ W_r^T / H ----------------------------------------------
-// B image rows = feature f = h*KP + k (F rows, tiles of 256), reduction index = c: element = W[(h*C + c)*K + k] / H
-__global__ void build_gd_images(const float* __restrict__ W, int K, int KP, int F, int Hh, int Cc, int n_kb, float* __restrict__ img)
-{
-    const int tile = blockIdx.z, kb = blockIdx.y;
-    const size_t tile_elems = size_t(256) * tc::BK;
-    float* hi = img + ((size_t(tile) * n_kb + kb) * 2 + 0) * tile_elems;
-    float* lo = img + ((size_t(tile) * n_kb + kb) * 2 + 1) * tile_elems;
-    const float invH = 1.f / float(Hh);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 256 * tc::BK; idx += gridDim.x * blockDim.x) {
-        const int r = idx / tc::BK, kk = idx % tc::BK;
-        const int f = tile * 256 + r, c = kb * tc::BK + kk;
-        float v = 0.f;
-        if (f < F && c < Cc) {
-            const int h = f / KP, k = f - h * KP;
-            if (k < K) v = W[int64_t(h * Cc + c) * K + k] * invH;
-        }
-        float hh, ll;
-        tc::split_tf32(v, hh, ll);
-        const uint32_t off = tc::kmajor_off(r, kk) >> 2;
-        hi[off] = hh;
-        lo[off] = ll;
-    }
-}
-
-int in_build_gd_image(const float* W, int K, void* prep, cudaStream_t st)
-{
-    const in::Dims d(K);
-    float* img = reinterpret_cast<float*>(reinterpret_cast<char*>(prep) + in::prep_off_wgd(d));
-    const int n_kb = tc::kblocks(in::C), n_tiles = (d.F + 255) / 256;
-    build_gd_images<<<dim3(8, n_kb, n_tiles), 256, 0, st>>>(W, d.K, d.KP, d.F, in::H, in::C, n_kb, img);
-    g_launches += 1;
-    GNNFD_LAUNCH_CHECK();
-    return GNNFD_OK;
-}
-
-// gd [n, F] (leading dimension F) for n rows of d_out [n, C]
-int in_gd_gemm(const float* d_out, int64_t n, int K, const void* prep, float* gd, cudaStream_t st)
-{
-    if (n == 0) return GNNFD_OK;
-    GNNFD_REQUIRE(tc_device_ok(), GNNFD_ERR_UNSUPPORTED, "in_gd_gemm: needs an sm_100 device");
-    const in::Dims d(K);
-    const float* img = reinterpret_cast<const float*>(reinterpret_cast<const char*>(prep) + in::prep_off_wgd(d));
-    const int n_kb = tc::kblocks(in::C), n_tiles = (d.F + 255) / 256;
-    const int64_t tiles = int64_t(n_tiles) * ((n + tc::BM - 1) / tc::BM);
-    const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-    GNNFD_CUDA(cudaFuncSetAttribute(tc::gemm_tc_ws<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::WS_SMEM));
-    tc::gemm_tc_ws<2, false><<<grid, tc::WS_THREADS, tc::WS_SMEM, st>>>(d_out, in::C, n, in::C, img, n_kb, n_tiles, gd, nullptr,
-                                                                      d.F, d.F, nullptr, nullptr, nullptr, nullptr, 0);
-    g_launches += 1;
     GNNFD_LAUNCH_CHECK();
     return GNNFD_OK;
 }

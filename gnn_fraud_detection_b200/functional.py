@@ -330,10 +330,15 @@ def in_bwd_edges(g: GraphCSR, x, a_src, a_dst, rowmax, rowsum, d_out, prep, nega
     if n_blocks is None:
         n_blocks = max(1, -(-g.n_dst * F * 4 // IN_GD_BLOCK_BYTES))
     blocks = g.item_blocks(n_blocks)
-    gd = torch.empty(max(hi - lo for _, _, lo, hi in blocks), F, dtype=torch.float32, device=dev)
+    max_rows = max(hi - lo for _, _, lo, hi in blocks)
+    gd = torch.empty(max_rows, F, dtype=torch.float32, device=dev)
+    gb = C.c_size_t()
+    _abi.check(L.gnnfd_in_bwd_gd_workspace_bytes(max_rows, C.byref(gb)))
+    gws = _aligned_u8(gb.value, dev)
     for bi, (i_lo, i_hi, r_lo, r_hi) in enumerate(blocks):
         if r_hi > r_lo:
-            _abi.check(L.gnnfd_in_bwd_gd(d_out[r_lo:r_hi].data_ptr(), r_hi - r_lo, K, prep.data_ptr(), gd.data_ptr(), _stream()))
+            _abi.check(L.gnnfd_in_bwd_gd(d_out[r_lo:r_hi].data_ptr(), r_hi - r_lo, K, prep.data_ptr(), gd.data_ptr(),
+                                         gws.data_ptr(), gws.numel(), _stream()))
         phase = 1 | (2 if bi == len(blocks) - 1 else 0)
         _abi.check(L.gnnfd_in_bwd_edges(g.ref(), x.data_ptr(), x.stride(0), K, a_src.data_ptr(), a_dst.data_ptr(),
                                         rowmax.data_ptr(), rowsum.data_ptr(), gd.data_ptr(), r_lo, i_lo, i_hi, r_lo, r_hi,

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 12
+#define GNNFD_ABI_VERSION 13
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -278,8 +278,11 @@ int gnnfd_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K,
 int gnnfd_in_out(const void* zimg, int64_t n, int64_t K, const void* prep, const float* bias, int act,
                  const float* post_scale, const float* post_shift, const float* residual, float* out,
                  gnnfd_stream_t stream);
-/* gd [n, gd_ld] = d_out [n,C] W_r^T / H; row-range agnostic (call per block of rows to bound gd). */
-int gnnfd_in_bwd_gd(const float* d_out, int64_t n, int64_t K, const void* prep, float* gd, gnnfd_stream_t stream);
+/* gd [n, gd_ld] = d_out [n,C] W_r^T / H; row-range agnostic (call per block of rows to bound gd).  ws (1024-byte aligned,
+ * gnnfd_in_bwd_gd_workspace_bytes) holds the fp16-pair image of the d_out rows that feeds the tensor cores. */
+int gnnfd_in_bwd_gd_workspace_bytes(int64_t n, size_t* bytes);
+int gnnfd_in_bwd_gd(const float* d_out, int64_t n, int64_t K, const void* prep, float* gd, void* ws, size_t ws_bytes,
+                    gnnfd_stream_t stream);
 int gnnfd_in_bwd_edges_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes);
 /* dz [E',H] (source-major order, row csr2csc[e]) and da_dst [n_dst,H] for the destination rows covered by the work items
  * [item_lo, item_hi) = rows [row_lo, row_hi) (0, n_items, 0, n_dst for everything); gd holds the Gd rows from gd_row0 on.

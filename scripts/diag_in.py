@@ -89,7 +89,12 @@ def case(name, N, K, ei, seed=0, n_blocks=None, keep=None, p=0.0):
     err("out", out, out_ref)
     dog = d_out.to(dev)
     gd = torch.empty(N, F, device=dev)
-    _abi.check(_abi.lib().gnnfd_in_bwd_gd(dog.data_ptr(), N, K, prep.data_ptr(), gd.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    import ctypes
+    gb = ctypes.c_size_t()
+    _abi.check(_abi.lib().gnnfd_in_bwd_gd_workspace_bytes(N, ctypes.byref(gb)))
+    gws = Fn._aligned_u8(gb.value, dev)
+    _abi.check(_abi.lib().gnnfd_in_bwd_gd(dog.data_ptr(), N, K, prep.data_ptr(), gd.data_ptr(), gws.data_ptr(), gws.numel(),
+                                          torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     KP = F // H
     Gd_ref = torch.einsum("nc,hck->nhk", d_out.double() / H, Wd.view(H, C, K))
