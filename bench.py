@@ -531,6 +531,11 @@ def run_gpu_arm(args):
                            "allgather": f"dst-range x{world}: NCCL all-gather of projected features, reduce-scatter of dxw",
                        }[args.mgpu],
                        "formulation": "input-space" if input_space else "projected-feature",
+                       "exchange": (None if part is None else {
+                           "multicast": "fused into the kernels: multimem.st / multimem.ld_reduce through the NVSwitch "
+                                        "(symmetric memory), no collective call on the data path",
+                           "peer": "fused into the kernels: NVLink stores / loads on peer memory (symmetric memory)",
+                       }.get(getattr(part, "exchange", "nccl"), "NCCL all-gather / reduce-scatter")),
                        "csr_build_ms": csr_ms, "x_image_build_ms": (ximg_ms if ximg is not None else None), "setup_s": gen_s,
                        "gemm_algo": args.algo, "note": note},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,

@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_INPUT = 0, 1, 2, 3
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -30,6 +30,14 @@ class HubPlan(C.Structure):
 
 class ItemPlan(C.Structure):
     _fields_ = [("n_items", C.c_int32), ("target", C.c_int32), ("item_start", C.c_void_p)]
+
+
+MAX_PEERS = 16
+
+
+class Peers(C.Structure):
+    """gnnfd_peers_t: the addresses of one symmetric buffer on every rank (+ its multicast mapping)."""
+    _fields_ = [("n_peers", C.c_int32), ("rank", C.c_int32), ("ptr", C.c_void_p * MAX_PEERS), ("multicast", C.c_void_p)]
 
 
 class Graph(C.Structure):
@@ -83,6 +91,8 @@ SIGNATURES = {
     "gnnfd_in_sizes": (_i, [_i64, _i64, _szp, _szp, _i64p, _i64p]),
     "gnnfd_in_pad_x": (_i, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "gnnfd_in_logits": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "gnnfd_in_logits_bcast": (_i, [_vp, _i64, _i64, _i64, _vp, _vp, _vp, C.POINTER(Peers), _i64, _i, _vp, _vp, _vp, _vp]),
+    "gnnfd_peer_reduce": (_i, [C.POINTER(Peers), _i64, _i64, _i, _i, _vp, _vp]),
     "gnnfd_in_prepare": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "gnnfd_in_fwd_workspace_bytes": (_i, [_gp, _szp]),
     "gnnfd_in_fwd": (_i, [_gp, _vp, _i64, _i64, _vp, _vp, _f, _vp, _f, _u64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

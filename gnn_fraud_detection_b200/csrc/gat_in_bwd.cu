@@ -165,8 +165,8 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
                     for (int i = 0; i < RG::NI; ++i)
                         if (RG::valid(i, q, n4)) {
                             const float4 v = lds128(a + uint32_t(i) * 64u);
-                            d0 = fmaf(g[i].x, v.x, d0); d1 = fmaf(g[i].y, v.y, d1);
-                            d2 = fmaf(g[i].z, v.z, d2); d3 = fmaf(g[i].w, v.w, d3);
+                            ffma2_vec(d0, d1, g[i].x, g[i].y, v.x, v.y);
+                            ffma2_vec(d2, d3, g[i].z, g[i].w, v.z, v.w);
                         }
                     float d = (d0 + d1) + (d2 + d3);
                     d += __shfl_xor_sync(FULL, d, 1);

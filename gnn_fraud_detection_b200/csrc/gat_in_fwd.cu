@@ -47,10 +47,23 @@ __global__ void in_u_kernel(const float* __restrict__ W, const float* __restrict
 // shared memory (ONE bulk copy per tile, double-buffered); lane = (head h, quarter q) as in the edge kernels: 44 + 44
 // u values in registers, per row 11 shared loads, 88 FMAs and two 2-step quad reductions.  Also max |x|.
 constexpr int LG_ROWS = 64, LG_WARPS = 8;
+// where the a_src rows go: mode 0 = a_src (local); 1 = row (row_off + r) of the same buffer on every peer (one 16-byte
+// store per peer over NVLink); 2 = one multimem.st to the multicast mapping (the NVSwitch replicates it to every rank)
+struct LogitPeers {
+    int mode, n;
+    int64_t row_off;
+    float* ptr[GNNFD_MAX_PEERS];
+    float* mc;
+};
+__device__ __forceinline__ void multimem_st_v4(float* p, float4 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
 template <int N4>
 __global__ void __launch_bounds__(LG_WARPS * 32, 2)
 in_logits_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int KP, const float* __restrict__ u,
-                 float* __restrict__ a_src, float* __restrict__ a_dst, unsigned* __restrict__ xmax_bits)
+                 float* __restrict__ a_src, float* __restrict__ a_dst, unsigned* __restrict__ xmax_bits, LogitPeers peers)
 {
     using RG = RowGeo<N4>;
     extern __shared__ __align__(128) uint8_t lsm[];
@@ -108,9 +121,23 @@ in_logits_kernel(const float* __restrict__ x, int64_t ldx, int64_t N, int KP, co
                 }
             ds += __shfl_xor_sync(FULL, ds, 1); dd += __shfl_xor_sync(FULL, dd, 1);
             ds += __shfl_xor_sync(FULL, ds, 2); dd += __shfl_xor_sync(FULL, dd, 2);
-            if (q == 0) {
-                a_src[(r0 + r) * H + h] = ds;
-                a_dst[(r0 + r) * H + h] = dd;
+            if (q == 0) a_dst[(r0 + r) * H + h] = dd;
+            if (peers.mode == 0) {
+                if (q == 0) a_src[(r0 + r) * H + h] = ds;
+            } else {
+                // lanes 0 and 16 collect heads 0-3 / 4-7 (every lane of a quad holds its head's sum) and store 16 bytes
+                const int b = lane & 16;
+                float4 v;
+                v.x = __shfl_sync(FULL, ds, b);
+                v.y = __shfl_sync(FULL, ds, b + 4);
+                v.z = __shfl_sync(FULL, ds, b + 8);
+                v.w = __shfl_sync(FULL, ds, b + 12);
+                if ((lane & 15) == 0) {
+                    const int64_t off = (peers.row_off + r0 + r) * H + (b >> 2);
+                    if (peers.mode == 2) multimem_st_v4(peers.mc + off, v);
+                    else
+                        for (int g = 0; g < peers.n; ++g) *reinterpret_cast<float4*>(peers.ptr[g] + off) = v;
+                }
             }
         }
         __syncthreads();                                // every warp is done with buffer b
@@ -329,8 +356,8 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
                     for (int i = 0; i < RG::NI; ++i)
                         if (RG::valid(i, q, n4)) {
                             const float4 v = lds128(a + uint32_t(i) * 64u);
-                            acc[i].x = fmaf(w, v.x, acc[i].x); acc[i].y = fmaf(w, v.y, acc[i].y);
-                            acc[i].z = fmaf(w, v.z, acc[i].z); acc[i].w = fmaf(w, v.w, acc[i].w);
+                            ffma2_bcast(acc[i].x, acc[i].y, w, v.x, v.y);
+                            ffma2_bcast(acc[i].z, acc[i].w, w, v.z, v.w);
                         }
                     if (PACK && ((lastmask >> t) & 1u)) {     // last edge of a packed row (weights already normalised)
                         sink.finish_norm(c0.row + __popc(lastmask & ((1u << t) - 1u)), acc, lane);
@@ -357,9 +384,12 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
 }
 
 constexpr int FWD_EXTRA = 256;   // r_all
+#ifndef GNNFD_IN_FWD_CTAS
+#define GNNFD_IN_FWD_CTAS 4
+#endif
 
 template <int N4, bool DROPOUT, bool PACK>
-__global__ void __launch_bounds__(IN_THREADS, 4)
+__global__ void __launch_bounds__(IN_THREADS, GNNFD_IN_FWD_CTAS)
 gat_in_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
                  const float* __restrict__ x, int64_t ldx, const float* __restrict__ a_src,
                  const float* __restrict__ a_dst, gnnfd_item_plan_t items, int hub_threshold, float slope,
@@ -558,13 +588,10 @@ int gnnfd_in_pad_x(const float* x, int64_t ldx, int64_t N, int64_t K, float* x16
 
 /* a_src / a_dst [N,H] for rows [0,N) of x, and xmax[0] = max(xmax[0], max |x|) (caller zeroes xmax before the first call;
  * across GPUs the per-rank maxima are max-reduced before gnnfd_in_prepare).  x: padded rows (gnnfd_in_pad_x layout). */
-int gnnfd_in_logits(const float* x, int64_t ldx, int64_t N, int64_t K, const float* W, const float* att_src,
-                    const float* att_dst, float* a_src, float* a_dst, float* xmax, void* prep, gnnfd_stream_t stream)
+static int in_logits_launch(const float* x, int64_t ldx, int64_t N, int64_t K, const float* W, const float* att_src,
+                            const float* att_dst, float* a_src, float* a_dst, float* xmax, void* prep, const LogitPeers& peers,
+                            cudaStream_t st)
 {
-    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && N >= 0, GNNFD_ERR_ARG, "in_logits: bad shape (K <= %d)", MAX_K);
-    GNNFD_REQUIRE(W && att_src && att_dst && xmax && prep, GNNFD_ERR_ARG, "in_logits: NULL argument");
-    GNNFD_REQUIRE(N == 0 || (x && a_src && a_dst), GNNFD_ERR_ARG, "in_logits: NULL tensor");
-    cudaStream_t st = (cudaStream_t)stream;
     const Dims d((int)K);
     GNNFD_REQUIRE(N == 0 || in_x_ok(x, ldx, d.KP), GNNFD_ERR_ARG,
                   "in_logits: x rows must be 16-byte aligned and zero-padded to %d floats (gnnfd_in_pad_x)", d.KP);
@@ -581,20 +608,53 @@ int gnnfd_in_logits(const float* x, int64_t ldx, int64_t N, int64_t K, const flo
         if (d.KP == 168) {
             rc = in_set_smem(in_logits_kernel<42>, smem);
             if (rc) return rc;
-            in_logits_kernel<42><<<blocks, LG_WARPS * 32, smem, st>>>(x, ldx, N, d.KP, u, a_src, a_dst, xb);
+            in_logits_kernel<42><<<blocks, LG_WARPS * 32, smem, st>>>(x, ldx, N, d.KP, u, a_src, a_dst, xb, peers);
         } else if (d.KP == 64) {
             rc = in_set_smem(in_logits_kernel<16>, smem);
             if (rc) return rc;
-            in_logits_kernel<16><<<blocks, LG_WARPS * 32, smem, st>>>(x, ldx, N, d.KP, u, a_src, a_dst, xb);
+            in_logits_kernel<16><<<blocks, LG_WARPS * 32, smem, st>>>(x, ldx, N, d.KP, u, a_src, a_dst, xb, peers);
         } else {
             rc = in_set_smem(in_logits_kernel<0>, smem);
             if (rc) return rc;
-            in_logits_kernel<0><<<blocks, LG_WARPS * 32, smem, st>>>(x, ldx, N, d.KP, u, a_src, a_dst, xb);
+            in_logits_kernel<0><<<blocks, LG_WARPS * 32, smem, st>>>(x, ldx, N, d.KP, u, a_src, a_dst, xb, peers);
         }
         g_launches += 1;
     }
     GNNFD_LAUNCH_CHECK();
     return GNNFD_OK;
+}
+
+int gnnfd_in_logits(const float* x, int64_t ldx, int64_t N, int64_t K, const float* W, const float* att_src,
+                    const float* att_dst, float* a_src, float* a_dst, float* xmax, void* prep, gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && N >= 0, GNNFD_ERR_ARG, "in_logits: bad shape (K <= %d)", MAX_K);
+    GNNFD_REQUIRE(W && att_src && att_dst && xmax && prep, GNNFD_ERR_ARG, "in_logits: NULL argument");
+    GNNFD_REQUIRE(N == 0 || (x && a_src && a_dst), GNNFD_ERR_ARG, "in_logits: NULL tensor");
+    LogitPeers peers{};
+    return in_logits_launch(x, ldx, N, K, W, att_src, att_dst, a_src, a_dst, xmax, prep, peers, (cudaStream_t)stream);
+}
+
+int gnnfd_in_logits_bcast(const float* x, int64_t ldx, int64_t N, int64_t K, const float* W, const float* att_src,
+                          const float* att_dst, const gnnfd_peers_t* a_src_all, int64_t row_offset, int use_multicast,
+                          float* a_dst, float* xmax, void* prep, gnnfd_stream_t stream)
+{
+    GNNFD_REQUIRE(K >= 1 && K <= MAX_K && N >= 0 && row_offset >= 0, GNNFD_ERR_ARG, "in_logits_bcast: bad shape (K <= %d)", MAX_K);
+    GNNFD_REQUIRE(W && att_src && att_dst && xmax && prep && a_src_all, GNNFD_ERR_ARG, "in_logits_bcast: NULL argument");
+    GNNFD_REQUIRE(N == 0 || (x && a_dst), GNNFD_ERR_ARG, "in_logits_bcast: NULL tensor");
+    GNNFD_REQUIRE(a_src_all->n_peers >= 1 && a_src_all->n_peers <= GNNFD_MAX_PEERS, GNNFD_ERR_ARG, "in_logits_bcast: 1..%d peers",
+                  GNNFD_MAX_PEERS);
+    GNNFD_REQUIRE(!use_multicast || a_src_all->multicast, GNNFD_ERR_ARG, "in_logits_bcast: no multicast mapping given");
+    LogitPeers peers{};
+    peers.mode = use_multicast ? 2 : 1;
+    peers.n = a_src_all->n_peers;
+    peers.row_off = row_offset;
+    peers.mc = reinterpret_cast<float*>(a_src_all->multicast);
+    for (int g = 0; g < peers.n; ++g) {
+        GNNFD_REQUIRE(a_src_all->ptr[g] && (reinterpret_cast<uintptr_t>(a_src_all->ptr[g]) & 15) == 0, GNNFD_ERR_ARG,
+                      "in_logits_bcast: peer buffer %d NULL or not 16-byte aligned", g);
+        peers.ptr[g] = reinterpret_cast<float*>(a_src_all->ptr[g]);
+    }
+    return in_logits_launch(x, ldx, N, K, W, att_src, att_dst, nullptr, a_dst, xmax, prep, peers, (cudaStream_t)stream);
 }
 
 /* scales + W images of the two dense stages into prep (gnnfd_in_sizes gives its size). */

@@ -155,6 +155,26 @@ __device__ __forceinline__ float4 lds128(uint32_t addr)
     return v;
 }
 
+// packed fp32x2 FMA (sm_100 FFMA2): two FMAs per issue slot, each component rounded exactly like fmaf
+__device__ __forceinline__ void ffma2_bcast(float& a0, float& a1, float w, float v0, float v1)     // a += w * v
+{
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(w));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(v0), "f"(v1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(a0), "f"(a1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(c));
+}
+__device__ __forceinline__ void ffma2_vec(float& a0, float& a1, float g0, float g1, float v0, float v1)   // a += g * v
+{
+    unsigned long long a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(g0), "f"(g1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(v0), "f"(v1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(a0), "f"(a1));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(c));
+}
+
 struct InRing {
     uint32_t ring_u32, full_u32, slot;   // shared-space addresses / bytes per slot
     uint8_t* extra;

@@ -283,6 +283,25 @@ def in_logits(x, W, att_src, att_dst, prep, xmax, n_rows=None):
     return a_src, a_dst
 
 
+def in_logits_bcast(x, W, att_src, att_dst, prep, xmax, peers, row_offset, use_multicast=False):
+    """``in_logits`` fused with the all-gather of ``a_src``: the rows go to ``row_offset ..`` of the symmetric buffer described
+    by ``peers`` (``_abi.Peers``) on EVERY rank; returns the local ``a_dst``."""
+    N, K = x.shape
+    a_dst = torch.empty(N, 8, dtype=torch.float32, device=x.device)
+    _abi.check(_abi.lib().gnnfd_in_logits_bcast(x.data_ptr(), x.stride(0), N, K, W.data_ptr(), att_src.data_ptr(),
+                                                att_dst.data_ptr(), C.byref(peers), int(row_offset), int(use_multicast),
+                                                a_dst.data_ptr(), xmax.data_ptr(), prep.data_ptr(), _stream()))
+    return a_dst
+
+
+def peer_reduce(peers, offset, n, out, op="sum", use_multicast=False):
+    """``out[:n]`` = sum / max over ranks of the symmetric buffer's elements ``offset .. offset+n`` (peer loads, or the
+    in-switch ``multimem.ld_reduce``)."""
+    _abi.check(_abi.lib().gnnfd_peer_reduce(C.byref(peers), int(offset), int(n), 0 if op == "sum" else 1, int(use_multicast),
+                                            out.data_ptr(), _stream()))
+    return out
+
+
 def in_prepare(W, K, xmax, prep):
     _abi.check(_abi.lib().gnnfd_in_prepare(W.data_ptr(), int(K), xmax.data_ptr(), prep.data_ptr(), _stream()))
 
@@ -347,8 +366,8 @@ def in_bwd_edges(g: GraphCSR, x, a_src, a_dst, rowmax, rowsum, d_out, prep, nega
     return dz, da_dst
 
 
-def in_dasrc(g: GraphCSR, dz):
-    da_src = torch.empty(g.n_src, 8, dtype=torch.float32, device=dz.device)
+def in_dasrc(g: GraphCSR, dz, out=None):
+    da_src = out if out is not None else torch.empty(g.n_src, 8, dtype=torch.float32, device=dz.device)
     _abi.check(_abi.lib().gnnfd_in_bwd_dasrc(g.ref(), dz.data_ptr(), da_src.data_ptr(), _stream()))
     return da_src
 

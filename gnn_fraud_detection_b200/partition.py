@@ -397,6 +397,46 @@ class ReplicatedInputPartition(DstRangePartition):
                             "all-to-all/all-gather/all-reduce, D2H of grads"}
 
 
+class PeerExchange:
+    """Symmetric (peer-accessible) buffers of the input-space exchange and the addresses the kernels need
+    (include/gnnfd_b200.h section 7).  Allocation, address exchange and the cross-GPU barrier come from torch symmetric
+    memory; the data itself is moved by the library's kernels (NVLink stores / loads, or NVSwitch multicast)."""
+
+    def __init__(self, n_pos, device, mode="auto", H=8):
+        import torch.distributed._symmetric_memory as symm
+        from . import _abi
+        grp = dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        if self.world > _abi.MAX_PEERS:
+            raise RuntimeError(f"peer exchange supports up to {_abi.MAX_PEERS} ranks")
+        self.a_src = symm.empty((n_pos, H), dtype=torch.float32, device=device)       # all-gathered source logits
+        self.da_part = symm.empty((n_pos, H), dtype=torch.float32, device=device)     # this rank's partial da_src
+        self.xmax = symm.empty((16,), dtype=torch.float32, device=device)
+        self.handles = [symm.rendezvous(t, grp) for t in (self.a_src, self.da_part, self.xmax)]
+        has_mc = all(int(getattr(h, "multicast_ptr", 0) or 0) != 0 for h in self.handles[:2])
+        if mode == "multicast" and not has_mc:
+            raise RuntimeError("GNNFD_EXCHANGE=multicast: the symmetric allocation has no multicast mapping on this box")
+        self.mode = "multicast" if (mode in ("auto", "multicast") and has_mc) else "peer"
+        self.a_src_peers, self.da_peers, self.xmax_peers = (self._peers(h) for h in self.handles)
+        self.da_part.zero_()
+        self.xmax.zero_()
+        self.barrier()
+
+    def _peers(self, h):
+        from . import _abi
+        p = _abi.Peers()
+        p.n_peers, p.rank = self.world, self.rank
+        for r, ptr in enumerate(h.buffer_ptrs):
+            p.ptr[r] = int(ptr)
+        p.multicast = int(getattr(h, "multicast_ptr", 0) or 0) or None
+        return p
+
+    def barrier(self):
+        """Cross-GPU barrier on the current stream (signal pads of the symmetric allocation): kernels enqueued before it on
+        every rank have completed -- their peer stores included -- before anything enqueued after it starts."""
+        self.handles[0].barrier()
+
+
 class InputSpacePartition(DstRangePartition):
     """Destination-range partition of the FIRST layer in the input-space formulation (csrc/in_common.cuh).
 
@@ -427,6 +467,18 @@ class InputSpacePartition(DstRangePartition):
         self.prep = Fn._aligned_u8(Fn.in_sizes(self.n_local, K)[0], self.device)
         self.xmax = torch.zeros(16, dtype=torch.float32, device=self.device)
         self.redundant_logits = os.environ.get("GNNFD_LOGITS_REDUNDANT", "0") == "1"
+        # exchange over peer memory (default when torch symmetric memory is available): "peer" = stores / loads per peer,
+        # "multicast" = multimem.st / multimem.ld_reduce through the NVSwitch, "nccl" = the plain collectives
+        mode = os.environ.get("GNNFD_EXCHANGE", "auto")
+        self.px = None
+        if self.world > 1 and mode != "nccl" and not self.redundant_logits:
+            try:
+                self.px = PeerExchange(self.n_pos, self.device, mode)
+            except Exception as ex:               # no symmetric memory on this box: NCCL collectives
+                if mode != "auto":
+                    raise
+                self.px_error = f"{type(ex).__name__}: {ex}"
+        self.exchange = self.px.mode if self.px is not None else ("nccl" if self.world > 1 else "none")
 
     def layer_fwd_bwd(self, x_full, W, a_s, a_d, bias, d_out, H, C, xw_dtype=None, algo=None, marks=None, graph=None):
         """``x_full``: the replicated input in padded position space ``[world*rows_padded, K]`` with 16-byte aligned,
@@ -438,16 +490,24 @@ class InputSpacePartition(DstRangePartition):
         lo = self.rank * P
         if getattr(self, "prep", None) is None:
             self.prepare_buffers(K)
-        prep, xmax = self.prep, self.xmax
+        prep, xmax, px = self.prep, self.xmax, self.px
         if marks: marks[0].record()
         # forward: logits of the own rows, gathered from every rank; softmax / aggregation / output GEMM are local
-        xmax.zero_()
         x_own = x_full[lo:lo + P]
-        if self.world > 1 and self.redundant_logits:
+        if px is not None:
+            # fused: the logits kernel stores its rows into a_src_full ON EVERY RANK (NVLink stores / one multicast store)
+            px.xmax.zero_()
+            a_dst_own = Fn.in_logits_bcast(x_own, W, a_s, a_d, prep, px.xmax, px.a_src_peers, lo, px.mode == "multicast")
+            px.barrier()
+            a_src_full = px.a_src
+            Fn.peer_reduce(px.xmax_peers, 0, 4, xmax, op="max")
+        elif self.world > 1 and self.redundant_logits:
             # every rank holds all of x: 32 B of logits per node can also be recomputed locally instead of gathered
+            xmax.zero_()
             a_src_full, a_dst_full = Fn.in_logits(x_full, W, a_s, a_d, prep, xmax)
             a_dst_own = a_dst_full[lo:lo + P]
         else:
+            xmax.zero_()
             a_src_own, a_dst_own = Fn.in_logits(x_own, W, a_s, a_d, prep, xmax)
             if self.world > 1:
                 a_src_full = torch.empty(self.n_pos, H, dtype=torch.float32, device=dev)
@@ -464,18 +524,25 @@ class InputSpacePartition(DstRangePartition):
         # backward: edge pass is local; the partial da_src over ALL source positions is reduce-scattered to the owners
         dz, da_dst = Fn.in_bwd_edges(g, x_full, a_src_full, a_dst_own, rowmax, rowsum, d_out, prep, 0.2)
         if marks: marks[4].record()
-        da_src_part = Fn.in_dasrc(g, dz)
-        if self.world > 1:
+        if px is not None:
+            # the partial stays in this rank's symmetric buffer; every owner pulls (or switch-reduces) its own row range
+            Fn.in_dasrc(g, dz, out=px.da_part)
+            px.barrier()
             da_src = torch.empty(P, H, dtype=torch.float32, device=dev)
-            dist.reduce_scatter_tensor(da_src, da_src_part)
+            Fn.peer_reduce(px.da_peers, lo * H, P * H, da_src, op="sum", use_multicast=px.mode == "multicast")
         else:
-            da_src = da_src_part
+            da_src_part = Fn.in_dasrc(g, dz)
+            if self.world > 1:
+                da_src = torch.empty(P, H, dtype=torch.float32, device=dev)
+                dist.reduce_scatter_tensor(da_src, da_src_part)
+            else:
+                da_src = da_src_part
         if marks: marks[5].record()
         dW, datt_s, datt_d, dbias = Fn.in_bwd_params(zimg, d_out, x_own[:n], W, a_s, a_d, da_src[:n], da_dst, prep)
         if self.world > 1:
             D = H * C
             flat = torch.cat([dW.reshape(-1), datt_s, datt_d, dbias])
-            dist.all_reduce(flat)
+            dist.all_reduce(flat)          # also the step-end rendezvous that keeps a fast rank out of the next step's buffers
             k = dW.numel()
             dW, datt_s, datt_d, dbias = flat[:k].view_as(dW), flat[k:k + D], flat[k + D:k + 2 * D], flat[k + 2 * D:]
         if marks: marks[6].record()

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 13
+#define GNNFD_ABI_VERSION 14
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -336,6 +336,31 @@ int gnnfd_gru_head_bwd(const float* x, const float* h_prev, const float* d_out, 
  * TP, FP, TN, FN at sigmoid >= 0.5 (src/train.py:146-149) -- no host synchronisation. */
 int gnnfd_bce_masked(const float* logits, const int64_t* y, int64_t N, float pos_weight, float upstream, float* loss,
                      float* d_logits, double* stats, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+
+/* ---- (7) multi-GPU exchange over peer memory (the reference itself is single-process) -------------------
+ * One process per GPU; every rank allocates the same buffer in peer-accessible ("symmetric") memory and passes the G device
+ * addresses (its own included, ptr[rank]) plus, where the allocation has one, the NVSwitch multicast address.  The kernels
+ * store / load straight through NVLink -- no staging buffer, no collective call; the caller separates a producing kernel
+ * from the consuming one with a cross-GPU barrier (any: a signal-pad barrier of the symmetric allocation, a 1-element
+ * all-reduce).  Host side: partition.PeerExchange (torch symmetric memory). */
+#define GNNFD_MAX_PEERS 16
+typedef struct gnnfd_peers {
+    int32_t n_peers;               /* G */
+    int32_t rank;                  /* this process */
+    void* ptr[GNNFD_MAX_PEERS];    /* the buffer's address on every rank, as mapped in THIS process */
+    void* multicast;               /* multicast mapping of the same buffer (NULL: none) */
+} gnnfd_peers_t;
+/* gnnfd_in_logits fused with the all-gather of a_src: the logit rows of the N own rows are stored into rows
+ * [row_offset, row_offset + N) of a_src_all [n_pos,H] ON EVERY RANK (use_multicast: one multimem.st per 16 bytes, replicated
+ * by the switch; else one store per peer).  a_dst, xmax stay local (pull-reduce xmax with gnnfd_peer_reduce). */
+int gnnfd_in_logits_bcast(const float* x, int64_t ldx, int64_t N, int64_t K, const float* W, const float* att_src,
+                          const float* att_dst, const gnnfd_peers_t* a_src_all, int64_t row_offset, int use_multicast,
+                          float* a_dst, float* xmax, void* prep, gnnfd_stream_t stream);
+/* out[i] = reduce over ranks of buf_r[offset + i], i in [0,n)  (op 0: sum, 1: max).  use_multicast (sum only, offset and n
+ * multiples of 4): multimem.ld_reduce -- the addition happens inside the NVSwitch; else peer loads summed in rank order
+ * (deterministic).  The reduce-scatter of the partial da_src [n_pos,H]: every rank reduces ITS OWN row range. */
+int gnnfd_peer_reduce(const gnnfd_peers_t* buf, int64_t offset, int64_t n, int op, int use_multicast, float* out,
+                      gnnfd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,32 @@ def _worker(rank, world, port, ret):
         errs += [float((o4 - out[lo:hi]).abs().max()), float((dW4 - dW).abs().max()), float((ds4 - datt_s).abs().max()),
                  float((dd4 - datt_d).abs().max()), float((db4 - dbias).abs().max())]
         rels["input-space dW vs 1 GPU projected-feature"] = float((dW4 - dW).norm() / dW.norm())
+        # the same layer with every exchange mechanism: NCCL collectives, per-peer NVLink stores / loads, NVSwitch multicast
+        modes = {part3.exchange: (o4, dW4, ds4, dd4)}
+        for mode in ("nccl", "peer", "multicast"):
+            if mode in modes:
+                continue
+            os.environ["GNNFD_EXCHANGE"] = mode
+            try:
+                pm = InputSpacePartition.build(ei, N, rank, world, dev)
+                om, (dWm, dsm, ddm, dbm) = pm.layer_fwd_bwd(x16[:, :K], W, a_s, a_d, bias, d_out[lo:hi].contiguous(), H, C)
+                assert pm.exchange == mode
+                modes[mode] = (om, dWm, dsm, ddm)
+            except RuntimeError as ex:
+                if mode != "multicast" or "multicast" not in str(ex):
+                    raise
+            finally:
+                os.environ.pop("GNNFD_EXCHANGE", None)
+        assert "nccl" in modes and "peer" in modes, list(modes)
+        for mode, (om, dWm, dsm, ddm) in modes.items():
+            errs += [float((om - out[lo:hi]).abs().max()), float((dWm - dW).abs().max()), float((dsm - datt_s).abs().max()),
+                     float((ddm - datt_d).abs().max())]
+            rels[f"input-space[{mode}] dW vs 1 GPU projected-feature"] = float((dWm - dW).norm() / dW.norm())
+        rels["exchange modes covered: " + ",".join(sorted(modes))] = 0.0
+        # a second step through the same buffers (stale data from step 1 must not leak into step 2)
+        o4b, (dW4b, _, _, _) = part3.layer_fwd_bwd(x16[:, :K], W * 0.5, a_s, a_d, bias, d_out[lo:hi].contiguous(), H, C)
+        o4c, (dW4c, _, _, _) = part3.layer_fwd_bwd(x16[:, :K], W, a_s, a_d, bias, d_out[lo:hi].contiguous(), H, C)
+        errs += [float((o4c - o4).abs().max()), float((dW4c - dW4).abs().max())]
         # ... and directly against the fp64 CPU oracle on a graph it can hold
         from oracle import pyg_gatconv as O
         N2, E2 = 20_000, 200_000
