@@ -323,11 +323,11 @@ def run_gpu_arm(args):
             a_src, a_dst = Fn.in_logits(x, W, a_s, a_d, in_prep, in_xmax)
             Fn.in_prepare(W, K, in_xmax, in_prep)
             if timed: marks[1].record()
-            zimg, rowmax, rowsum = Fn.in_fwd(g, x, a_src, a_dst, 0.2, in_prep)
+            zimg, att = Fn.in_fwd(g, x, a_src, a_dst, 0.2, in_prep)
             if timed: marks[2].record()
             out = Fn.in_out(zimg, N, K, in_prep, bias)
             if timed: marks[3].record()
-            dz, da_dst = Fn.in_bwd_edges(g, x, a_src, a_dst, rowmax, rowsum, d_out, in_prep, 0.2)
+            dz, da_dst = Fn.in_bwd_edges(g, x, att, d_out, in_prep, 0.2)
             if timed: marks[4].record()
             da_src = Fn.in_dasrc(g, dz)
             if timed: marks[5].record()

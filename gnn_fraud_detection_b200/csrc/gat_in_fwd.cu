@@ -10,7 +10,7 @@
 // ahead, rows delivered by the bulk-copy engine into a per-warp ring; packs of short rows; hub rows split into chunks
 // merged in chunk order (deterministic).
 #include "in_common.cuh"
-#include "gat_phase_fwd.cuh"
+#include "gat_stream.cuh"
 
 #ifndef GNNFD_IN_UNROLL_FWD
 #define GNNFD_IN_UNROLL_FWD 1     // the row epilogue (image write) sits inside the edge loop: unrolling it 4x thrashes the i-cache
@@ -206,110 +206,342 @@ __global__ void in_wout_image_kernel(const float* __restrict__ W, int K, int KP,
 }
 
 // ---- sinks: what happens when a row (or a hub chunk) is complete --------------------------------------------------------
-// lane (h, q) holds acc[i] = the float4 16*i + 4*q .. +4 of head h's aggregated input
+// lane l holds acc[h*NI + i] = features 2*(l + 32 i), +1 of head h's aggregated input (FeatGeo)
 template <int N4>
-struct ZSink {      // normalise, save the row statistics, write the row of the fp16-pair image
-    using RG = RowGeo<N4>;
-    uint8_t* zimg; float* rowmax; float* rowsum; const float* scal; int KP, NKB;
-    __device__ __forceinline__ void write_row(int row, float4 (&acc)[RG::NI], float inv, int lane) const
+struct ZSink {      // write the row of the fp16-pair image (the weights arrive normalised)
+    using FG = FeatGeo<N4>;
+    static constexpr int NA = H * FG::NI;
+    uint8_t* zimg; const float* scal; int KP, NKB;
+    __device__ __forceinline__ void write_row(int row, float2 (&acc)[NA], int lane) const
     {
-        const int h = lane >> 2, q = lane & 3, n4 = KP >> 2;
-        const float f = inv * scal[0];
+        const int n2 = KP >> 1;
+        const float f = scal[0];
         const uint32_t rr = uint32_t(row) & (TILE - 1);
         uint8_t* base = zimg + size_t(row >> 7) * size_t(NKB) * KBLOCK + (rr >> 3) * 1024u + (rr & 7u) * 128u;
 #pragma unroll
-        for (int i = 0; i < RG::NI; ++i)
-            if (RG::valid(i, q, n4)) {
-                // 4 consecutive features = half a 16-byte chunk; the 4 q-lanes of a head fill one 32-byte sector per plane
-                const uint32_t ft = uint32_t(h * KP + 16 * i + 4 * q), kb = ft >> 6, e = ft & 63u;
-                __half2 h0, l0, h1, l1;
-                split_h2(acc[i].x * f, acc[i].y * f, h0, l0);
-                split_h2(acc[i].z * f, acc[i].w * f, h1, l1);
-                uint8_t* p = base + size_t(kb) * KBLOCK + (((e >> 3) ^ (rr & 7u)) << 4) + (e & 7u) * 2u;
-                uint2 hv, lv;
-                hv.x = *reinterpret_cast<uint32_t*>(&h0); hv.y = *reinterpret_cast<uint32_t*>(&h1);
-                lv.x = *reinterpret_cast<uint32_t*>(&l0); lv.y = *reinterpret_cast<uint32_t*>(&l1);
-                *reinterpret_cast<uint2*>(p) = hv;
-                *reinterpret_cast<uint2*>(p + PLANE) = lv;
+        for (int i = 0; i < FG::NI; ++i)
+            if (FG::valid(i, lane, n2)) {
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    // 2 consecutive features = 4 bytes per plane; the 32 lanes of one store cover 64 consecutive features
+                    const uint32_t ft = uint32_t(h * KP + 64 * i + 2 * lane), kb = ft >> 6, e = ft & 63u;
+                    __half2 hi, lo;
+                    split_h2(acc[h * FG::NI + i].x * f, acc[h * FG::NI + i].y * f, hi, lo);
+                    uint8_t* p = base + size_t(kb) * KBLOCK + (((e >> 3) ^ (rr & 7u)) << 4) + (e & 7u) * 2u;
+                    *reinterpret_cast<__half2*>(p) = hi;
+                    *reinterpret_cast<__half2*>(p + PLANE) = lo;
+                }
             }
     }
-    __device__ __forceinline__ void finish(int row, float m, float s, float4 (&acc)[RG::NI], int lane) const
-    {
-        const float st = s + 1e-16f;                       // PyG softmax: out / (sum + 1e-16)
-        if ((lane & 3) == 0) {
-            rowmax[int64_t(row) * H + (lane >> 2)] = m;
-            rowsum[int64_t(row) * H + (lane >> 2)] = st;
-        }
-        write_row(row, acc, 1.f / st, lane);
-    }
-    __device__ __forceinline__ void finish_norm(int row, float4 (&acc)[RG::NI], int lane) const { write_row(row, acc, 1.f, lane); }
+    __device__ __forceinline__ void finish_norm(int row, float2 (&acc)[NA], int lane) const { write_row(row, acc, lane); }
     __device__ __forceinline__ void empty(int row, int lane) const
     {
-        float4 acc[RG::NI];
+        float2 acc[NA];
 #pragma unroll
-        for (int i = 0; i < RG::NI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        finish(row, 0.f, 0.f, acc, lane);
+        for (int i = 0; i < NA; ++i) acc[i] = make_float2(0.f, 0.f);
+        write_row(row, acc, lane);                         // the row statistics of an empty row are written by the alpha pass
     }
 };
 template <int N4>
-struct ZPartialSink {   // hub chunk c: unnormalised partial (m, s, acc)
-    using RG = RowGeo<N4>;
-    static constexpr int PART_ACC = RG::NI * 32 * 4;      // floats of one partial accumulator set
-    float* part_ms; float* part_acc; int c;
-    __device__ __forceinline__ void finish(int, float m, float s, float4 (&acc)[RG::NI], int lane) const
+struct ZPartialSink {   // hub chunk c: partial accumulator (the weights are normalised, so partials simply add)
+    using FG = FeatGeo<N4>;
+    static constexpr int NA = H * FG::NI;
+    static constexpr int PART_ACC = NA * 32 * 2;          // floats of one partial accumulator set
+    float* part_acc; int c;
+    __device__ __forceinline__ void finish_partial(float2 (&acc)[NA], int lane) const
     {
-        if ((lane & 3) == 0) {
-            part_ms[int64_t(c) * 2 * H + (lane >> 2)] = m;
-            part_ms[int64_t(c) * 2 * H + H + (lane >> 2)] = s;
-        }
-        float4* p = reinterpret_cast<float4*>(part_acc + int64_t(c) * PART_ACC);
+        float2* p = reinterpret_cast<float2*>(part_acc + int64_t(c) * PART_ACC);
 #pragma unroll
-        for (int i = 0; i < RG::NI; ++i) p[i * 32 + lane] = acc[i];
+        for (int i = 0; i < NA; ++i) p[i * 32 + lane] = acc[i];
     }
-    __device__ __forceinline__ void finish_norm(int, float4 (&)[RG::NI], int) const {}
+    __device__ __forceinline__ void finish_norm(int, float2 (&)[NA], int) const {}
     __device__ __forceinline__ void empty(int, int) const {}
 };
 
-template <int NI>
-__device__ __forceinline__ void acc_zero(float4 (&acc)[NI])
+template <int NA>
+__device__ __forceinline__ void acc_zero(float2 (&acc)[NA])
 {
 #pragma unroll
-    for (int i = 0; i < NI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < NA; ++i) acc[i] = make_float2(0.f, 0.f);
 }
 
-// The stream loop (PACK: packs of whole short rows share one phase A, as in gat_fwd_items_pack).
-template <int N4, bool DROPOUT, bool PACK, class Sink>
-__device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, const Sink& sink, float* rowmax, float* rowsum,
-                                              const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-                                              const int32_t* __restrict__ perm, int n4, const float* __restrict__ a_src,
-                                              const float* __restrict__ a_dst, float slope, KeepMask keep,
-                                              float keep_scale, int lane)
+// =====================================================================================================================
+// Pass 1: attention coefficients.  alpha [E',H] in CSR order, NORMALISED, before dropout; the sign bit of alpha[e,h] says
+// that the logit was in LeakyReLU's negative region (the backward needs that and nothing else of the logits), and
+// jflag[e] = col[e] | (e is the last edge of its row) << 31.  The feature passes (forward and backward) then stream
+// edges without any softmax state: no logit gathers, no exp, no scans, no row statistics in their registers.
+// Warp per work item as everywhere; lane = edge.  Rows of <= 32 edges (alone or in packs) are finished from registers;
+// longer rows make a statistics sweep and a write sweep (the re-gathered logits are L2-warm); hub rows get the same
+// two sweeps chunk-parallel (in_alpha_hub_*).
+// =====================================================================================================================
+__device__ __forceinline__ float with_sign(float a, bool neg) { return __uint_as_float(__float_as_uint(a) | (neg ? 0x80000000u : 0u)); }
+
+// the write sweep of <= 32 edges of ONE row whose statistics (m, 1/s) are known
+__device__ __forceinline__ void alpha_write_chunk(int beg, int n, bool ends_row, const float (&adst)[H], const float (&m)[H],
+                                                  const float (&sinv)[H], const int32_t* __restrict__ col,
+                                                  const float* __restrict__ a_src, float slope, float* __restrict__ alpha,
+                                                  int32_t* __restrict__ jflag, int lane)
 {
-    using RG = RowGeo<N4>;
-    const int h = lane >> 2, q = lane & 3;
+    if (lane < n) {
+        const int e = beg + lane, j = col[e];
+        float as[H], o[H];
+        load_vecH<H>(a_src + int64_t(j) * H, as);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float z = as[h] + adst[h];
+            o[h] = with_sign(expf(leaky(z, slope) - m[h]) * sinv[h], !(z > 0.f));
+        }
+        store_vecH<H>(alpha + int64_t(e) * H, o);
+        jflag[e] = j | ((ends_row && lane == n - 1) ? int(0x80000000u) : 0);
+    }
+}
+
+// statistics of <= 32 edges of one row folded into the running (m, s) of the row (all lanes hold the result)
+__device__ __forceinline__ void alpha_stat_chunk(int beg, int n, const float (&adst)[H], const int32_t* __restrict__ col,
+                                                 const float* __restrict__ a_src, float slope, float (&m)[H], float (&s)[H], int lane)
+{
+    float e[H];
+    if (lane < n) {
+        const int j = col[beg + lane];
+        float as[H];
+        load_vecH<H>(a_src + int64_t(j) * H, as);
+#pragma unroll
+        for (int h = 0; h < H; ++h) e[h] = leaky(as[h] + adst[h], slope);
+    } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) e[h] = -INFINITY;
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const float cm = warp_max(e[h]);
+        const float cs = warp_sum(lane < n ? expf(e[h] - cm) : 0.f);
+        const float mn = fmaxf(m[h], cm);
+        s[h] = s[h] * expf(m[h] - mn) + cs * expf(cm - mn);       // expf(-inf) = 0 on the first chunk
+        m[h] = mn;
+    }
+}
+
+template <bool PACK>
+__global__ void __launch_bounds__(IN_THREADS)
+in_alpha_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ a_src,
+               const float* __restrict__ a_dst, gnnfd_item_plan_t items, int hub_threshold, float slope,
+               float* __restrict__ alpha, int32_t* __restrict__ jflag, float* __restrict__ rowmax, float* __restrict__ rowsum)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x * IN_WARPS + warp;
+    if (item >= items.n_items) return;
+    ChunkCursor cur;
+    cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
+    auto on_empty = [&](int r) {
+        if (lane < H) {
+            rowmax[int64_t(r) * H + lane] = 0.f;
+            rowsum[int64_t(r) * H + lane] = 1e-16f;
+        }
+    };
+    int row = 0, beg = 0, n = 0, k = 0, la = 0, lb = 0;
+    bool first = false, last = false;
+    while (true) {
+        const int kind = PACK ? cur.next_any(rowptr, lane, row, beg, n, first, last, k, la, lb, on_empty)
+                              : (cur.next(rowptr, row, beg, n, first, last, on_empty) ? 1 : 0);
+        if (!kind) break;
+        if (PACK && kind == 2) {
+            // pack of k whole rows: segmented scans over the lanes of each row (as fwd_phase_a_pack)
+            const bool act = lane < n;
+            const int e_id = beg + lane;
+            int lo = 0, hi = k - 1;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const int bm = __shfl_sync(FULL, lb, mid);
+                if (bm > e_id) hi = mid; else lo = min(mid + 1, k - 1);
+            }
+            const int sa = __shfl_sync(FULL, la, lo) - beg, sb = __shfl_sync(FULL, lb, lo) - beg - 1;
+            const int r = row + lo;
+            float z[H];
+            int j = 0;
+            if (act) {
+                j = col[e_id];
+                float as[H], ad[H];
+                load_vecH<H>(a_src + int64_t(j) * H, as);
+                load_vecH<H>(a_dst + int64_t(r) * H, ad);
+#pragma unroll
+                for (int h = 0; h < H; ++h) z[h] = as[h] + ad[h];
+            } else {
+#pragma unroll
+                for (int h = 0; h < H; ++h) z[h] = -INFINITY;
+            }
+            float o[H], mrow[H], srow[H];
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                const float e = act ? leaky(z[h], slope) : -INFINITY;
+                float mx = e;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float t = __shfl_up_sync(FULL, mx, d);
+                    if (lane - d >= sa) mx = fmaxf(mx, t);
+                }
+                mrow[h] = __shfl_sync(FULL, mx, sb);
+                const float pexp = act ? expf(e - mrow[h]) : 0.f;
+                float sm = pexp;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float t = __shfl_up_sync(FULL, sm, d);
+                    if (lane - d >= sa) sm += t;
+                }
+                srow[h] = __shfl_sync(FULL, sm, sb) + 1e-16f;       // PyG softmax: out / (sum + 1e-16)
+                o[h] = with_sign(pexp / srow[h], !(z[h] > 0.f));
+            }
+            if (act) {
+                store_vecH<H>(alpha + int64_t(e_id) * H, o);
+                jflag[e_id] = j | (lane == sb ? int(0x80000000u) : 0);
+                if (lane == sb) {
+                    store_vecH<H>(rowmax + int64_t(r) * H, mrow);
+                    store_vecH<H>(rowsum + int64_t(r) * H, srow);
+                }
+            }
+            continue;
+        }
+        // a single row (kind 1, first chunk of it): statistics sweep over all of its chunks, then the write sweep
+        float adst[H], m[H], sv[H];
+        load_vecH<H>(a_dst + int64_t(row) * H, adst);
+#pragma unroll
+        for (int h = 0; h < H; ++h) { m[h] = -INFINITY; sv[h] = 0.f; }
+        const int row_beg = beg, r = row;
+        alpha_stat_chunk(beg, n, adst, col, a_src, slope, m, sv, lane);
+        int row_end = beg + n;
+        while (!last) {
+            cur.next(rowptr, row, beg, n, first, last, on_empty);     // stays inside the row until last
+            alpha_stat_chunk(beg, n, adst, col, a_src, slope, m, sv, lane);
+            row_end = beg + n;
+        }
+        float sinv[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) { sv[h] += 1e-16f; sinv[h] = 1.f / sv[h]; }
+        if (lane == 0) {
+            store_vecH<H>(rowmax + int64_t(r) * H, m);
+            store_vecH<H>(rowsum + int64_t(r) * H, sv);
+        }
+        for (int b = row_beg; b < row_end; b += 32)
+            alpha_write_chunk(b, min(32, row_end - b), b + 32 >= row_end, adst, m, sinv, col, a_src, slope, alpha, jflag, lane);
+    }
+}
+
+// hub rows: (1) statistics of every 512-edge chunk, (2) one warp per hub row folds them in chunk order, (3) write sweep
+__global__ void __launch_bounds__(IN_THREADS)
+in_alpha_hub_stats(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ a_src,
+                   const float* __restrict__ a_dst, gnnfd_hub_plan_t plan, float slope, float* __restrict__ part_ms)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * IN_WARPS + warp;
+    if (c >= plan.n_chunk) return;
+    const int slot = plan.chunk_hub[c], i = plan.hub_row[slot];
+    const int beg = rowptr[i] + (c - plan.hub_chunk_ptr[slot]) * plan.chunk;
+    const int end = min(rowptr[i + 1], beg + plan.chunk);
+    float adst[H], m[H], sv[H];
+    load_vecH<H>(a_dst + int64_t(i) * H, adst);
+#pragma unroll
+    for (int h = 0; h < H; ++h) { m[h] = -INFINITY; sv[h] = 0.f; }
+    for (int b = beg; b < end; b += 32) alpha_stat_chunk(b, min(32, end - b), adst, col, a_src, slope, m, sv, lane);
+    if (lane == 0) {
+        store_vecH<H>(part_ms + int64_t(c) * 2 * H, m);
+        store_vecH<H>(part_ms + int64_t(c) * 2 * H + H, sv);
+    }
+}
+__global__ void in_alpha_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_ms, float* __restrict__ rowmax,
+                                   float* __restrict__ rowsum)
+{
+    const int slot = blockIdx.x, h = threadIdx.x;          // one thread per head: the chunk order is the summation order
+    if (h >= H) return;
+    const int i = plan.hub_row[slot];
+    float m = -INFINITY, s = 0.f;
+    for (int c = plan.hub_chunk_ptr[slot]; c < plan.hub_chunk_ptr[slot + 1]; ++c) {
+        const float cm = part_ms[int64_t(c) * 2 * H + h], cs = part_ms[int64_t(c) * 2 * H + H + h];
+        const float mn = fmaxf(m, cm);
+        s = s * expf(m - mn) + cs * expf(cm - mn);
+        m = mn;
+    }
+    rowmax[int64_t(i) * H + h] = m;
+    rowsum[int64_t(i) * H + h] = s + 1e-16f;
+}
+__global__ void __launch_bounds__(IN_THREADS)
+in_alpha_hub_write(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const float* __restrict__ a_src,
+                   const float* __restrict__ a_dst, gnnfd_hub_plan_t plan, float slope, const float* __restrict__ rowmax,
+                   const float* __restrict__ rowsum, float* __restrict__ alpha, int32_t* __restrict__ jflag)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * IN_WARPS + warp;
+    if (c >= plan.n_chunk) return;
+    const int slot = plan.chunk_hub[c], i = plan.hub_row[slot];
+    const int beg = rowptr[i] + (c - plan.hub_chunk_ptr[slot]) * plan.chunk;
+    const int row_end = rowptr[i + 1], end = min(row_end, beg + plan.chunk);
+    float adst[H], m[H], sinv[H];
+    load_vecH<H>(a_dst + int64_t(i) * H, adst);
+    load_vecH<H>(rowmax + int64_t(i) * H, m);
+    load_vecH<H>(rowsum + int64_t(i) * H, sinv);
+#pragma unroll
+    for (int h = 0; h < H; ++h) sinv[h] = 1.f / sinv[h];
+    for (int b = beg; b < end; b += 32)
+        alpha_write_chunk(b, min(32, end - b), b + 32 >= row_end, adst, m, sinv, col, a_src, slope, alpha, jflag, lane);
+}
+
+// =====================================================================================================================
+// Pass 2: Z[i,h,:] = sum_e alpha_used[e,h] x[col[e],:].  The stream needs only the edge range of its rows: per chunk of <= 32
+// edges lane = edge loads alpha (32 B) and jflag (4 B) -- coalesced, nothing depends on a gathered value -- one chunk ahead
+// of the feature traffic; dropout is applied while staging.  Row ends come from the flag bit, so packs and single rows
+// are the same code.
+// =====================================================================================================================
+struct FeatChunk {
+    int row, beg, n;
+    unsigned lastmask;      // staged edges that end a row
+};
+
+template <bool DROPOUT>
+__device__ __forceinline__ void stage_chunk(FeatChunk& c, const float* __restrict__ alpha, const int32_t* __restrict__ jflag,
+                                            const int32_t* __restrict__ perm, KeepMask keep, float keep_scale, float* p_s, int* j_s,
+                                            int lane)
+{
+    int jf = 0;
+    float w[H];
+    if (lane < c.n) {
+        const int e = c.beg + lane;
+        jf = jflag[e];
+        load_vecH<H>(alpha + int64_t(e) * H, w);
+        unsigned kbits = 0xffu;
+        if (DROPOUT) kbits = keep.bits(perm[e], H);
+#pragma unroll
+        for (int h = 0; h < H; ++h) w[h] = ((kbits >> h) & 1u) ? fabsf(w[h]) * (DROPOUT ? keep_scale : 1.f) : 0.f;
+    } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) w[h] = 0.f;
+    }
+    store_vecH<H>(p_s + lane * H, w);
+    j_s[lane] = jf & 0x7fffffff;
+    c.lastmask = __ballot_sync(FULL, jf < 0);
+    __syncwarp();
+}
+
+// HUB: one (row, range) segment whose partial sum goes to the sink at the end; else whole rows, finished at the flags
+template <int N4, bool DROPOUT, bool PACK, bool HUB, class Sink>
+__device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, const Sink& sink, const int32_t* __restrict__ rowptr,
+                                              const int32_t* __restrict__ perm, int n4, const float* __restrict__ alpha,
+                                              const int32_t* __restrict__ jflag, KeepMask keep, float keep_scale, int lane)
+{
+    using FG = FeatGeo<N4>;
+    constexpr int NA = H * FG::NI;
+    (void)n4;
     auto on_empty = [&](int r) { sink.empty(r, lane); };
-    int* r_all = reinterpret_cast<int*>(ring.extra);            // [2][32] row id | last-edge flag per staged edge (packs)
-    ChunkStat<H> c0, c1;
-    int kind0 = 0, kind1 = 0;
-    int b0 = 0, beg = 0, k = 0, la = 0, lb = 0;
-    auto next = [&](ChunkStat<H>& c) -> int {
-        if (PACK) return cur.next_any(rowptr, lane, c.row, beg, c.n, c.first, c.last, k, la, lb, on_empty);
-        return cur.next(rowptr, c.row, beg, c.n, c.first, c.last, on_empty) ? 1 : 0;
+    FeatChunk c0, c1;
+    int b0 = 0;
+    auto next = [&](FeatChunk& c) -> bool {
+        bool first, last;
+        int k, la, lb;
+        if (PACK) return cur.next_any(rowptr, lane, c.row, c.beg, c.n, first, last, k, la, lb, on_empty) != 0;
+        return cur.next(rowptr, c.row, c.beg, c.n, first, last, on_empty);
     };
-    auto phase_a = [&](ChunkStat<H>& c, int kind, int buf) {
-        if (PACK && kind == 2)
-            fwd_phase_a_pack<GI, DROPOUT>(c.row, beg, c.n, k, la, lb, col, perm, a_src, a_dst, slope, keep, keep_scale, rowmax,
-                                          rowsum, ring.p_s + buf * 32 * H, ring.j_s + buf * 32, r_all + buf * 32, lane);
-        else
-            fwd_phase_a<GI, DROPOUT>(c, beg, col, perm, a_src, a_dst, slope, keep, keep_scale, ring.p_s + buf * 32 * H,
-                                     ring.j_s + buf * 32, lane);
-    };
-    kind0 = next(c0);
-    if (!kind0) return;
-    phase_a(c0, kind0, b0);
+    if (!next(c0)) return;
+    stage_chunk<DROPOUT>(c0, alpha, jflag, perm, keep, keep_scale, ring.p_s + b0 * 32 * H, ring.j_s + b0 * 32, lane);
     int issued0 = 0, issued1 = 0;
-    float m = -INFINITY, s = 0.f;                       // online-softmax state of THIS lane's head
-    float4 acc[RG::NI];
+    float2 acc[NA];
     acc_zero(acc);
     while (true) {
         const int* j0 = ring.j_s + b0 * 32;
@@ -318,31 +550,11 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
             const int k0 = min(ring.room(), c0.n - issued0);
             if (k0 > 0) { ring.issue_many(j0 + issued0, k0, lane); issued0 += k0; }
         }
-        kind1 = next(c1);
+        const bool more = next(c1);
         issued1 = 0;
-        if (kind1) phase_a(c1, kind1, b0 ^ 1);
-        if (c0.first) {
-            m = -INFINITY;
-            s = 0.f;
-            acc_zero(acc);
-        }
-        float fch = 1.f;
-        unsigned lastmask = 0;                          // packs: lanes (= staged edges) that end a row
-        if (PACK && kind0 == 2) {
-            lastmask = __ballot_sync(FULL, r_all[b0 * 32 + lane] < 0);
-        } else {
-            const float cm = pick_head(c0.cm, h), cs = pick_head(c0.cs, h);
-            const float mn = fmaxf(m, cm);
-            const float fold = expf(m - mn);            // 0 on the first chunk (m = -inf)
-            fch = expf(cm - mn);
-            s = s * fold + cs * fch;
-            m = mn;
-            if (!c0.first) {
-#pragma unroll
-                for (int i = 0; i < RG::NI; ++i) { acc[i].x *= fold; acc[i].y *= fold; acc[i].z *= fold; acc[i].w *= fold; }
-            }
-        }
-        const float* p0 = ring.p_s + b0 * 32 * H + h;
+        if (more) stage_chunk<DROPOUT>(c1, alpha, jflag, perm, keep, keep_scale, ring.p_s + (b0 ^ 1) * 32 * H, ring.j_s + (b0 ^ 1) * 32, lane);
+        const uint32_t p0 = st_smem_u32(ring.p_s + b0 * 32 * H);
+        const unsigned lastmask = HUB ? 0u : c0.lastmask;
         // edges in groups of four: one warp barrier and one (multi-lane) refill per group
         for (int t0 = 0; t0 < c0.n; t0 += 4) {
             const int cnt = min(4, c0.n - t0);
@@ -350,16 +562,18 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
             for (int r = 0; r < 4; ++r) {
                 if (r < cnt) {
                     const int t = t0 + r;
-                    const uint32_t a = ring.front_at(r) + uint32_t(q) * 16u;
-                    const float w = p0[t * H] * fch;
+                    const uint32_t a = ring.front_at(r) + uint32_t(lane) * 8u;
+                    const float4 w0 = lds128(p0 + uint32_t(t) * (H * 4u)), w1 = lds128(p0 + uint32_t(t) * (H * 4u) + 16u);   // broadcast
+                    const float w[H] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    // no validity predicate here: a lane beyond the row's end reads the bytes that follow the slot (inside this
+                    // warp's shared memory) into accumulators that the sinks never write out -- cheaper than a divergent tail
 #pragma unroll
-                    for (int i = 0; i < RG::NI; ++i)
-                        if (RG::valid(i, q, n4)) {
-                            const float4 v = lds128(a + uint32_t(i) * 64u);
-                            ffma2_bcast(acc[i].x, acc[i].y, w, v.x, v.y);
-                            ffma2_bcast(acc[i].z, acc[i].w, w, v.z, v.w);
-                        }
-                    if (PACK && ((lastmask >> t) & 1u)) {     // last edge of a packed row (weights already normalised)
+                    for (int i = 0; i < FG::NI; ++i) {
+                        const float2 v = lds64(a + uint32_t(i) * 256u);
+#pragma unroll
+                        for (int hh = 0; hh < H; ++hh) ffma2_bcast(acc[hh * FG::NI + i].x, acc[hh * FG::NI + i].y, w[hh], v.x, v.y);
+                    }
+                    if ((lastmask >> t) & 1u) {           // last edge of a row (weights are normalised)
                         sink.finish_norm(c0.row + __popc(lastmask & ((1u << t) - 1u)), acc, lane);
                         acc_zero(acc);
                     }
@@ -369,30 +583,28 @@ __device__ __forceinline__ void in_fwd_stream(ChunkCursor& cur, InRing& ring, co
             int free_slots = cnt;
             const int k0 = min(free_slots, c0.n - issued0);
             if (k0 > 0) { ring.issue_many(j0 + issued0, k0, lane); issued0 += k0; free_slots -= k0; }
-            if (kind1 && free_slots > 0) {
+            if (more && free_slots > 0) {
                 const int k1 = min(free_slots, c1.n - issued1);
                 if (k1 > 0) { ring.issue_many(j1 + issued1, k1, lane); issued1 += k1; }
             }
         }
-        if (kind0 == 1 && c0.last) sink.finish(c0.row, m, s, acc, lane);
-        if (!kind1) break;
+        if (!more) break;
         c0 = c1;
-        kind0 = kind1;
         issued0 = issued1;
         b0 ^= 1;
     }
+    if constexpr (HUB) sink.finish_partial(acc, lane);
 }
 
-constexpr int FWD_EXTRA = 256;   // r_all
+constexpr int FWD_EXTRA = 0;
 #ifndef GNNFD_IN_FWD_CTAS
-#define GNNFD_IN_FWD_CTAS 4
+#define GNNFD_IN_FWD_CTAS 5
 #endif
 
 template <int N4, bool DROPOUT, bool PACK>
 __global__ void __launch_bounds__(IN_THREADS, GNNFD_IN_FWD_CTAS)
-gat_in_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                 const float* __restrict__ x, int64_t ldx, const float* __restrict__ a_src,
-                 const float* __restrict__ a_dst, gnnfd_item_plan_t items, int hub_threshold, float slope,
+gat_in_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, const float* __restrict__ x, int64_t ldx,
+                 const float* __restrict__ alpha, const int32_t* __restrict__ jflag, gnnfd_item_plan_t items, int hub_threshold,
                  KeepMask keep, float keep_scale, ZSink<N4> sink)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -403,18 +615,15 @@ gat_in_fwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     ring.init(smem + warp * in_warp_bytes(sink.KP, FWD_EXTRA), x, ldx, sink.KP, lane);
     ChunkCursor cur;
     cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
-    in_fwd_stream<N4, DROPOUT, PACK>(cur, ring, sink, sink.rowmax, sink.rowsum, rowptr, col, perm, sink.KP >> 2, a_src, a_dst,
-                                     slope, keep, keep_scale, lane);
+    in_fwd_stream<N4, DROPOUT, PACK, false>(cur, ring, sink, rowptr, perm, sink.KP >> 2, alpha, jflag, keep, keep_scale, lane);
 }
 
-// one warp per (hub row, chunk): partial (m, s, unnormalised acc)
+// one warp per (hub row, chunk): partial accumulators
 template <int N4, bool DROPOUT>
-__global__ void __launch_bounds__(IN_THREADS, 4)
-gat_in_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                      const float* __restrict__ x, int64_t ldx, int KP, const float* __restrict__ a_src,
-                      const float* __restrict__ a_dst, gnnfd_hub_plan_t plan, float slope,
-                      KeepMask keep, float keep_scale, float* __restrict__ part_ms,
-                      float* __restrict__ part_acc)
+__global__ void __launch_bounds__(IN_THREADS, GNNFD_IN_FWD_CTAS)
+gat_in_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, const float* __restrict__ x, int64_t ldx,
+                      int KP, const float* __restrict__ alpha, const int32_t* __restrict__ jflag, gnnfd_hub_plan_t plan,
+                      KeepMask keep, float keep_scale, float* __restrict__ part_acc)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -428,56 +637,40 @@ gat_in_fwd_hub_chunks(const int32_t* __restrict__ rowptr, const int32_t* __restr
     ring.init(smem + warp * in_warp_bytes(KP, FWD_EXTRA), x, ldx, KP, lane);
     ChunkCursor cur;
     cur.start_segment(i, beg, end);
-    ZPartialSink<N4> sink{part_ms, part_acc, c};
-    in_fwd_stream<N4, DROPOUT, false>(cur, ring, sink, nullptr, nullptr, rowptr, col, perm, KP >> 2, a_src, a_dst, slope, keep,
-                                      keep_scale, lane);
+    ZPartialSink<N4> sink{part_acc, c};
+    in_fwd_stream<N4, DROPOUT, false, true>(cur, ring, sink, rowptr, perm, KP >> 2, alpha, jflag, keep, keep_scale, lane);
 }
 
-// one CTA per hub row: warp w folds chunks w, w+8, ... (online-softmax combine), the eight warp states are folded in
-// warp order -- a fixed order, so the result is deterministic
+// one CTA per hub row: warp w sums chunks w, w+8, ..., the eight warp sums are added in warp order -- a fixed order, so the
+// result is deterministic
 template <int N4>
 __global__ void __launch_bounds__(ROW_THREADS)
-gat_in_fwd_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_ms, const float* __restrict__ part_acc, ZSink<N4> sink)
+gat_in_fwd_hub_merge(gnnfd_hub_plan_t plan, const float* __restrict__ part_acc, ZSink<N4> sink)
 {
-    using RG = RowGeo<N4>;
+    constexpr int NA = ZSink<N4>::NA;
     constexpr int PART_ACC = ZPartialSink<N4>::PART_ACC;
-    extern __shared__ __align__(16) float msm[];               // [ROW_WARPS][2H] then [ROW_WARPS][PART_ACC]
-    float* st_ms = msm;
-    float4* st_acc = reinterpret_cast<float4*>(msm + ROW_WARPS * 2 * H);
+    extern __shared__ __align__(16) float msm[];               // [ROW_WARPS][PART_ACC]
+    float2* st_acc = reinterpret_cast<float2*>(msm);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int h = lane >> 2;
     const int slot = blockIdx.x;
     const int i = plan.hub_row[slot];
     const int c0 = plan.hub_chunk_ptr[slot], c1 = plan.hub_chunk_ptr[slot + 1];
-    float M = -INFINITY, s = 0.f;
-    float4 acc[RG::NI];
+    float2 acc[NA];
     acc_zero(acc);
-    auto fold = [&](float mc, float sc, const float4* __restrict__ pacc) {
-        const float mn = fmaxf(M, mc);
-        const float fo = (M == -INFINITY) ? 0.f : expf(M - mn);
-        const float fn = (mc == -INFINITY) ? 0.f : expf(mc - mn);
-        s = s * fo + sc * fn;
-        M = mn;
+    auto add = [&](const float2* __restrict__ pacc) {
 #pragma unroll
-        for (int k = 0; k < RG::NI; ++k) {
-            const float4 v = pacc[k * 32 + lane];
-            acc[k].x = fmaf(v.x, fn, acc[k].x * fo); acc[k].y = fmaf(v.y, fn, acc[k].y * fo);
-            acc[k].z = fmaf(v.z, fn, acc[k].z * fo); acc[k].w = fmaf(v.w, fn, acc[k].w * fo);
+        for (int k = 0; k < NA; ++k) {
+            const float2 v = pacc[k * 32 + lane];
+            acc[k].x += v.x; acc[k].y += v.y;
         }
     };
-    for (int c = c0 + warp; c < c1; c += ROW_WARPS)
-        fold(part_ms[int64_t(c) * 2 * H + h], part_ms[int64_t(c) * 2 * H + H + h],
-             reinterpret_cast<const float4*>(part_acc + int64_t(c) * PART_ACC));
-    if ((lane & 3) == 0) {
-        st_ms[warp * 2 * H + h] = M;
-        st_ms[warp * 2 * H + H + h] = s;
-    }
+    for (int c = c0 + warp; c < c1; c += ROW_WARPS) add(reinterpret_cast<const float2*>(part_acc + int64_t(c) * PART_ACC));
 #pragma unroll
-    for (int k = 0; k < RG::NI; ++k) st_acc[warp * (PART_ACC / 4) + k * 32 + lane] = acc[k];
+    for (int k = 0; k < NA; ++k) st_acc[warp * (PART_ACC / 2) + k * 32 + lane] = acc[k];
     __syncthreads();
     if (warp != 0) return;
-    for (int w = 1; w < ROW_WARPS; ++w) fold(st_ms[w * 2 * H + h], st_ms[w * 2 * H + H + h], st_acc + w * (PART_ACC / 4));
-    sink.finish(i, M, s, acc, lane);
+    for (int w = 1; w < ROW_WARPS; ++w) add(st_acc + w * (PART_ACC / 2));
+    sink.finish_norm(i, acc, lane);
 }
 
 template <class Kn>
@@ -490,10 +683,41 @@ static int in_set_smem(Kn kernel, int bytes)
 // x as the edge kernels need it: 16-byte aligned rows of at least KP floats
 bool in_x_ok(const float* x, int64_t ldx, int KP) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ldx % 4 == 0 && ldx >= KP; }
 
+// attention pass: alpha / jflag for every edge, rowmax / rowsum for every row
+static int launch_in_alpha(const gnnfd_graph_t* g, const float* a_src, const float* a_dst, float slope, float* alpha, int32_t* jflag,
+                           float* rowmax, float* rowsum, void* ws, size_t ws_bytes, cudaStream_t st)
+{
+    const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
+    const unsigned grid = (unsigned)((g->items_dst.n_items + IN_WARPS - 1) / IN_WARPS);
+    static const bool pack = [] {
+        const char* e = getenv("GNNFD_FWD_PACK");
+        return e ? atoi(e) != 0 : true;
+    }();
+    if (pack)
+        in_alpha_items<true><<<grid, IN_THREADS, 0, st>>>(g->rowptr, g->col, a_src, a_dst, g->items_dst, thr, slope, alpha, jflag, rowmax, rowsum);
+    else
+        in_alpha_items<false><<<grid, IN_THREADS, 0, st>>>(g->rowptr, g->col, a_src, a_dst, g->items_dst, thr, slope, alpha, jflag, rowmax, rowsum);
+    g_launches += 1;
+    if (g->hub_dst.n_hub > 0) {
+        const gnnfd_hub_plan_t& pl = g->hub_dst;
+        const size_t need = carve_bytes(size_t(pl.n_chunk) * 2 * H, 4);
+        GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "in_fwd: workspace %zu < %zu", ws_bytes, need);
+        char* p = reinterpret_cast<char*>(ws);
+        float* part_ms = carve<float>(p, size_t(pl.n_chunk) * 2 * H);
+        const unsigned gc = (unsigned)((pl.n_chunk + IN_WARPS - 1) / IN_WARPS);
+        in_alpha_hub_stats<<<gc, IN_THREADS, 0, st>>>(g->rowptr, g->col, a_src, a_dst, pl, slope, part_ms);
+        in_alpha_hub_merge<<<(unsigned)pl.n_hub, 32, 0, st>>>(pl, part_ms, rowmax, rowsum);
+        in_alpha_hub_write<<<gc, IN_THREADS, 0, st>>>(g->rowptr, g->col, a_src, a_dst, pl, slope, rowmax, rowsum, alpha, jflag);
+        g_launches += 3;
+    }
+    GNNFD_LAUNCH_CHECK();
+    return GNNFD_OK;
+}
+
 template <int N4>
-static int launch_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, const Dims& d, const float* a_src, const float* a_dst,
-                         float slope, const uint8_t* keep_mask, float p_drop, uint64_t seed, const float* scal, void* zimg, float* rowmax,
-                         float* rowsum, void* ws, size_t ws_bytes, cudaStream_t st)
+static int launch_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, const Dims& d, const float* alpha, const int32_t* jflag,
+                         const uint8_t* keep_mask, float p_drop, uint64_t seed, const float* scal, void* zimg, void* ws,
+                         size_t ws_bytes, cudaStream_t st)
 {
     const bool drop = p_drop > 0.f;              // explicit mask, or (mask == NULL) the counter-based RNG keyed on seed
     float ks = 1.f;
@@ -501,7 +725,7 @@ static int launch_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, co
     const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
     const int smem = IN_WARPS * in_warp_bytes(d.KP, FWD_EXTRA);
     const unsigned grid = (unsigned)((g->items_dst.n_items + IN_WARPS - 1) / IN_WARPS);
-    ZSink<N4> sink{reinterpret_cast<uint8_t*>(zimg), rowmax, rowsum, scal, d.KP, d.NKB};
+    ZSink<N4> sink{reinterpret_cast<uint8_t*>(zimg), scal, d.KP, d.NKB};
     static const bool pack = [] {
         const char* e = getenv("GNNFD_FWD_PACK");
         return e ? atoi(e) != 0 : true;
@@ -510,8 +734,8 @@ static int launch_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, co
 #define GNNFD_IN_FWD(DD, PP)                                                                                           \
     rc = in_set_smem(gat_in_fwd_items<N4, DD, PP>, smem);                                                              \
     if (rc) return rc;                                                                                                 \
-    gat_in_fwd_items<N4, DD, PP><<<grid, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, x, ldx, a_src, a_dst,       \
-                                                                 g->items_dst, thr, slope, keep, ks, sink)
+    gat_in_fwd_items<N4, DD, PP><<<grid, IN_THREADS, smem, st>>>(g->rowptr, g->perm, x, ldx, alpha, jflag, g->items_dst, thr, keep, \
+                                                                 ks, sink)
     if (pack) { if (drop) { GNNFD_IN_FWD(true, true); } else { GNNFD_IN_FWD(false, true); } }
     else      { if (drop) { GNNFD_IN_FWD(true, false); } else { GNNFD_IN_FWD(false, false); } }
 #undef GNNFD_IN_FWD
@@ -522,24 +746,22 @@ static int launch_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, co
         const size_t need = carve_bytes(size_t(pl.n_chunk) * 2 * H, 4) + carve_bytes(size_t(pl.n_chunk) * PART_ACC, 4);
         GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "in_fwd: workspace %zu < %zu", ws_bytes, need);
         char* p = reinterpret_cast<char*>(ws);
-        float* part_ms = carve<float>(p, size_t(pl.n_chunk) * 2 * H);
+        carve<float>(p, size_t(pl.n_chunk) * 2 * H);           // (the attention pass's chunk statistics)
         float* part_acc = carve<float>(p, size_t(pl.n_chunk) * PART_ACC);
         const unsigned gc = (unsigned)((pl.n_chunk + IN_WARPS - 1) / IN_WARPS);
         if (drop) {
             rc = in_set_smem(gat_in_fwd_hub_chunks<N4, true>, smem);
             if (rc) return rc;
-            gat_in_fwd_hub_chunks<N4, true><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, x, ldx, d.KP, a_src, a_dst, pl,
-                                                                         slope, keep, ks, part_ms, part_acc);
+            gat_in_fwd_hub_chunks<N4, true><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->perm, x, ldx, d.KP, alpha, jflag, pl, keep, ks, part_acc);
         } else {
             rc = in_set_smem(gat_in_fwd_hub_chunks<N4, false>, smem);
             if (rc) return rc;
-            gat_in_fwd_hub_chunks<N4, false><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, x, ldx, d.KP, a_src, a_dst, pl,
-                                                                          slope, keep, ks, part_ms, part_acc);
+            gat_in_fwd_hub_chunks<N4, false><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->perm, x, ldx, d.KP, alpha, jflag, pl, keep, ks, part_acc);
         }
-        const int msm = (ROW_WARPS * 2 * H + ROW_WARPS * PART_ACC) * 4;
+        const int msm = ROW_WARPS * PART_ACC * 4;
         rc = in_set_smem(gat_in_fwd_hub_merge<N4>, msm);
         if (rc) return rc;
-        gat_in_fwd_hub_merge<N4><<<(unsigned)pl.n_hub, ROW_THREADS, msm, st>>>(pl, part_ms, part_acc, sink);
+        gat_in_fwd_hub_merge<N4><<<(unsigned)pl.n_hub, ROW_THREADS, msm, st>>>(pl, part_acc, sink);
         g_launches += 2;
     }
     GNNFD_LAUNCH_CHECK();
@@ -681,15 +903,19 @@ int gnnfd_in_fwd_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes)
     return GNNFD_OK;
 }
 
-/* Aggregation in input space: zimg (fp16-pair image of Z, rows = destinations), rowmax / rowsum [n_dst,H]. */
+/* Aggregation in input space.  Pass 1 writes the attention coefficients alpha [E',H] (CSR order, normalised, sign bit =
+ * LeakyReLU negative region), jflag [E'] (source id | row-end flag) and rowmax / rowsum [n_dst,H]; pass 2 streams the edges
+ * and writes zimg (fp16-pair image of Z, rows = destinations).  alpha and jflag are what the backward reads. */
 int gnnfd_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src, const float* a_dst,
                  float negative_slope, const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed, const void* prep, void* zimg,
-                 float* rowmax, float* rowsum, void* ws, size_t ws_bytes, gnnfd_stream_t stream)
+                 float* rowmax, float* rowsum, float* alpha, int32_t* jflag, void* ws, size_t ws_bytes, gnnfd_stream_t stream)
 {
     int rc = check_graph(g, false, "in_fwd");
     if (rc) return rc;
     GNNFD_REQUIRE(K >= 1 && K <= MAX_K, GNNFD_ERR_ARG, "in_fwd: bad shape (K <= %d)", MAX_K);
     GNNFD_REQUIRE(g->n_dst == 0 || (x && a_src && a_dst && prep && zimg && rowmax && rowsum), GNNFD_ERR_ARG, "in_fwd: NULL tensor");
+    GNNFD_REQUIRE(g->n_edges == 0 || (alpha && jflag), GNNFD_ERR_ARG, "in_fwd: NULL alpha / jflag");
+    GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(alpha) & 15) == 0, GNNFD_ERR_ARG, "in_fwd: alpha must be 16-byte aligned");
     GNNFD_REQUIRE(p_drop >= 0.f && p_drop <= 0.9f, GNNFD_ERR_ARG, "in_fwd: dropout p must be in [0,0.9] on the input-space path");
     GNNFD_REQUIRE((reinterpret_cast<uintptr_t>(zimg) & 1023) == 0, GNNFD_ERR_ARG, "in_fwd: zimg must be 1024-byte aligned");
     if (g->n_dst == 0) return GNNFD_OK;
@@ -705,11 +931,11 @@ int gnnfd_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K,
         const size_t last = size_t(g->n_dst / TILE) * d.NKB * KBLOCK;
         GNNFD_CUDA(cudaMemsetAsync(reinterpret_cast<char*>(zimg) + last, 0, size_t(d.NKB) * KBLOCK, st));
     }
-    if (d.KP == 168)
-        return launch_in_fwd<42>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, dropout_seed, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
-    if (d.KP == 64)
-        return launch_in_fwd<16>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, dropout_seed, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
-    return launch_in_fwd<0>(g, x, ldx, d, a_src, a_dst, negative_slope, keep_mask, p_drop, dropout_seed, scal, zimg, rowmax, rowsum, ws, ws_bytes, st);
+    rc = launch_in_alpha(g, a_src, a_dst, negative_slope, alpha, jflag, rowmax, rowsum, ws, ws_bytes, st);
+    if (rc) return rc;
+    if (d.KP == 168) return launch_in_fwd<42>(g, x, ldx, d, alpha, jflag, keep_mask, p_drop, dropout_seed, scal, zimg, ws, ws_bytes, st);
+    if (d.KP == 64) return launch_in_fwd<16>(g, x, ldx, d, alpha, jflag, keep_mask, p_drop, dropout_seed, scal, zimg, ws, ws_bytes, st);
+    return launch_in_fwd<0>(g, x, ldx, d, alpha, jflag, keep_mask, p_drop, dropout_seed, scal, zimg, ws, ws_bytes, st);
 }
 
 }  // extern "C"

@@ -109,6 +109,22 @@ struct RowGeo {
     __device__ static __forceinline__ bool valid(int i, int q, int n4) { return N4 > 0 ? (4 * i + q < N4) : (4 * i + q < n4); }
 };
 
+// Forward aggregation: lane = FEATURE group.  Lane l owns the float2s l + 32*i (i = 0, 1, 2) of the staged row and keeps the
+// accumulators of ALL heads for them (8 x 3 float2 = 48 fp32).  Per edge the warp then reads the 672-byte row exactly once
+// (3 conflict-free LDS.64 = 6 shared-memory wavefronts) plus the 8 weights (broadcast), against 44 wavefronts when every head
+// re-reads the row -- the (head, quarter) layout had the forward at 81 % of the shared-memory pipe (ncu, round 2).
+template <int N4>
+struct FeatGeo {
+    static constexpr int NI = N4 > 0 ? (2 * N4 + 31) / 32 : MAX_K / 64;       // float2s per lane
+    __device__ static __forceinline__ bool valid(int i, int lane, int n2) { return N4 > 0 ? (lane + 32 * i < 2 * N4) : (lane + 32 * i < n2); }
+};
+__device__ __forceinline__ float2 lds64(uint32_t addr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+
 // ---- per-warp ring of staged x rows ------------------------------------------------------------------------------
 // Rows must be 16-byte aligned and zero-padded to KP floats (ldx % 4 == 0, ldx >= KP: gnnfd_in_pad_x builds such a copy
 // of an unaligned x): lane 0 hands a whole row to the bulk-copy engine (cp.async.bulk global->shared, mbarrier

@@ -306,22 +306,33 @@ def in_prepare(W, K, xmax, prep):
     _abi.check(_abi.lib().gnnfd_in_prepare(W.data_ptr(), int(K), xmax.data_ptr(), prep.data_ptr(), _stream()))
 
 
+class InAttention:
+    """What the input-space forward saves for the backward: ``alpha [E',H]`` (CSR order, normalised, before dropout; sign bit =
+    LeakyReLU negative region), ``jflag [E']`` (source id | row-end flag), ``rowmax`` / ``rowsum [n_dst,H]``."""
+    __slots__ = ("alpha", "jflag", "rowmax", "rowsum", "a_src", "a_dst")
+
+    def __init__(self, alpha, jflag, rowmax, rowsum, a_src, a_dst):
+        self.alpha, self.jflag, self.rowmax, self.rowsum, self.a_src, self.a_dst = alpha, jflag, rowmax, rowsum, a_src, a_dst
+
+
 def in_fwd(g: GraphCSR, x, a_src, a_dst, negative_slope, prep, keep_mask=None, p_drop=0.0, seed=0):
-    """Aggregation in input space -> (zimg, rowmax, rowsum)."""
+    """Aggregation in input space -> (zimg, InAttention)."""
     L = _abi.lib()
     dev, K = x.device, x.size(1)
     zb = in_sizes(g.n_dst, K)[1]
     zimg = _aligned_u8(zb, dev)
     rowmax = torch.empty(g.n_dst, 8, dtype=torch.float32, device=dev)
     rowsum = torch.empty(g.n_dst, 8, dtype=torch.float32, device=dev)
+    alpha = torch.empty(max(g.n_edges, 1), 8, dtype=torch.float32, device=dev)
+    jflag = torch.empty(max(g.n_edges, 1), dtype=torch.int32, device=dev)
     nb = C.c_size_t()
     _abi.check(L.gnnfd_in_fwd_workspace_bytes(g.ref(), C.byref(nb)))
     ws = _ws(nb.value, dev)
     _abi.check(L.gnnfd_in_fwd(g.ref(), x.data_ptr(), x.stride(0), K, a_src.data_ptr(), a_dst.data_ptr(),
                               float(negative_slope), _abi.ptr(keep_mask), float(p_drop), int(seed), prep.data_ptr(),
-                              zimg.data_ptr(),
-                              rowmax.data_ptr(), rowsum.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-    return zimg, rowmax, rowsum
+                              zimg.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), alpha.data_ptr(), jflag.data_ptr(),
+                              ws.data_ptr(), ws.numel(), _stream()))
+    return zimg, InAttention(alpha, jflag, rowmax, rowsum, a_src, a_dst)
 
 
 def in_out(zimg, n, K, prep, bias, act=_abi.ACT_NONE, post_scale=None, post_shift=None, residual=None):
@@ -335,7 +346,7 @@ def in_out(zimg, n, K, prep, bias, act=_abi.ACT_NONE, post_scale=None, post_shif
 IN_GD_BLOCK_BYTES = 8 << 30     # upper bound of the Gd buffer of the backward edge pass (rows are processed in blocks)
 
 
-def in_bwd_edges(g: GraphCSR, x, a_src, a_dst, rowmax, rowsum, d_out, prep, negative_slope, keep_mask=None, p_drop=0.0,
+def in_bwd_edges(g: GraphCSR, x, att: "InAttention", d_out, prep, negative_slope, keep_mask=None, p_drop=0.0,
                  n_blocks=None, seed=0):
     """Gd GEMM + backward edge pass, in blocks of destination rows.  Returns dz [E',H] (source-major) and da_dst."""
     L = _abi.lib()
@@ -359,8 +370,8 @@ def in_bwd_edges(g: GraphCSR, x, a_src, a_dst, rowmax, rowsum, d_out, prep, nega
             _abi.check(L.gnnfd_in_bwd_gd(d_out[r_lo:r_hi].data_ptr(), r_hi - r_lo, K, prep.data_ptr(), gd.data_ptr(),
                                          gws.data_ptr(), gws.numel(), _stream()))
         phase = 1 | (2 if bi == len(blocks) - 1 else 0)
-        _abi.check(L.gnnfd_in_bwd_edges(g.ref(), x.data_ptr(), x.stride(0), K, a_src.data_ptr(), a_dst.data_ptr(),
-                                        rowmax.data_ptr(), rowsum.data_ptr(), gd.data_ptr(), r_lo, i_lo, i_hi, r_lo, r_hi,
+        _abi.check(L.gnnfd_in_bwd_edges(g.ref(), x.data_ptr(), x.stride(0), K, att.a_src.data_ptr(), att.a_dst.data_ptr(),
+                                        att.rowmax.data_ptr(), att.rowsum.data_ptr(), gd.data_ptr(), r_lo, i_lo, i_hi, r_lo, r_hi,
                                         float(negative_slope), _abi.ptr(keep_mask), float(p_drop), int(seed), dz.data_ptr(),
                                         da_dst.data_ptr(), ws.data_ptr(), ws.numel(), phase, _stream()))
     return dz, da_dst
@@ -412,9 +423,10 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
             xmax = torch.zeros(16, dtype=torch.float32, device=x.device)
             a_src, a_dst = in_logits(x, W, a_s, a_d, prep, xmax)
             in_prepare(W, K, xmax, prep)
-            zimg, rowmax, rowsum = in_fwd(g, x, a_src, a_dst, negative_slope, prep, keep_mask, p_drop, seed)
+            zimg, att = in_fwd(g, x, a_src, a_dst, negative_slope, prep, keep_mask, p_drop, seed)
             out = in_out(zimg, g.n_dst, K, prep, bias)
-        ctx.save_for_backward(x, W, a_s, a_d, a_src, a_dst, rowmax, rowsum, keep_mask, zimg, prep)
+        rowmax, rowsum = att.rowmax, att.rowsum
+        ctx.save_for_backward(x, W, a_s, a_d, a_src, a_dst, rowmax, rowsum, att.alpha, att.jflag, keep_mask, zimg, prep)
         ctx.g, ctx.slope, ctx.p, ctx.seed = g, negative_slope, p_drop, seed
         ctx.has_bias = bias is not None
         ctx.att_shape = att_src.shape
@@ -425,7 +437,7 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, *unused):
-        x, W, a_s, a_d, a_src, a_dst, rowmax, rowsum, keep_mask, zimg, prep = ctx.saved_tensors
+        x, W, a_s, a_d, a_src, a_dst, rowmax, rowsum, alpha, jflag, keep_mask, zimg, prep = ctx.saved_tensors
         g = ctx.g
         if not g.has_csc:
             raise RuntimeError("backward needs the CSC twin; build the graph with build_csc=True")
@@ -433,8 +445,8 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
             raise RuntimeError("the input-space formulation computes no gradient w.r.t. x (first layer only)")
         d_out = d_out.contiguous().float()
         with torch.cuda.device(x.device):
-            dz, da_dst = in_bwd_edges(g, x, a_src, a_dst, rowmax, rowsum, d_out, prep, ctx.slope, keep_mask, ctx.p,
-                                      seed=ctx.seed)
+            att = InAttention(alpha, jflag, rowmax, rowsum, a_src, a_dst)
+            dz, da_dst = in_bwd_edges(g, x, att, d_out, prep, ctx.slope, keep_mask, ctx.p, seed=ctx.seed)
             da_src = in_dasrc(g, dz)
             dW, datt_src, datt_dst, dbias = in_bwd_params(zimg, d_out, x, W, a_s, a_d, da_src, da_dst, prep)
         return (None, dW, datt_src.view(ctx.att_shape), datt_dst.view(ctx.att_shape), dbias if ctx.has_bias else None,

@@ -187,7 +187,7 @@ class GATConv(nn.Module):
                 xmax = torch.zeros(16, dtype=torch.float32, device=x.device)
                 a_src, a_dst = Fn.in_logits(x16, W, a_s, a_d, prep, xmax)
                 Fn.in_prepare(W, K, xmax, prep)
-                zimg, _, _ = Fn.in_fwd(g, x16, a_src, a_dst, self.negative_slope, prep)
+                zimg, _ = Fn.in_fwd(g, x16, a_src, a_dst, self.negative_slope, prep)
                 return Fn.in_out(zimg, g.n_dst, K, prep, self.bias, act, scale, shift, res)
             x = x if x.stride(1) == 1 else x.contiguous()
             xw, a_src, a_dst = Fn.project_fwd(x, W, a_s, a_d, H, C, self.feature_dtype, self.gemm_algo)

@@ -517,12 +517,12 @@ class InputSpacePartition(DstRangePartition):
                 a_src_full = a_src_own
         Fn.in_prepare(W, K, xmax, prep)
         if marks: marks[1].record()
-        zimg, rowmax, rowsum = Fn.in_fwd(g, x_full, a_src_full, a_dst_own, 0.2, prep)
+        zimg, att = Fn.in_fwd(g, x_full, a_src_full, a_dst_own, 0.2, prep)
         if marks: marks[2].record()
         out = Fn.in_out(zimg, n, K, prep, bias)
         if marks: marks[3].record()
         # backward: edge pass is local; the partial da_src over ALL source positions is reduce-scattered to the owners
-        dz, da_dst = Fn.in_bwd_edges(g, x_full, a_src_full, a_dst_own, rowmax, rowsum, d_out, prep, 0.2)
+        dz, da_dst = Fn.in_bwd_edges(g, x_full, att, d_out, prep, 0.2)
         if marks: marks[4].record()
         if px is not None:
             # the partial stays in this rank's symmetric buffer; every owner pulls (or switch-reduces) its own row range

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 14
+#define GNNFD_ABI_VERSION 15
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -269,11 +269,14 @@ int gnnfd_in_logits(const float* x, int64_t ldx, int64_t N, int64_t K, const flo
                     gnnfd_stream_t stream);
 int gnnfd_in_prepare(const float* W, int64_t K, const float* xmax, void* prep, gnnfd_stream_t stream);
 int gnnfd_in_fwd_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes);
-/* edge_update + message + aggregate in input space -> zimg, rowmax / rowsum [n_dst,H] (as gnnfd_gat_fwd saves them). */
+/* edge_update + message + aggregate in input space -> zimg, rowmax / rowsum [n_dst,H] (as gnnfd_gat_fwd saves them).
+ * Two passes: the attention pass writes alpha [E',H] (fp32, CSR order, normalised, BEFORE dropout; the sign bit marks logits
+ * in LeakyReLU's negative region) and jflag [E'] (int32: source id | row-end flag << 31); the feature pass streams the edges
+ * with those.  alpha and jflag are outputs the caller keeps for gnnfd_in_bwd_edges. */
 int gnnfd_in_fwd(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src,
                  const float* a_dst, float negative_slope, const uint8_t* keep_mask, float p_drop,
-                 uint64_t dropout_seed, const void* prep, void* zimg, float* rowmax, float* rowsum, void* ws,
-                 size_t ws_bytes, gnnfd_stream_t stream);
+                 uint64_t dropout_seed, const void* prep, void* zimg, float* rowmax, float* rowsum, float* alpha,
+                 int32_t* jflag, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
 /* out [n,C] = act((Z W_r / H + bias) * post_scale + post_shift) + residual  (epilogue as gnnfd_gat_fwd_fused). */
 int gnnfd_in_out(const void* zimg, int64_t n, int64_t K, const void* prep, const float* bias, int act,
                  const float* post_scale, const float* post_shift, const float* residual, float* out,

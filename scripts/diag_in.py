@@ -80,7 +80,8 @@ def case(name, N, K, ei, seed=0, n_blocks=None, keep=None, p=0.0):
     Fn.in_prepare(Wg, K, xmax, prep)
     scal = prep[:16].view(torch.float32).cpu()
     print("  scal", scal.tolist())
-    zimg, rowmax, rowsum = Fn.in_fwd(g, xg, a_src, a_dst, 0.2, prep, keep_g, p)
+    zimg, att = Fn.in_fwd(g, xg, a_src, a_dst, 0.2, prep, keep_g, p)
+    rowmax, rowsum = att.rowmax, att.rowsum
     torch.cuda.synchronize()
     Z = decode_zimg(zimg, N, K, float(scal[0]))
     err("Z", Z[:, :, :K], Z_ref)
@@ -101,7 +102,7 @@ def case(name, N, K, ei, seed=0, n_blocks=None, keep=None, p=0.0):
     err("Gd", gd.view(N, H, KP)[:, :, :K], Gd_ref)
     if KP > K:
         print("  Gd pad max", float(gd.view(N, H, KP)[:, :, K:].abs().max()))
-    dz, da_dst = Fn.in_bwd_edges(g, xg, a_src, a_dst, rowmax, rowsum, dog, prep, 0.2, keep_g, p, n_blocks=n_blocks)
+    dz, da_dst = Fn.in_bwd_edges(g, xg, att, dog, prep, 0.2, keep_g, p, n_blocks=n_blocks)
     torch.cuda.synchronize()
     # closed form pieces in fp64 (with dropout: d_alpha path scaled by keep/(1-p))
     dO_h = (d_out.double() / H)[:, None, :].expand(N, H, C)
@@ -143,10 +144,10 @@ def big_case(N=200_000, E=2_000_000, K=166):
     xmax = torch.zeros(16, device=dev)
     a_src, a_dst = Fn.in_logits(xg, Wg, asg, adg, prep, xmax)
     Fn.in_prepare(Wg, K, xmax, prep)
-    zimg, rowmax, rowsum = Fn.in_fwd(g, xg, a_src, a_dst, 0.2, prep)
+    zimg, att = Fn.in_fwd(g, xg, a_src, a_dst, 0.2, prep)
     out = Fn.in_out(zimg, N, K, prep, bg)
     err("out", out, ro)
-    dz, da_dst = Fn.in_bwd_edges(g, xg, a_src, a_dst, rowmax, rowsum, d_out, prep, 0.2)
+    dz, da_dst = Fn.in_bwd_edges(g, xg, att, d_out, prep, 0.2)
     da_src = Fn.in_dasrc(g, dz)
     err("da_src", da_src, cf["da_src"]); err("da_dst", da_dst, cf["da_dst"])
     dW, ds, dd, db = Fn.in_bwd_params(zimg, d_out, xg, Wg, asg, adg, da_src, da_dst, prep)

@@ -53,11 +53,11 @@ def test_blocked_backward_matches_unblocked():
     xmax = torch.zeros(16, device="cuda")
     a_src, a_dst = Fn.in_logits(xg, W, asf, adf, prep, xmax)
     Fn.in_prepare(W, K, xmax, prep)
-    zimg, rowmax, rowsum = Fn.in_fwd(g, xg, a_src, a_dst, 0.2, prep)
+    zimg, att = Fn.in_fwd(g, xg, a_src, a_dst, 0.2, prep)
     d_out = torch.randn(N, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) / N
-    ref = Fn.in_bwd_edges(g, xg, a_src, a_dst, rowmax, rowsum, d_out, prep, 0.2, n_blocks=1)
+    ref = Fn.in_bwd_edges(g, xg, att, d_out, prep, 0.2, n_blocks=1)
     for nb in (2, 5):
-        got = Fn.in_bwd_edges(g, xg, a_src, a_dst, rowmax, rowsum, d_out, prep, 0.2, n_blocks=nb)
+        got = Fn.in_bwd_edges(g, xg, att, d_out, prep, 0.2, n_blocks=nb)
         assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1])
 
 
