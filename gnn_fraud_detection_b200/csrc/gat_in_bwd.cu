@@ -27,6 +27,70 @@ constexpr int IN_UNROLL_BWD = GNNFD_IN_UNROLL_BWD;
 bool in_x_ok(const float* x, int64_t ldx, int KP);   // gat_in_fwd.cu
 
 
+constexpr int BWD_SLOTS = 6;      // 6 row slots: with the Gd buffer that still fits 4 CTAs (16 warps) per SM in shared memory
+using BwdRing = InRingT<BWD_SLOTS>;
+
+// Staging of one chunk (lane = edge) from what the forward's attention pass saved: alpha (sign bit = LeakyReLU negative
+// region) and jflag (source id | row end).  No logit gathers, no exp, no row statistics.
+// bits layout per staged edge: [0,8) LeakyReLU-positive, [8,16) dropout keep, [16,21) first lane of the row, [21,26) last lane
+// of the row (packs only), bit 26 = this edge is the last of its row.
+template <bool DROPOUT>
+__device__ __forceinline__ void stage_bwd_chunk(const BwdChunk& c, bool pack, const float* __restrict__ alpha,
+                                                const int32_t* __restrict__ jflag, const int32_t* __restrict__ perm, KeepMask keep,
+                                                float* p_s, int* j_s, int* bits_s, int lane)
+{
+    int jf = 0, bits = 0;
+    float w[H];
+    if (lane < c.n) {
+        const int e = c.beg + lane;
+        jf = jflag[e];
+        load_vecH<H>(alpha + int64_t(e) * H, w);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            bits |= int((__float_as_uint(w[h]) >> 31) ^ 1u) << h;
+            w[h] = fabsf(w[h]);
+        }
+        if (DROPOUT) bits |= int(keep.bits(perm[e], H)) << 8;
+        else bits |= 0xff00;
+    } else {
+#pragma unroll
+        for (int h = 0; h < H; ++h) w[h] = 0.f;
+    }
+    const unsigned lastmask = __ballot_sync(FULL, jf < 0);
+    if (lane < c.n) {
+        bits |= int(jf < 0) << 26;
+        if (pack) {
+            const unsigned below = lastmask & ((1u << lane) - 1u);
+            const int sa = below ? 32 - __clz(below) : 0;
+            const int sb = __ffs(lastmask >> lane) - 1 + lane;
+            bits |= (sa << 16) | (sb << 21);
+        }
+    }
+    store_vecH<H>(p_s + lane * H, w);
+    j_s[lane] = jf & 0x7fffffff;
+    bits_s[lane] = bits;
+    __syncwarp();
+}
+
+// second sweep of a long row: dz = slope' * (u - alpha * t); lane-local partial of da_dst
+__device__ __forceinline__ void in_sweep2(int beg, int end, const int32_t* __restrict__ csr2csc, const float* __restrict__ alpha,
+                                          float slope, const float (&t)[H], int lane, float* __restrict__ dz, float (&dad)[H])
+{
+    for (int e = beg + lane; e < end; e += 32) {
+        float a[H], u[H], o[H];
+        const int64_t pos = csr2csc[e];          // edge gradients live in source-major order
+        load_vecH<H>(alpha + int64_t(e) * H, a);
+        load_vecH<H>(dz + pos * H, u);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const float sl = (__float_as_uint(a[h]) >> 31) ? slope : 1.f;
+            o[h] = sl * (u[h] - fabsf(a[h]) * t[h]);
+            dad[h] += o[h];
+        }
+        store_vecH<H>(dz + pos * H, o);
+    }
+}
+
 // per-warp scratch beyond the ring: dal_s [32][H] floats, bits_s [2][32] ints, the Gd row buffer [F] floats
 __host__ __device__ inline int bwd_extra_bytes(int F) { return 32 * H * 4 + 2 * 32 * 4 + F * 4; }
 
@@ -86,12 +150,10 @@ struct GdBuf {
 // HUB = false: whole rows (optionally packs of short rows), results go to da_dst.  HUB = true: one (row, range) segment,
 // the partial t of the segment goes to part_t[chunk_id]; the second sweep is a separate kernel.
 template <int N4, bool DROPOUT, bool PACK, bool HUB>
-__device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, GdBuf<N4>& gdb, const int32_t* __restrict__ rowptr,
-                                              const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                                              const int32_t* __restrict__ csr2csc, const float* __restrict__ a_src,
-                                              const float* __restrict__ a_dst, const float* __restrict__ rowmax,
-                                              const float* __restrict__ rowsum, float slope, KeepMask keep,
-                                              float keep_scale, float* __restrict__ dz, float* __restrict__ da_dst,
+__device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, BwdRing& ring, GdBuf<N4>& gdb, const int32_t* __restrict__ rowptr,
+                                              const int32_t* __restrict__ perm, const int32_t* __restrict__ csr2csc,
+                                              const float* __restrict__ alpha_g, const int32_t* __restrict__ jflag, float slope,
+                                              KeepMask keep, float keep_scale, float* __restrict__ dz, float* __restrict__ da_dst,
                                               float* __restrict__ part_t, int chunk_id, int lane)
 {
     using RG = RowGeo<N4>;
@@ -109,12 +171,9 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
         return cur.next(rowptr, c.row, c.beg, c.n, c.first, c.last, on_empty) ? 1 : 0;
     };
     auto phase_a = [&](const BwdChunk& c, int kind, int kk, int buf) {
-        if (PACK && kind == 2)   // CONCAT = true: the dO-row prefetch of the projected-feature kernel does not apply here
-            bwd_phase_a_pack<GI, true, DROPOUT>(c.row, c.beg, c.n, kk, la, lb, col, perm, a_src, a_dst, rowmax, rowsum, nullptr,
-                                                slope, keep, ring.p_s + buf * 32 * H, ring.j_s + buf * 32, bits_s + buf * 32, lane);
-        else
-            bwd_phase_a<GI, DROPOUT>(c, col, perm, a_src, a_dst, rowmax, rowsum, slope, keep, ring.p_s + buf * 32 * H,
-                                     ring.j_s + buf * 32, bits_s + buf * 32, lane);
+        (void)kk;
+        stage_bwd_chunk<DROPOUT>(c, PACK && kind == 2, alpha_g, jflag, perm, keep, ring.p_s + buf * 32 * H, ring.j_s + buf * 32,
+                                 bits_s + buf * 32, lane);
     };
     kind0 = next(c0, k0);
     if (!kind0) return;
@@ -248,12 +307,10 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
                         if (lane == 0) store_vecH<H>(part_t + int64_t(chunk_id) * H, trow);
                     } else {
                         __syncwarp();
-                        RowStat<H> r;
-                        load_row_stat<H>(r, c0.row, a_dst, rowmax, rowsum);
                         float dad[H];
 #pragma unroll
                         for (int hh = 0; hh < H; ++hh) dad[hh] = 0.f;
-                        dst_sweep2<GI>(r, row_beg, c0.beg + c0.n, col, csr2csc, a_src, slope, trow, lane, dz, H, dad);
+                        in_sweep2(row_beg, c0.beg + c0.n, csr2csc, alpha_g, slope, trow, lane, dz, dad);
 #pragma unroll
                         for (int hh = 0; hh < H; ++hh) dad[hh] = warp_sum(dad[hh]);
                         if (lane == 0) store_vecH<H>(da_dst + int64_t(c0.row) * H, dad);
@@ -276,7 +333,7 @@ __device__ __forceinline__ void in_bwd_stream(ChunkCursor& cur, InRing& ring, Gd
 }
 
 template <int N4>
-__device__ __forceinline__ void gdbuf_init(GdBuf<N4>& gdb, InRing& ring, const float* gd, int F, int KP)
+__device__ __forceinline__ void gdbuf_init(GdBuf<N4>& gdb, BwdRing& ring, const float* gd, int F, int KP)
 {
     gdb.buf_u32 = st_smem_u32(ring.extra + 32 * H * 4 + 2 * 32 * 4);
     gdb.bar = ring.spare_bar();
@@ -285,12 +342,15 @@ __device__ __forceinline__ void gdbuf_init(GdBuf<N4>& gdb, InRing& ring, const f
     gdb.KP = KP;
 }
 
+#ifndef GNNFD_IN_BWD_CTAS
+#define GNNFD_IN_BWD_CTAS 4
+#endif
+
 template <int N4, bool DROPOUT, bool PACK>
-__global__ void __launch_bounds__(IN_THREADS, 3)
-gat_in_bwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                 const int32_t* __restrict__ csr2csc, const float* __restrict__ x, int64_t ldx, int KP,
-                 const float* __restrict__ a_src, const float* __restrict__ a_dst, const float* __restrict__ rowmax,
-                 const float* __restrict__ rowsum, const float* __restrict__ gd, gnnfd_item_plan_t items, int item_lo,
+__global__ void __launch_bounds__(IN_THREADS, GNNFD_IN_BWD_CTAS)
+gat_in_bwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, const int32_t* __restrict__ csr2csc,
+                 const float* __restrict__ x, int64_t ldx, int KP, const float* __restrict__ alpha,
+                 const int32_t* __restrict__ jflag, const float* __restrict__ gd, gnnfd_item_plan_t items, int item_lo,
                  int item_hi, int hub_threshold, float slope, KeepMask keep, float keep_scale,
                  float* __restrict__ dz, float* __restrict__ da_dst)
 {
@@ -299,25 +359,23 @@ gat_in_bwd_items(const int32_t* __restrict__ rowptr, const int32_t* __restrict__
     const int item = item_lo + blockIdx.x * IN_WARPS + warp;
     if (item >= item_hi) return;
     const int F = H * KP;
-    InRing ring;
-    ring.init(smem + warp * in_warp_bytes(KP, bwd_extra_bytes(F)), x, ldx, KP, lane);
+    BwdRing ring;
+    ring.init(smem + warp * in_warp_bytes(KP, bwd_extra_bytes(F), BWD_SLOTS), x, ldx, KP, lane);
     GdBuf<N4> gdb;
     gdbuf_init(gdb, ring, gd, F, KP);
     ChunkCursor cur;
     cur.start_rows(items.item_start[item], items.item_start[item + 1], hub_threshold);
-    in_bwd_stream<N4, DROPOUT, PACK, false>(cur, ring, gdb, rowptr, col, perm, csr2csc, a_src, a_dst, rowmax, rowsum, slope, keep,
-                                            keep_scale, dz, da_dst, nullptr, 0, lane);
+    in_bwd_stream<N4, DROPOUT, PACK, false>(cur, ring, gdb, rowptr, perm, csr2csc, alpha, jflag, slope, keep, keep_scale, dz, da_dst,
+                                            nullptr, 0, lane);
 }
 
 // hub rows, step 1: one warp per chunk -- first sweep, partial t (rows outside [row_lo, row_hi) belong to another block)
 template <int N4, bool DROPOUT>
-__global__ void __launch_bounds__(IN_THREADS, 3)
-gat_in_bwd_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const int32_t* __restrict__ perm,
-                const int32_t* __restrict__ csr2csc, const float* __restrict__ x, int64_t ldx, int KP,
-                const float* __restrict__ a_src, const float* __restrict__ a_dst, const float* __restrict__ rowmax,
-                const float* __restrict__ rowsum, const float* __restrict__ gd, gnnfd_hub_plan_t plan, int row_lo, int row_hi,
-                float slope, KeepMask keep, float keep_scale, float* __restrict__ dz,
-                float* __restrict__ part_t)
+__global__ void __launch_bounds__(IN_THREADS, GNNFD_IN_BWD_CTAS)
+gat_in_bwd_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ perm, const int32_t* __restrict__ csr2csc,
+                const float* __restrict__ x, int64_t ldx, int KP, const float* __restrict__ alpha,
+                const int32_t* __restrict__ jflag, const float* __restrict__ gd, gnnfd_hub_plan_t plan, int row_lo, int row_hi,
+                float slope, KeepMask keep, float keep_scale, float* __restrict__ dz, float* __restrict__ part_t)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -329,14 +387,37 @@ gat_in_bwd_hub1(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ 
     const int beg = rowptr[i] + (c - plan.hub_chunk_ptr[slot]) * plan.chunk;
     const int end = min(rowptr[i + 1], beg + plan.chunk);
     const int F = H * KP;
-    InRing ring;
-    ring.init(smem + warp * in_warp_bytes(KP, bwd_extra_bytes(F)), x, ldx, KP, lane);
+    BwdRing ring;
+    ring.init(smem + warp * in_warp_bytes(KP, bwd_extra_bytes(F), BWD_SLOTS), x, ldx, KP, lane);
     GdBuf<N4> gdb;
     gdbuf_init(gdb, ring, gd, F, KP);
     ChunkCursor cur;
     cur.start_segment(i, beg, end);
-    in_bwd_stream<N4, DROPOUT, false, true>(cur, ring, gdb, rowptr, col, perm, csr2csc, a_src, a_dst, rowmax, rowsum, slope, keep,
-                                            keep_scale, dz, nullptr, part_t, c, lane);
+    in_bwd_stream<N4, DROPOUT, false, true>(cur, ring, gdb, rowptr, perm, csr2csc, alpha, jflag, slope, keep, keep_scale, dz, nullptr,
+                                            part_t, c, lane);
+}
+
+// hub rows, step 2: second sweep of every chunk with the row's total t, partial da_dst
+__global__ void __launch_bounds__(ROW_THREADS)
+gat_in_bwd_hub2(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr2csc, const float* __restrict__ alpha,
+                gnnfd_hub_plan_t plan, float slope, const float* __restrict__ t_total, float* __restrict__ dz,
+                float* __restrict__ part_dad)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = blockIdx.x * ROW_WARPS + warp;
+    if (c >= plan.n_chunk) return;
+    const int slot = plan.chunk_hub[c];
+    const int64_t i = plan.hub_row[slot];
+    const int beg = rowptr[i] + (c - plan.hub_chunk_ptr[slot]) * plan.chunk;
+    const int end = min(rowptr[i + 1], beg + plan.chunk);
+    float t[H], dad[H];
+    load_vecH<H>(t_total + int64_t(slot) * H, t);      // the same total in every chunk of the row
+#pragma unroll
+    for (int h = 0; h < H; ++h) dad[h] = 0.f;
+    in_sweep2(beg, end, csr2csc, alpha, slope, t, lane, dz, dad);
+#pragma unroll
+    for (int h = 0; h < H; ++h) dad[h] = warp_sum(dad[h]);
+    if (lane == 0) store_vecH<H>(part_dad + int64_t(c) * H, dad);
 }
 
 template <class Kn>
@@ -365,8 +446,8 @@ int gnnfd_in_bwd_edges_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes)
  * (= rows [row_lo, row_hi), which must be the rows those items cover; pass 0, n_items, 0, n_dst for everything).
  * gd holds the Gd rows of [gd_row0, ...) with leading dimension F.  phase bit 0: process the row block (items + first
  * hub sweep); bit 1: finish the hub rows (second sweep; after the LAST block, with the same ws). */
-int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src,
-                       const float* a_dst, const float* rowmax, const float* rowsum, const float* gd, int64_t gd_row0,
+int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* alpha,
+                       const int32_t* jflag, const float* gd, int64_t gd_row0,
                        int64_t item_lo, int64_t item_hi, int64_t row_lo, int64_t row_hi, float negative_slope,
                        const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed, float* dz, float* da_dst, void* ws, size_t ws_bytes,
                        int phase, gnnfd_stream_t stream)
@@ -375,7 +456,8 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
     if (rc) return rc;
     GNNFD_REQUIRE(K >= 1 && K <= MAX_K, GNNFD_ERR_ARG, "in_bwd_edges: bad shape (K <= %d)", MAX_K);
     if (g->n_dst == 0) return GNNFD_OK;
-    GNNFD_REQUIRE(x && a_src && a_dst && rowmax && rowsum && gd && da_dst, GNNFD_ERR_ARG, "in_bwd_edges: NULL tensor");
+    GNNFD_REQUIRE(x && gd && da_dst, GNNFD_ERR_ARG, "in_bwd_edges: NULL tensor");
+    GNNFD_REQUIRE(g->n_edges == 0 || (alpha && jflag), GNNFD_ERR_ARG, "in_bwd_edges: NULL alpha / jflag (outputs of gnnfd_in_fwd)");
     GNNFD_REQUIRE(g->n_edges == 0 || (dz && g->csr2csc), GNNFD_ERR_ARG, "in_bwd_edges: dz / csr2csc is NULL");
     GNNFD_REQUIRE(p_drop >= 0.f && p_drop <= 0.9f, GNNFD_ERR_ARG, "in_bwd_edges: dropout p must be in [0,0.9]");
     GNNFD_REQUIRE(g->items_dst.n_items > 0 && g->items_dst.item_start, GNNFD_ERR_ARG, "in_bwd_edges: no work-item plan over rowptr");
@@ -391,7 +473,7 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
     const int thr = g->hub_dst.n_hub > 0 ? g->hub_dst.threshold : INT_MAX;
     GNNFD_REQUIRE(in_x_ok(x, ldx, d.KP), GNNFD_ERR_ARG,
                   "in_bwd_edges: x rows must be 16-byte aligned and zero-padded to %d floats (gnnfd_in_pad_x)", d.KP);
-    const int smem = IN_WARPS * in_warp_bytes(d.KP, bwd_extra_bytes(d.F));
+    const int smem = IN_WARPS * in_warp_bytes(d.KP, bwd_extra_bytes(d.F), BWD_SLOTS);
     const float* gd0 = gd - gd_row0 * d.F;          // indexed by global destination row
     const gnnfd_hub_plan_t& pl = g->hub_dst;
     float *part_t = nullptr, *part_dad = nullptr, *t_total = nullptr;
@@ -414,15 +496,14 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
 #define GNNFD_IN_BWD(NN, DD, PP)                                                                                       \
     rc = in_set_smem_bwd(gat_in_bwd_items<NN, DD, PP>, smem);                                                          \
     if (rc) return rc;                                                                                                 \
-    gat_in_bwd_items<NN, DD, PP><<<grid, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, x, ldx, d.KP, a_src, \
-                                                                 a_dst, rowmax, rowsum, gd0, g->items_dst, (int)item_lo,   \
-                                                                 (int)item_hi, thr, negative_slope, keep, ks, dz, da_dst)
+    gat_in_bwd_items<NN, DD, PP><<<grid, IN_THREADS, smem, st>>>(g->rowptr, g->perm, g->csr2csc, x, ldx, d.KP, alpha, jflag, gd0, \
+                                                                 g->items_dst, (int)item_lo, (int)item_hi, thr, negative_slope,  \
+                                                                 keep, ks, dz, da_dst)
 #define GNNFD_IN_HUB1(NN, DD)                                                                                          \
     rc = in_set_smem_bwd(gat_in_bwd_hub1<NN, DD>, smem);                                                               \
     if (rc) return rc;                                                                                                 \
-    gat_in_bwd_hub1<NN, DD><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->col, g->perm, g->csr2csc, x, ldx, d.KP, a_src, a_dst, \
-                                                          rowmax, rowsum, gd0, pl, (int)row_lo, (int)row_hi, negative_slope, \
-                                                          keep, ks, dz, part_t)
+    gat_in_bwd_hub1<NN, DD><<<gc, IN_THREADS, smem, st>>>(g->rowptr, g->perm, g->csr2csc, x, ldx, d.KP, alpha, jflag, gd0, pl,   \
+                                                          (int)row_lo, (int)row_hi, negative_slope, keep, ks, dz, part_t)
 #define GNNFD_IN_BWD_ALL(NN)                                                                                           \
     if (pack) { if (drop) { GNNFD_IN_BWD(NN, true, true); } else { GNNFD_IN_BWD(NN, false, true); } }                  \
     else      { if (drop) { GNNFD_IN_BWD(NN, true, false); } else { GNNFD_IN_BWD(NN, false, false); } }                \
@@ -442,8 +523,7 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
         const unsigned gh = (unsigned)((pl.n_hub + ROW_WARPS - 1) / ROW_WARPS);
         const unsigned gc2 = (unsigned)((pl.n_chunk + ROW_WARPS - 1) / ROW_WARPS);
         gat_hub_chunk_sum<H, false><<<gh, ROW_THREADS, 0, st>>>(pl, part_t, t_total);
-        gat_bwd_dst_hub2<GI><<<gc2, ROW_THREADS, 0, st>>>(g->rowptr, g->col, g->csr2csc, a_src, a_dst, rowmax, rowsum, pl,
-                                                          negative_slope, t_total, dz, H, part_dad);
+        gat_in_bwd_hub2<<<gc2, ROW_THREADS, 0, st>>>(g->rowptr, g->csr2csc, alpha, pl, negative_slope, t_total, dz, part_dad);
         gat_hub_chunk_sum<H, true><<<gh, ROW_THREADS, 0, st>>>(pl, part_dad, da_dst);
         g_launches += 3;
     }

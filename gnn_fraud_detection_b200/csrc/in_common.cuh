@@ -131,12 +131,12 @@ __device__ __forceinline__ float2 lds64(uint32_t addr)
 // complete_tx).  Per-warp layout:  [R slots of KP*4 bytes][p_s: 2 x 32 x H floats][j_s: 2 x 32 ints][R+1 mbarriers][extra]
 constexpr int IN_WARPS = 4;
 constexpr int IN_THREADS = IN_WARPS * 32;
-constexpr int IN_R = 8, IN_LOG_R = 3;                      // ring slots per warp (power of two)
-constexpr int IN_P_BYTES = 2 * 32 * H * 4, IN_J_BYTES = 2 * 32 * 4, IN_BAR_BYTES = ((IN_R + 1) * 8 + 15) / 16 * 16;
+constexpr int IN_R_MAX = 8;                                // ring slots per warp: 8 (forward) or 4 (backward), a power of two
+constexpr int IN_P_BYTES = 2 * 32 * H * 4, IN_J_BYTES = 2 * 32 * 4, IN_BAR_BYTES = ((IN_R_MAX + 1) * 8 + 15) / 16 * 16;
 
-__host__ __device__ inline int in_warp_bytes(int KP, int extra)
+__host__ __device__ inline int in_warp_bytes(int KP, int extra, int slots = IN_R_MAX)
 {
-    return (IN_R * KP * 4 + IN_P_BYTES + IN_J_BYTES + IN_BAR_BYTES + extra + 127) / 128 * 128;
+    return (slots * KP * 4 + IN_P_BYTES + IN_J_BYTES + IN_BAR_BYTES + extra + 127) / 128 * 128;
 }
 
 __device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes)
@@ -191,7 +191,9 @@ __device__ __forceinline__ void ffma2_vec(float& a0, float& a1, float g0, float 
     asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(c));
 }
 
-struct InRing {
+template <int R_>
+struct InRingT {
+    static constexpr int IN_R = R_;            // any count <= IN_R_MAX (a power of two costs one instruction less per wait)
     uint32_t ring_u32, full_u32, slot;   // shared-space addresses / bytes per slot
     uint8_t* extra;
     float* p_s;      // [2][32*H]
@@ -223,7 +225,7 @@ struct InRing {
     __device__ __forceinline__ void issue(int j, int lane)
     {
         if (lane == 0) {
-            const uint32_t s = uint32_t(issued) & (IN_R - 1);
+            const uint32_t s = uint32_t(issued) % uint32_t(IN_R);
             const uint32_t bar = full_u32 + 8u * s;
             mbar_expect_tx_u32(bar, slot);
             bulk_g2s_u32(ring_u32 + s * slot, x + int64_t(j) * ldx, slot, bar);
@@ -235,7 +237,7 @@ struct InRing {
     {
         if (lane < cnt) {
             const uint32_t n = uint32_t(issued + lane);
-            const uint32_t s = n & (IN_R - 1);
+            const uint32_t s = n % uint32_t(IN_R);
             const uint32_t bar = full_u32 + 8u * s;
             mbar_expect_tx_u32(bar, slot);
             bulk_g2s_u32(ring_u32 + s * slot, x + int64_t(j[lane]) * ldx, slot, bar);
@@ -248,8 +250,8 @@ struct InRing {
     __device__ __forceinline__ uint32_t front_at(int r)
     {
         const uint32_t n = uint32_t(consumed + r);
-        const uint32_t s = n & (IN_R - 1);
-        mbar_wait_u32(full_u32 + 8u * s, (n >> IN_LOG_R) & 1u);
+        const uint32_t s = n % uint32_t(IN_R);
+        mbar_wait_u32(full_u32 + 8u * s, (n / uint32_t(IN_R)) & 1u);
         return ring_u32 + s * slot;
     }
     __device__ __forceinline__ void pop()
@@ -265,6 +267,7 @@ struct InRing {
     }
     __device__ __forceinline__ int room() const { return IN_R - (issued - consumed); }
 };
+using InRing = InRingT<8>;
 
 // arr[h] with a run-time h, without dynamic register indexing
 __device__ __forceinline__ float pick_head(const float (&arr)[H], int h)

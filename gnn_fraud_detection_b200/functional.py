@@ -370,8 +370,8 @@ def in_bwd_edges(g: GraphCSR, x, att: "InAttention", d_out, prep, negative_slope
             _abi.check(L.gnnfd_in_bwd_gd(d_out[r_lo:r_hi].data_ptr(), r_hi - r_lo, K, prep.data_ptr(), gd.data_ptr(),
                                          gws.data_ptr(), gws.numel(), _stream()))
         phase = 1 | (2 if bi == len(blocks) - 1 else 0)
-        _abi.check(L.gnnfd_in_bwd_edges(g.ref(), x.data_ptr(), x.stride(0), K, att.a_src.data_ptr(), att.a_dst.data_ptr(),
-                                        att.rowmax.data_ptr(), att.rowsum.data_ptr(), gd.data_ptr(), r_lo, i_lo, i_hi, r_lo, r_hi,
+        _abi.check(L.gnnfd_in_bwd_edges(g.ref(), x.data_ptr(), x.stride(0), K, att.alpha.data_ptr(), att.jflag.data_ptr(),
+                                        gd.data_ptr(), r_lo, i_lo, i_hi, r_lo, r_hi,
                                         float(negative_slope), _abi.ptr(keep_mask), float(p_drop), int(seed), dz.data_ptr(),
                                         da_dst.data_ptr(), ws.data_ptr(), ws.numel(), phase, _stream()))
     return dz, da_dst

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 15
+#define GNNFD_ABI_VERSION 16
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -289,9 +289,10 @@ int gnnfd_in_bwd_gd(const float* d_out, int64_t n, int64_t K, const void* prep, 
 int gnnfd_in_bwd_edges_workspace_bytes(const gnnfd_graph_t* g, size_t* bytes);
 /* dz [E',H] (source-major order, row csr2csc[e]) and da_dst [n_dst,H] for the destination rows covered by the work items
  * [item_lo, item_hi) = rows [row_lo, row_hi) (0, n_items, 0, n_dst for everything); gd holds the Gd rows from gd_row0 on.
- * phase bit 0: process the block; bit 1: finish the hub rows (after the last block, same ws).  Needs the CSC twin. */
-int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* a_src,
-                       const float* a_dst, const float* rowmax, const float* rowsum, const float* gd,
+ * phase bit 0: process the block; bit 1: finish the hub rows (after the last block, same ws).  Needs the CSC twin.
+ * alpha / jflag: what gnnfd_in_fwd saved (the backward gathers no logits and recomputes no softmax). */
+int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int64_t K, const float* alpha,
+                       const int32_t* jflag, const float* gd,
                        int64_t gd_row0, int64_t item_lo, int64_t item_hi, int64_t row_lo, int64_t row_hi,
                        float negative_slope, const uint8_t* keep_mask, float p_drop, uint64_t dropout_seed,
                        float* dz, float* da_dst, void* ws, size_t ws_bytes, int phase, gnnfd_stream_t stream);
