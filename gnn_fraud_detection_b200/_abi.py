@@ -18,7 +18,7 @@ F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_INPUT = 0, 1, 2, 3
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -105,7 +105,7 @@ SIGNATURES = {
     "gnnfd_in_bwd_dasrc": (_i, [_gp, _vp, _vp, _vp]),
     "gnnfd_in_bwd_params_workspace_bytes": (_i, [_i64, _i64, _szp]),
     "gnnfd_in_bwd_params": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
-                                 _vp]),
+                                 _i, _vp]),
     # model-level fused operators
     "gnnfd_model_ops_workspace_bytes": (_i, [_i64, _szp]),
     "gnnfd_bn_sums": (_i, [_vp, _i64, _i, _vp, _vp, _sz, _vp]),

@@ -871,15 +871,19 @@ int gnnfd_in_bwd_params_workspace_bytes(int64_t n, int64_t K, size_t* bytes)
 }
 
 /* Parameter gradients of the layer from the saved image and the logit gradients of THIS rank's n rows:
- *   dW [H*C, K], datt_src / datt_dst [H*C], dbias [C]   (x, da_src, da_dst, d_out: rows [0, n)). */
+ *   dW [H*C, K], datt_src / datt_dst [H*C], dbias [C]   (x, da_src, da_dst, d_out: rows [0, n)).
+ * phase bit 0: the tensor-core reduction dO^T Z into ws (needs no logit gradients -- across GPUs it runs while da_src is still
+ * being exchanged); bit 1: the node reductions with da_src / da_dst and the final dW (same ws); 3 = both. */
 int gnnfd_in_bwd_params(const void* zimg, const float* d_out, const float* x, int64_t ldx, int64_t n, int64_t K,
                         const float* W, const float* att_src, const float* att_dst, const float* da_src,
                         const float* da_dst, const void* prep, float* dW, float* datt_src, float* datt_dst,
-                        float* dbias, void* ws, size_t ws_bytes, gnnfd_stream_t stream)
+                        float* dbias, void* ws, size_t ws_bytes, int phase, gnnfd_stream_t stream)
 {
     GNNFD_REQUIRE(K >= 1 && K <= MAX_K && n >= 0 && ldx >= K, GNNFD_ERR_ARG, "in_bwd_params: bad shape");
     GNNFD_REQUIRE(W && att_src && att_dst && prep && dW && datt_src && datt_dst && dbias, GNNFD_ERR_ARG, "in_bwd_params: NULL argument");
-    GNNFD_REQUIRE(n == 0 || (zimg && d_out && x && da_src && da_dst), GNNFD_ERR_ARG, "in_bwd_params: NULL tensor");
+    GNNFD_REQUIRE(phase >= 1 && phase <= 3, GNNFD_ERR_ARG, "in_bwd_params: phase must be 1, 2 or 3");
+    GNNFD_REQUIRE(n == 0 || (zimg && d_out && x), GNNFD_ERR_ARG, "in_bwd_params: NULL tensor");
+    GNNFD_REQUIRE(n == 0 || !(phase & 2) || (da_src && da_dst), GNNFD_ERR_ARG, "in_bwd_params: NULL logit gradients");
     size_t need = 0;
     gnnfd_in_bwd_params_workspace_bytes(n, K, &need);
     GNNFD_REQUIRE(ws && ws_bytes >= need, GNNFD_ERR_WORKSPACE, "in_bwd_params: workspace %zu < %zu", ws_bytes, need);
@@ -893,26 +897,31 @@ int gnnfd_in_bwd_params(const void* zimg, const float* d_out, const float* x, in
     float* P = carve<float>(q, size_t(S) * dw_partial_floats(d));
     float* Gm = carve<float>(q, size_t(2) * H * K);
     unsigned* dmax = reinterpret_cast<unsigned*>(carve<float>(q, 16));
-    // datt, dbias and G = [da_src | da_dst]^T x (node reductions over x, shared with the projected-feature path)
-    int rc = in_param_grads_simt(x, ldx, W, da_src, da_dst, d_out, n, K, datt_src, datt_dst, dbias, Gm, p, simt_bytes, st);
-    if (rc) return rc;
     const int64_t pstride = (int64_t)dw_partial_floats(d);
-    GNNFD_CUDA(cudaMemsetAsync(P, 0, size_t(S) * pstride * sizeof(float), st));
-    GNNFD_CUDA(cudaMemsetAsync(dmax, 0, 64, st));
-    if (n > 0) {
-        int64_t blocks = (n * C + 255) / 256;
-        if (blocks > int64_t(sm_count()) * 8) blocks = int64_t(sm_count()) * 8;
-        in_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_out, n * C, dmax);
-        const int64_t tps = (n_tiles + S - 1) / S;
-        GNNFD_CUDA(cudaFuncSetAttribute(in_dw_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3_SMEM));
-        in_dw_gemm<<<2 * S, G3_THREADS, G3_SMEM, st>>>(reinterpret_cast<const uint8_t*>(zimg), d_out,
-                                                       reinterpret_cast<const float*>(dmax), n, d.NKB, d.F, tps, P, pstride);
-        g_launches += 2;
+    if (phase & 1) {
+        // the tensor-core part: slab partials of dO^T Z (needs neither da_src nor da_dst)
+        GNNFD_CUDA(cudaMemsetAsync(P, 0, size_t(S) * pstride * sizeof(float), st));
+        GNNFD_CUDA(cudaMemsetAsync(dmax, 0, 64, st));
+        if (n > 0) {
+            int64_t blocks = (n * C + 255) / 256;
+            if (blocks > int64_t(sm_count()) * 8) blocks = int64_t(sm_count()) * 8;
+            in_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_out, n * C, dmax);
+            const int64_t tps = (n_tiles + S - 1) / S;
+            GNNFD_CUDA(cudaFuncSetAttribute(in_dw_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G3_SMEM));
+            in_dw_gemm<<<2 * S, G3_THREADS, G3_SMEM, st>>>(reinterpret_cast<const uint8_t*>(zimg), d_out,
+                                                           reinterpret_cast<const float*>(dmax), n, d.NKB, d.F, tps, P, pstride);
+            g_launches += 2;
+        }
     }
-    in_dw_finalize<<<(H * C * d.K + 255) / 256, 256, 0, st>>>(P, S, pstride, reinterpret_cast<const float*>(prep),
-                                                             reinterpret_cast<const float*>(dmax), Gm, att_src, att_dst, d.K,
-                                                             d.KP, dW);
-    g_launches += 1;
+    if (phase & 2) {
+        // datt, dbias and G = [da_src | da_dst]^T x (node reductions over x, shared with the projected-feature path)
+        int rc = in_param_grads_simt(x, ldx, W, da_src, da_dst, d_out, n, K, datt_src, datt_dst, dbias, Gm, p, simt_bytes, st);
+        if (rc) return rc;
+        in_dw_finalize<<<(H * C * d.K + 255) / 256, 256, 0, st>>>(P, S, pstride, reinterpret_cast<const float*>(prep),
+                                                                 reinterpret_cast<const float*>(dmax), Gm, att_src, att_dst, d.K,
+                                                                 d.KP, dW);
+        g_launches += 1;
+    }
     GNNFD_LAUNCH_CHECK();
     return GNNFD_OK;
 }

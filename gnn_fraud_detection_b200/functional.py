@@ -385,6 +385,13 @@ def in_dasrc(g: GraphCSR, dz, out=None):
 
 def in_bwd_params(zimg, d_out, x, W, att_src, att_dst, da_src, da_dst, prep):
     """dW, datt_src, datt_dst, dbias from the saved image and the logit gradients of x's rows."""
+    return in_bwd_params_split(zimg, d_out, x, W, att_src, att_dst, prep, _phase=3, _da=(da_src, da_dst))
+
+
+def in_bwd_params_split(zimg, d_out, x, W, att_src, att_dst, prep, _phase=1, _da=None):
+    """The same in two steps: this call enqueues the tensor-core reduction ``dO^T Z`` (which needs no logit gradients) and
+    returns ``finish(da_src, da_dst) -> (dW, datt_src, datt_dst, dbias)`` -- across GPUs the first step runs while ``da_src``
+    is still being exchanged on another stream."""
     L = _abi.lib()
     n, K = x.shape
     dev = x.device
@@ -394,12 +401,23 @@ def in_bwd_params(zimg, d_out, x, W, att_src, att_dst, da_src, da_dst, prep):
     dbias = torch.empty(64, dtype=torch.float32, device=dev)
     nb = C.c_size_t()
     _abi.check(L.gnnfd_in_bwd_params_workspace_bytes(n, K, C.byref(nb)))
-    ws = _ws(nb.value, dev)
-    _abi.check(L.gnnfd_in_bwd_params(zimg.data_ptr(), d_out.data_ptr(), x.data_ptr(), x.stride(0), n, K, W.data_ptr(),
-                                     att_src.data_ptr(), att_dst.data_ptr(), da_src.data_ptr(), da_dst.data_ptr(),
-                                     prep.data_ptr(), dW.data_ptr(), datt_src.data_ptr(), datt_dst.data_ptr(),
-                                     dbias.data_ptr(), ws.data_ptr(), ws.numel(), _stream()))
-    return dW, datt_src, datt_dst, dbias
+    ws = _ws(nb.value, dev) if _phase == 3 else torch.empty(nb.value, dtype=torch.uint8, device=dev)
+
+    def call(phase, da_src, da_dst):
+        _abi.check(L.gnnfd_in_bwd_params(zimg.data_ptr(), d_out.data_ptr(), x.data_ptr(), x.stride(0), n, K, W.data_ptr(),
+                                         att_src.data_ptr(), att_dst.data_ptr(), _abi.ptr(da_src), _abi.ptr(da_dst),
+                                         prep.data_ptr(), dW.data_ptr(), datt_src.data_ptr(), datt_dst.data_ptr(),
+                                         dbias.data_ptr(), ws.data_ptr(), ws.numel(), phase, _stream()))
+
+    if _phase == 3:
+        call(3, *_da)
+        return dW, datt_src, datt_dst, dbias
+    call(1, None, None)
+
+    def finish(da_src, da_dst):
+        call(2, da_src, da_dst)
+        return dW, datt_src, datt_dst, dbias
+    return finish
 
 
 class GATConvInputSpaceFunction(torch.autograd.Function):

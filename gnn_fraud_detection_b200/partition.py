@@ -420,6 +420,7 @@ class PeerExchange:
         self.a_src_peers, self.da_peers, self.xmax_peers = (self._peers(h) for h in self.handles)
         self.da_part.zero_()
         self.xmax.zero_()
+        self.side = torch.cuda.Stream(device=device)          # the da_src exchange runs here, under the dW GEMM
         self.barrier()
 
     def _peers(self, h):
@@ -525,11 +526,20 @@ class InputSpacePartition(DstRangePartition):
         dz, da_dst = Fn.in_bwd_edges(g, x_full, att, d_out, prep, 0.2)
         if marks: marks[4].record()
         if px is not None:
-            # the partial stays in this rank's symmetric buffer; every owner pulls (or switch-reduces) its own row range
+            # the partial stays in this rank's symmetric buffer; every owner pulls (or switch-reduces) its own row range.
+            # The barrier + reduction run on a side stream UNDER the tensor-core part of the weight gradient (dO^T Z),
+            # which does not need da_src.
             Fn.in_dasrc(g, dz, out=px.da_part)
-            px.barrier()
+            if marks: marks[5].record()
             da_src = torch.empty(P, H, dtype=torch.float32, device=dev)
-            Fn.peer_reduce(px.da_peers, lo * H, P * H, da_src, op="sum", use_multicast=px.mode == "multicast")
+            main = torch.cuda.current_stream()
+            px.side.wait_stream(main)
+            with torch.cuda.stream(px.side):
+                px.barrier()
+                Fn.peer_reduce(px.da_peers, lo * H, P * H, da_src, op="sum", use_multicast=px.mode == "multicast")
+            finish = Fn.in_bwd_params_split(zimg, d_out, x_own[:n], W, a_s, a_d, prep)
+            main.wait_stream(px.side)
+            dW, datt_s, datt_d, dbias = finish(da_src[:n], da_dst)
         else:
             da_src_part = Fn.in_dasrc(g, dz)
             if self.world > 1:
@@ -537,8 +547,8 @@ class InputSpacePartition(DstRangePartition):
                 dist.reduce_scatter_tensor(da_src, da_src_part)
             else:
                 da_src = da_src_part
-        if marks: marks[5].record()
-        dW, datt_s, datt_d, dbias = Fn.in_bwd_params(zimg, d_out, x_own[:n], W, a_s, a_d, da_src[:n], da_dst, prep)
+            if marks: marks[5].record()
+            dW, datt_s, datt_d, dbias = Fn.in_bwd_params(zimg, d_out, x_own[:n], W, a_s, a_d, da_src[:n], da_dst, prep)
         if self.world > 1:
             D = H * C
             flat = torch.cat([dW.reshape(-1), datt_s, datt_d, dbias])

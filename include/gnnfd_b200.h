@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 16
+#define GNNFD_ABI_VERSION 17
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -299,11 +299,13 @@ int gnnfd_in_bwd_edges(const gnnfd_graph_t* g, const float* x, int64_t ldx, int6
 /* da_src [n_src,H] = per-source sums of dz (over g's CSC). */
 int gnnfd_in_bwd_dasrc(const gnnfd_graph_t* g, const float* dz, float* da_src, gnnfd_stream_t stream);
 int gnnfd_in_bwd_params_workspace_bytes(int64_t n, int64_t K, size_t* bytes);
-/* dW [H*C,K], datt_src / datt_dst [H*C], dbias [C] from the saved image and the logit gradients of rows [0,n). */
+/* dW [H*C,K], datt_src / datt_dst [H*C], dbias [C] from the saved image and the logit gradients of rows [0,n).
+ * phase bit 0: tensor-core reduction dO^T Z into ws (no logit gradients needed: overlaps their exchange across GPUs);
+ * bit 1: node reductions with da_src / da_dst + final dW (same ws); 3 = both. */
 int gnnfd_in_bwd_params(const void* zimg, const float* d_out, const float* x, int64_t ldx, int64_t n, int64_t K,
                         const float* W, const float* att_src, const float* att_dst, const float* da_src,
                         const float* da_dst, const void* prep, float* dW, float* datt_src, float* datt_dst,
-                        float* dbias, void* ws, size_t ws_bytes, gnnfd_stream_t stream);
+                        float* dbias, void* ws, size_t ws_bytes, int phase, gnnfd_stream_t stream);
 
 /* ---- (6) model-level fused operators around the layers ---------------------------------------------------
  * Train-mode tail of the reference's layer loop (src/models/gat.py:82-91 == src/models/tgn.py:96-105): BatchNorm1d with batch
