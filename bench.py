@@ -448,9 +448,10 @@ def run_gpu_arm(args):
         stage_b = {"in_logits": own["in_logits"], "in_fwd_edges": own["in_fwd_edges"], "in_out_gemm": own["in_out_gemm"],
                    "in_bwd_gd_edges": own["in_bwd_gd"] + own["in_bwd_edges"], "in_bwd_dasrc": own["in_bwd_dasrc"],
                    "in_bwd_params": own["in_bwd_params"]}
-        kernels = {"in_logits": "in_logits_kernel", "in_fwd_edges": "gat_in_fwd_items (+hub chunks/merge)",
+        kernels = {"in_logits": "in_logits_kernel", "in_fwd_edges": "in_alpha_items + gat_in_fwd_items (+hub chunks/merge)",
                    "in_out_gemm": "in_out_gemm (tcgen05 kind::f16, bulk-fed)",
-                   "in_bwd_gd_edges": "gemm_tc_ws<2> (Gd) + gat_in_bwd_items (+hub)", "in_bwd_dasrc": "in_dasrc_kernel",
+                   "in_bwd_gd_edges": "in_proj_gemm<false> (Gd, tcgen05 kind::f16) + gat_in_bwd_items (+hub)",
+                   "in_bwd_dasrc": "in_dasrc_kernel",
                    "in_bwd_params": "in_dw_gemm (tcgen05 kind::f16, MN-major) + dax_partial"}
     else:
         own = roofline.stage_bytes(n_local, Ep, K, H, C, False, s_bytes, need_dx=False, n_src=(N if world > 1 else None))
