@@ -423,6 +423,9 @@ def run_gpu_arm(args):
         except Exception as ex:     # capture not possible on this stack: keep the eager number
             graph_note = f"CUDA graph capture failed ({type(ex).__name__}: {str(ex)[:120]}); eager timing reported"
             ms_per_step = eager_ms_per_step
+    selfcheck = None
+    if world > 1 and not args.no_selfcheck:
+        selfcheck = multi_gpu_selfcheck(type(part), rank, world, dev, K, H, C)
     clocks = sampler.stop()
     stage_ms = {s: statistics.mean(m[i].elapsed_time(m[i + 1]) for m in all_marks) for i, s in enumerate(stages)}
     if os.environ.get("GNNFD_BENCH_DEBUG"):
@@ -541,6 +544,7 @@ def run_gpu_arm(args):
                        "gemm_algo": args.algo, "note": note},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "timing": {"eager_ms_per_step": eager_ms_per_step, "host_enqueue_ms_per_step": host_enqueue_ms, "cuda_graph": graph_note},
+            "selfcheck": selfcheck,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -551,6 +555,49 @@ def run_gpu_arm(args):
 # ------------------------------------------------------------------------------------------------
 # BASELINE.json configs[2]: TemporalGNN over 49 snapshots, sharded by time step (no data-path collective)
 # ------------------------------------------------------------------------------------------------
+def multi_gpu_selfcheck(partition_cls, rank, world, dev, K, H, C):
+    """Every multi-GPU run checks itself (outside the timed region): the SAME partition class on a 200K-node / 2M-edge graph
+    of the same family, against the single-GPU projected-feature layer computed redundantly on every rank.  Returns the
+    worst relative L2 error over the ranks of (out rows, dW, datt_src, dbias)."""
+    import torch.distributed as dist
+    from gnn_fraud_detection_b200 import GATConv, build_csr, functional as Fn, partition, synth
+    n, e = 200_000, 2_000_000
+    ei = synth.powerlaw_graph(n, e, seed=5, device=dev)
+    x = torch.randn(n, K, device=dev, generator=torch.Generator(device=dev).manual_seed(10))
+    torch.manual_seed(11)
+    conv = GATConv(K, C, heads=H, concat=False).to(dev)
+    W, bias = conv.lin_src.weight.detach(), conv.bias.detach()
+    a_s, a_d = conv.att_src.detach().view(-1).contiguous(), conv.att_dst.detach().view(-1).contiguous()
+    d_out = torch.randn(n, C, device=dev, generator=torch.Generator(device=dev).manual_seed(12)) / n
+    g = build_csr(ei, n)
+    xw, a_src, a_dst = Fn.project_fwd(x, W, a_s, a_d, H, C)
+    out, rowmax, rowsum = Fn.gat_fwd(g, xw, a_src, a_dst, bias, H, C, 0.2, False)
+    dxw, da_src, da_dst = Fn.gat_bwd(g, xw, a_src, a_dst, rowmax, rowsum, d_out, a_s, a_d, H, C, 0.2, False)
+    dW, datt_s, _, dbias, _ = Fn.project_bwd(x, W, dxw, xw, da_src, da_dst, d_out, H, C, C, False)
+    part = partition_cls.build(ei, n, rank, world, dev)
+    lo, hi = int(part.plan.start[rank]), int(part.plan.start[rank + 1])
+    if isinstance(part, partition.InputSpacePartition):
+        xp = torch.zeros(part.n_pos, Fn.in_sizes(0, K)[3], device=dev)
+        xp[part.plan.to_pos(torch.arange(n, device=dev)), :K] = x
+        xp = xp[:, :K]
+    elif isinstance(part, partition.ReplicatedInputPartition):
+        xp = torch.zeros(part.n_pos, K, device=dev)
+        xp[part.plan.to_pos(torch.arange(n, device=dev))] = x
+    else:
+        xp = torch.zeros(part.rows_padded, K, device=dev)
+        xp[:hi - lo] = x[lo:hi]
+    o2, (dW2, ds2, _, db2) = part.layer_fwd_bwd(xp, W, a_s, a_d, bias, d_out[lo:hi].contiguous(), H, C, torch.float32, 0)
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+    errs = torch.tensor([rel(o2, out[lo:hi]), rel(dW2, dW), rel(ds2, datt_s), rel(db2, dbias)], device=dev)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    names = ["out", "dW", "datt_src", "dbias"]
+    res = {k: float(v) for k, v in zip(names, errs.tolist())}
+    res["graph"] = f"powerlaw N={n} E={e}"
+    res["against"] = "single-GPU projected-feature layer on every rank"
+    res["ok"] = bool(max(errs.tolist()) <= 3e-5)
+    return res
+
+
 def run_tgn_snapshots(args):
     """A step = one full-batch TRAINING step of the reference's TemporalGNN (2 GAT layers + BatchNorm/ReLU/residual tail +
     GRU head, src/models/tgn.py) with the reference's loss (masked BCE, pos_weight 50) over all 49 snapshots: every rank
@@ -747,6 +794,7 @@ def main():
                     "3 input-space formulation (first layer)")
     ap.add_argument("--bf16", action="store_true", help="bf16 storage of projected features")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-selfcheck", action="store_true", help="skip the multi-GPU parity self-check (outside the timed region)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
