@@ -305,7 +305,7 @@ def run_gpu_arm(args):
             in_xmax = torch.zeros(16, device=dev)
     else:
         stages = ["project_fwd", "gat_fwd", "gat_bwd_dst_src", "project_bwd"]
-    ximg = None
+    ximg, ximg_ms = None, None
     if world == 1 and not input_space and Fn.image_projection_applies(x, H, C, xw_dtype, args.algo):
         t0 = time.perf_counter()
         ximg = Fn.XImage(x)
@@ -497,7 +497,8 @@ def run_gpu_arm(args):
             x_host = torch.empty(x.shape, dtype=x.dtype, pin_memory=True).copy_(x)
             ei_host = torch.empty(ei.shape, dtype=ei.dtype, pin_memory=True).copy_(ei)
             torch.cuda.synchronize()
-            del x, ei, g, d_out, all_marks, ximg
+            del x, ei, g, d_out, all_marks
+            ximg = None
             Fn.GLOBAL_XIMAGE_CACHE.clear()
             GLOBAL_CSR_CACHE.clear()
             torch.cuda.empty_cache()
@@ -540,7 +541,7 @@ def run_gpu_arm(args):
                                         "(symmetric memory), no collective call on the data path",
                            "peer": "fused into the kernels: NVLink stores / loads on peer memory (symmetric memory)",
                        }.get(getattr(part, "exchange", "nccl"), "NCCL all-gather / reduce-scatter")),
-                       "csr_build_ms": csr_ms, "x_image_build_ms": (ximg_ms if ximg is not None else None), "setup_s": gen_s,
+                       "csr_build_ms": csr_ms, "x_image_build_ms": ximg_ms, "setup_s": gen_s,
                        "gemm_algo": args.algo, "note": note},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "timing": {"eager_ms_per_step": eager_ms_per_step, "host_enqueue_ms_per_step": host_enqueue_ms, "cuda_graph": graph_note},

@@ -20,7 +20,9 @@ timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 # step 4 of 4 (3 warm-ups): skip the first three launches of each kernel, capture the fourth
 timeout 500 ncu --set full --clock-control none --import-source on \
     -k regex:'gat_fwd_items_pack|gat_bwd_dst_items_pack|gat_bwd_src_rows|in_proj_gemm|dw_tc2' -s 15 -c 5 \
-    -o gpurun_out/prof_${T}_200m -f $CMD > gpurun_out/ncu_full_$T.log 2>&1; echo "ncu full exit $?"
+    -o /tmp/prof_${T}_200m -f $CMD > gpurun_out/ncu_full_$T.log 2>&1; echo "ncu full exit $?"
+# the report itself is too big to travel (gpurun_out is capped at 64 MiB): keep its raw page as CSV
+ncu -i /tmp/prof_${T}_200m.ncu-rep --page raw --csv > gpurun_out/ncu_raw_${T}_200m.csv 2>/dev/null
 fi
 CMD2="python bench.py --workload powerlaw_20m --algo 3 --steps 1 --warmup 3 --no-e2e --no-cpu"
 if timeout 200 $CMD2 > gpurun_out/ncu_plain_in_$T.log 2>&1; then
@@ -28,6 +30,8 @@ timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
     --log-file gpurun_out/launches_${T}_in_20m.csv $CMD2 > gpurun_out/ncu_launch_in_$T.log 2>&1; echo "ncu launch list (input-space) exit $?"
 timeout 500 ncu --set full --clock-control none --import-source on \
     -k regex:'in_alpha_items|gat_in_fwd_items|gat_in_bwd_items|in_out_gemm|in_dw_gemm|in_proj_gemm|in_logits_kernel' -s 27 -c 9 \
-    -o gpurun_out/prof_${T}_in_20m -f $CMD2 > gpurun_out/ncu_full_in_$T.log 2>&1; echo "ncu full (input-space) exit $?"
+    -o /tmp/prof_${T}_in_20m -f $CMD2 > gpurun_out/ncu_full_in_$T.log 2>&1; echo "ncu full (input-space) exit $?"
+ncu -i /tmp/prof_${T}_in_20m.ncu-rep --page raw --csv > gpurun_out/ncu_raw_${T}_in_20m.csv 2>/dev/null
 fi
 nvidia-smi --query-gpu=name,clocks.max.sm,power.limit --format=csv
+du -sh gpurun_out

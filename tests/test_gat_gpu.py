@@ -315,9 +315,13 @@ def test_projection_from_cached_image(N, K):
     assert float(((as_i.double().cpu() - ra).abs() / rowmag).max()) <= 4e-6 and float(((ad_i.double().cpu() - rd).abs() / rowmag).max()) <= 4e-6
     xw_t, as_t, _ = Fn.project_fwd(xg, Wg, asg, adg, H, C, torch.float32, _abi.GEMM_TC)
     assert float(((xw_i - xw_t).double().cpu().abs() / rowmag).max()) <= 4e-6
-    # the cache hands back the same image for the same tensor and a new one after an in-place edit
+    # the cache builds the image the SECOND time it sees a tensor (a fresh x per step never pays for it), hands back the same
+    # image afterwards, and starts over after an in-place edit
     c = Fn.XImageCache()
+    assert c.get(xg) is None
     i1 = c.get(xg)
-    assert c.get(xg) is i1
+    assert i1 is not None and c.get(xg) is i1
     xg.mul_(2.0)
-    assert c.get(xg) is not i1
+    assert c.get(xg) is None
+    i2 = c.get(xg)
+    assert i2 is not None and i2 is not i1
