@@ -13,12 +13,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GNNFD_B200_LIB") or os.path.join(_HERE, "libgnnfd_b200.so")   # override: A/B runs of two builds
 
 # enums (mirror include/gnnfd_b200.h)
-ADD_SELF_LOOPS, BUILD_CSC = 1, 2
+ADD_SELF_LOOPS, BUILD_CSC, ORDER_DST_SRC = 1, 2, 4
 F32, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_ELU = 0, 1, 2
 GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_INPUT = 0, 1, 2, 3
 HUB_THRESHOLD, HUB_CHUNK = 512, 512
-ABI_VERSION = 17
+ABI_VERSION = 18
 
 _i32p = C.POINTER(C.c_int32)
 
@@ -63,6 +63,7 @@ SIGNATURES = {
     "gnnfd_subgraph_build": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64p, _vp, _sz, _vp]),
     "gnnfd_launch_count": (_i64, []),
     "gnnfd_launch_count_reset": (None, []),
+    "gnnfd_shutdown": (_i, []),
     "gnnfd_csr_workspace_bytes": (_i, [_i64, _i64, _i, _szp]),
     "gnnfd_csr_build": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64p, _vp, _sz, _vp]),
     "gnnfd_hub_plan_workspace_bytes": (_i, [_i64, _szp]),

@@ -261,13 +261,13 @@ radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
 static int radix_sort_pairs(const uint32_t* keys_in, int64_t n, int key_bits, uint32_t* kA, uint32_t* vA,
                             uint32_t* kB, uint32_t* vB, uint32_t* counts, uint32_t* block_sums,
                             uint32_t* total_dev, const uint32_t** res_k, const uint32_t** res_v,
-                            cudaStream_t st)
+                            cudaStream_t st, const uint32_t* vals_in = nullptr)
 {
     const int nblocks = (int)((n + RS_TILE - 1) / RS_TILE);
     int passes = (key_bits + 7) / 8;
     if (passes < 1) passes = 1;
     const uint32_t* kin = keys_in;
-    const uint32_t* vin = nullptr;
+    const uint32_t* vin = vals_in;
     uint32_t* kout = kA;
     uint32_t* vout = vA;
     for (int p = 0; p < passes; ++p) {
@@ -311,6 +311,13 @@ __global__ void finalize_csr(const uint32_t* __restrict__ key, const uint32_t* _
         col[e] = srcc[p];
         if (dst_sorted) dst_sorted[e] = (int32_t)key[e];
     }
+}
+// ORDER_DST_SRC, between the two sorts: the destination of every source-sorted edge becomes the key of the second sort
+__global__ void gather_keys(const uint32_t* __restrict__ key_of, const uint32_t* __restrict__ idx, int64_t n,
+                            uint32_t* __restrict__ out)
+{
+    for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < n; e += int64_t(gridDim.x) * blockDim.x)
+        out[e] = key_of[idx[e]];
 }
 __global__ void finalize_csc(const uint32_t* __restrict__ val, const int32_t* __restrict__ dst_sorted, int64_t n,
                              int32_t* __restrict__ csc_row, int32_t* __restrict__ csc_eid)
@@ -457,6 +464,12 @@ int gnnfd_item_plan(const int32_t* ptr, int64_t n_rows, int64_t n_edges, int32_t
 }
 int64_t gnnfd_launch_count(void) { return (int64_t)g_launches.load(); }
 void gnnfd_launch_count_reset(void) { g_launches.store(0); }
+int gnnfd_shutdown(void)
+{
+    g_dropout_seed_src = nullptr;
+    g_launches.store(0);
+    return GNNFD_OK;
+}
 
 int gnnfd_csr_workspace_bytes(int64_t N, int64_t E, int flags, size_t* bytes)
 {
@@ -515,10 +528,30 @@ int gnnfd_csr_build(const int64_t* edge_index, int64_t E, int64_t N, int flags, 
     // 3. stable sort by destination; values = positions in edge_index'
     const int bits = bits_for(N);
     const uint32_t *rk = nullptr, *rv = nullptr;
-    // first pass reads kA and must not write it: run A -> B -> A ...
-    rc = radix_sort_pairs(w.kA, Ep, bits, w.kB, w.vB, w.kA, w.vA, w.counts, w.block_sums, w.scalars + 2, &rk, &rv, st);
-    if (rc) return rc;
-    finalize_csr<<<grid_for(Ep, 256), 256, 0, st>>>(rk, rv, w.srcc, Ep, col, perm, w.dst_sorted);
+    int32_t* dst_sorted_out = w.dst_sorted;
+    if (flags & GNNFD_ORDER_DST_SRC) {
+        // PyG sort_edge_index(sort_by_row=False): stable sort on (dst', src') = LSD over the two fields: first a stable sort
+        // by source (values = positions in edge_index'), then a stable sort of THAT sequence by destination.  kA (the
+        // destinations) must survive the first sort, so it ping-pongs between (kB, vB) and (dst_sorted, vA).
+        uint32_t* dk = reinterpret_cast<uint32_t*>(w.dst_sorted);
+        rc = radix_sort_pairs(reinterpret_cast<const uint32_t*>(w.srcc), Ep, bits, w.kB, w.vB, dk, w.vA, w.counts, w.block_sums,
+                              w.scalars + 2, &rk, &rv, st);
+        if (rc) return rc;
+        uint32_t* k1 = const_cast<uint32_t*>(rk);      // the sorted sources are no longer needed: their buffer takes the new keys
+        uint32_t* v1 = const_cast<uint32_t*>(rv);
+        uint32_t* k2 = (k1 == w.kB) ? dk : w.kB;
+        uint32_t* v2 = (v1 == w.vB) ? w.vA : w.vB;
+        gather_keys<<<grid_for(Ep, 256), 256, 0, st>>>(w.kA, v1, Ep, k1);
+        g_launches += 1;
+        rc = radix_sort_pairs(k1, Ep, bits, k2, v2, k1, v1, w.counts, w.block_sums, w.scalars + 2, &rk, &rv, st, v1);
+        if (rc) return rc;
+        if (rk == dk) dst_sorted_out = nullptr;        // the sorted keys already sit in dst_sorted
+    } else {
+        // first pass reads kA and must not write it: run A -> B -> A ...
+        rc = radix_sort_pairs(w.kA, Ep, bits, w.kB, w.vB, w.kA, w.vA, w.counts, w.block_sums, w.scalars + 2, &rk, &rv, st);
+        if (rc) return rc;
+    }
+    finalize_csr<<<grid_for(Ep, 256), 256, 0, st>>>(rk, rv, w.srcc, Ep, col, perm, dst_sorted_out);
     fill_ptr<<<grid_for(Ep, 256), 256, 0, st>>>(rk, Ep, N, rowptr);
     g_launches += 2;
     GNNFD_LAUNCH_CHECK();

@@ -124,8 +124,12 @@ class GraphCSR:
 
 
 def build_csr(edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = True, build_csc: bool = True,
-              hub_threshold: int = _abi.HUB_THRESHOLD, hub_chunk: int = _abi.HUB_CHUNK) -> GraphCSR:
-    """edge_index [2,E] int64 (cuda) -> GraphCSR, via ``gnnfd_csr_build`` (stable radix sort on device)."""
+              hub_threshold: int = _abi.HUB_THRESHOLD, hub_chunk: int = _abi.HUB_CHUNK, order: str = "dst") -> GraphCSR:
+    """edge_index [2,E] int64 (cuda) -> GraphCSR, via ``gnnfd_csr_build`` (stable radix sort on device).
+    ``order="dst"``: edges of a row in their order of appearance (what PyG's scatter sees, the default);
+    ``order="dst_src"``: additionally sorted by source within a row (PyG ``sort_edge_index(sort_by_row=False)``)."""
+    if order not in ("dst", "dst_src"):
+        raise ValueError(f"order must be 'dst' or 'dst_src', got {order!r}")
     if edge_index.dim() != 2 or edge_index.size(0) != 2:
         raise ValueError(f"edge_index must be [2, E], got {tuple(edge_index.shape)}")
     if edge_index.dtype != torch.int64:
@@ -135,7 +139,8 @@ def build_csr(edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = T
     L = _abi.lib()
     ei = edge_index.contiguous()
     E, N, dev = ei.size(1), int(num_nodes), ei.device
-    flags = (_abi.ADD_SELF_LOOPS if add_self_loops else 0) | (_abi.BUILD_CSC if build_csc else 0)
+    flags = ((_abi.ADD_SELF_LOOPS if add_self_loops else 0) | (_abi.BUILD_CSC if build_csc else 0)
+             | (_abi.ORDER_DST_SRC if order == "dst_src" else 0))
     cap = E + (N if add_self_loops else 0)
     with torch.cuda.device(dev):
         nbytes = C.c_size_t()

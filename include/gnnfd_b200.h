@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GNNFD_ABI_VERSION 17
+#define GNNFD_ABI_VERSION 18
 
 typedef void* gnnfd_stream_t; /* cudaStream_t */
 
@@ -50,7 +50,9 @@ enum {
     GNNFD_ERR_UNSUPPORTED = -5  /* (H,C), dtype or option not built */
 };
 
-enum { GNNFD_ADD_SELF_LOOPS = 1, GNNFD_BUILD_CSC = 2 };          /* gnnfd_csr_build flags */
+/* gnnfd_csr_build flags.  Default edge order inside a row = order of appearance in edge_index' (stable sort on dst', what
+ * PyG's scatter sees); GNNFD_ORDER_DST_SRC = PyG sort_edge_index(sort_by_row=False): stable sort on (dst', src'). */
+enum { GNNFD_ADD_SELF_LOOPS = 1, GNNFD_BUILD_CSC = 2, GNNFD_ORDER_DST_SRC = 4 };
 enum { GNNFD_F32 = 0, GNNFD_BF16 = 1 };                           /* xw_dtype */
 enum { GNNFD_ACT_NONE = 0, GNNFD_ACT_RELU = 1, GNNFD_ACT_ELU = 2 };/* fused epilogue activation */
 enum { GNNFD_GEMM_AUTO = 0, GNNFD_GEMM_SIMT = 1, GNNFD_GEMM_TC = 2 }; /* projection algorithm */
@@ -114,6 +116,9 @@ size_t gnnfd_sizeof_item_plan(void);
 /* Number of kernel launches issued by this library since the last reset (bench.py "gpu_launches"). */
 int64_t gnnfd_launch_count(void);
 void gnnfd_launch_count_reset(void);
+/* End of use.  The library owns no device memory (every buffer and workspace is the caller's), so this only detaches the
+ * process-wide state it does keep: the dropout seed source and the launch counter.  Safe to call more than once. */
+int gnnfd_shutdown(void);
 
 /* ---- (1) edge_index -> destination-sorted CSR ------------------------------------------------
  * Replaces: remove_self_loops/add_self_loops + the per-call scatter ordering inside GATConv.forward

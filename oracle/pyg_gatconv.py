@@ -71,16 +71,21 @@ def rewrite_self_loops(edge_index: torch.Tensor, num_nodes: int, add_self_loops:
     return torch.cat([ei, torch.stack([loop, loop])], dim=1)
 
 
-def csr_oracle(edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = True):
+def csr_oracle(edge_index: torch.Tensor, num_nodes: int, add_self_loops: bool = True, order: str = "dst"):
     """Destination-sorted CSR of the rewritten edge list.
 
     ``perm`` is ``torch.sort(dst', stable=True).indices`` (positions into ``edge_index'``), ``col`` the
     source of each sorted edge, ``rowptr`` int64 ``[N+1]``.  Stable => the self-loop is the last entry
-    of every row.
+    of every row.  ``order="dst_src"`` is PyG's ``sort_edge_index(edge_index', sort_by_row=False)``: a stable
+    sort on the composite key ``dst' * N + src'`` (duplicates keep their order of appearance).
     """
     ei = rewrite_self_loops(edge_index, num_nodes, add_self_loops)
     src, dst = ei[0], ei[1]
-    dst_sorted, perm = torch.sort(dst, stable=True)
+    if order == "dst_src":
+        _, perm = torch.sort(dst * max(num_nodes, 1) + src, stable=True)
+        dst_sorted = dst[perm]
+    else:
+        dst_sorted, perm = torch.sort(dst, stable=True)
     counts = torch.bincount(dst_sorted, minlength=num_nodes)
     rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64)
     rowptr[1:] = torch.cumsum(counts, 0)

@@ -10,9 +10,9 @@ from oracle import pyg_gatconv as O
 pytestmark = pytest.mark.gpu
 
 
-def _check(ei_cpu, N, loops=True):
-    g = build_csr(ei_cpu.cuda(), N, add_self_loops=loops, build_csc=True)
-    rowptr, col, perm, ei2 = O.csr_oracle(ei_cpu, N, loops)
+def _check(ei_cpu, N, loops=True, order="dst"):
+    g = build_csr(ei_cpu.cuda(), N, add_self_loops=loops, build_csc=True, order=order)
+    rowptr, col, perm, ei2 = O.csr_oracle(ei_cpu, N, loops, order)
     assert g.n_edges == ei2.size(1)
     assert torch.equal(g.rowptr.cpu().long(), rowptr)
     assert torch.equal(g.col.cpu().long(), col)
@@ -29,6 +29,32 @@ def _check(ei_cpu, N, loops=True):
 @pytest.mark.parametrize("loops", [True, False])
 def test_csr_bit_exact_random(N, E, loops):
     _check(synth.random_graph(N, E, seed=N * 7 + E), N, loops)      # includes self loops and duplicates
+
+
+@pytest.mark.parametrize("N,E", [(5, 0), (2, 1), (33, 100), (257, 5000), (4097, 40000), (70000, 300000), (300, 70000)])
+@pytest.mark.parametrize("loops", [True, False])
+def test_csr_order_dst_src_bit_exact(N, E, loops):
+    """GNNFD_ORDER_DST_SRC = PyG sort_edge_index(sort_by_row=False): rows sorted by source, duplicates in input order."""
+    g = _check(synth.random_graph(N, E, seed=N * 5 + E), N, loops, order="dst_src")
+    rp, col = g.rowptr.cpu().long(), g.col.cpu().long()
+    if g.n_edges:
+        row = torch.repeat_interleave(torch.arange(N), rp[1:] - rp[:-1])
+        key = row * N + col
+        assert bool((key[1:] >= key[:-1]).all())
+
+
+def test_layer_is_invariant_to_the_row_order():
+    """The layer's result does not depend on the order of a row's edges beyond fp32 summation order."""
+    from gnn_fraud_detection_b200 import GATConv
+    N, E, K = 3000, 30000, 166
+    ei = synth.random_graph(N, E, seed=3).cuda()
+    x = torch.randn(N, K, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    torch.manual_seed(1)
+    conv = GATConv(K, 64, heads=8, concat=False).cuda().eval()
+    with torch.no_grad():
+        a = conv(x, build_csr(ei, N))
+        b = conv(x, build_csr(ei, N, order="dst_src"))
+    assert float((a - b).abs().max()) <= 2e-6
 
 
 def test_csr_empty_graph():

@@ -199,3 +199,18 @@ def test_reference_checkpoints_load_strict_and_golden_vectors(golden_dir):
 def test_glorot_bounds():
     t = O.glorot_(torch.empty(512, 166))
     assert t.abs().max() <= math.sqrt(6 / (512 + 166)) + 1e-7
+
+
+def test_csr_oracle_dst_src_order_matches_numpy_lexsort():
+    """order="dst_src" (PyG sort_edge_index(sort_by_row=False)) against an independent statement: numpy lexsort on
+    (src, dst) is stable, so duplicates keep their order of appearance."""
+    import numpy as np
+    from gnn_fraud_detection_b200 import synth
+    for N, E, loops in [(7, 40, True), (50, 400, False), (300, 5000, True)]:
+        ei = synth.random_graph(N, E, seed=N + E)
+        rowptr, col, perm, ei2 = O.csr_oracle(ei, N, loops, order="dst_src")
+        src, dst = ei2[0].numpy(), ei2[1].numpy()
+        ref = np.lexsort((src, dst))                    # last key is the primary one
+        assert np.array_equal(perm.numpy(), ref)
+        assert np.array_equal(col.numpy(), src[ref])
+        assert np.array_equal(np.diff(rowptr.numpy()), np.bincount(dst, minlength=N))
