@@ -584,17 +584,18 @@ class InputSpacePartition(DstRangePartition):
         def one():
             main = torch.cuda.current_stream()
             ed = ei_host.to(dev, non_blocking=True)
+            xf = torch.empty(self.n_pos, ld, dtype=torch.float32, device=dev)
             copy_stream.wait_stream(main)
-            with torch.cuda.stream(copy_stream):       # feature copy overlaps the index build below
+            with torch.cuda.stream(copy_stream):       # feature copy AND its all-gather over NVLink overlap the index build
                 xo = x_own_host.to(dev, non_blocking=True)
+                if self.world > 1:
+                    dist.all_gather_into_tensor(xf, xo)
+                else:
+                    xf.copy_(xo)
             g = self.build_graph(ed)
             main.wait_stream(copy_stream)
             xo.record_stream(main)
-            xf = torch.empty(self.n_pos, ld, dtype=torch.float32, device=dev)
-            if self.world > 1:
-                dist.all_gather_into_tensor(xf, xo)
-            else:
-                xf.copy_(xo)
+            xf.record_stream(copy_stream)
             out, grads = self.layer_fwd_bwd(xf[:, :K], W, a_s, a_d, bias, d_out, H, C, graph=g)
             return [t.cpu() for t in grads] + [out[:1].cpu()]
 
@@ -613,5 +614,6 @@ class InputSpacePartition(DstRangePartition):
         d2h = sum(t.numel() * t.element_size() for t in res)
         return {"value": E_total / dt, "unit": "edges/s", "h2d_bytes_per_step": h2d * self.world,
                 "d2h_bytes_per_step": d2h * self.world, "steps": steps, "ms_per_step": dt * 1e3,
-                "includes": "per rank: H2D of own x rows + own edge list, all-gather of x over NVLink, CSR/CSC rebuild, "
-                            "fwd+bwd with all-gather/reduce-scatter of [N,H] logits, all-reduce of grads, D2H of grads"}
+                "includes": "per rank: H2D of own x rows + own edge list, all-gather of x over NVLink (both under the CSR/CSC "
+                            "rebuild), fwd+bwd with the [N,H] logit exchange (" + str(getattr(self, "exchange", "nccl")) + "), "
+                            "all-reduce of grads, D2H of grads"}
