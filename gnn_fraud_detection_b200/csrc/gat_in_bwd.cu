@@ -4,7 +4,9 @@
 //     u = alpha * d_alpha (dropout-scaled), t = sum_row u, dz = slope' * (u - alpha t), da_dst[i] = sum_row dz
 // dz is written in SOURCE-MAJOR order (slot csr2csc[e]) so that da_src = per-source sums (gnnfd_in_bwd_dasrc) reads it
 // contiguously.  No alpha_used / dxw: the weight gradient comes from the saved Z image (in_gemm.cu).
-// Same warp-stream structure as gat_bwd_dst.cu (work items, phase A one chunk ahead, packs of short rows, hub rows in
+// alpha (with the LeakyReLU region in its sign bit) and the row-end flags are what the forward's attention pass saved: the
+// staging of a chunk (lane = edge) is two coalesced loads, no logit gathers, no exp, no row statistics.
+// Same warp-stream structure as gat_bwd_dst.cu (work items, staging one chunk ahead, packs of short rows, hub rows in
 // chunks with a deterministic merge); x rows arrive through the per-warp bulk-copy ring, and the destination's Gd row
 // is prefetched by the copy engine into a per-warp shared-memory buffer while the previous row is processed.
 #include "in_common.cuh"

@@ -1,14 +1,16 @@
 // Input-space forward of the first GAT layer (see in_common.cuh for the algebra):
 //   gnnfd_in_logits   a_src / a_dst straight from x (u = W_h^T att precomputed), + max |x| for the fp16-pair scale
 //   gnnfd_in_prepare  per-call constants: scales, the W images of the two dense stages
-//   gnnfd_in_fwd      LeakyReLU + online segment softmax + alpha-weighted gather-sum of INPUT rows x[j] (K*4 bytes per
-//                     edge instead of the 2 KB projected row), one accumulator set per head, written as the fp16-pair
-//                     tensor-core image Z that gnnfd_in_out (in_gemm.cu) multiplies with W.
+//   gnnfd_in_fwd      two passes.  ATTENTION pass (lane = edge): LeakyReLU + segment softmax -> normalised alpha [E',H] with
+//                     the LeakyReLU region in its sign bit, jflag [E'] = source id | row-end flag, rowmax / rowsum; kept
+//                     for the backward.  FEATURE pass: alpha-weighted gather-sum of INPUT rows x[j] (K*4 bytes per edge
+//                     instead of the 2 KB projected row), lane = feature group with the accumulators of all heads, written
+//                     as the fp16-pair tensor-core image Z that gnnfd_in_out (in_gemm.cu) multiplies with W.
 // Replaces, for the reference's first layer (src/models/gat.py:39,80; tgn.py:43,94), the same PyG stages as
 // gnnfd_project_fwd + gnnfd_gat_fwd: lin_src / (x*att).sum(-1) / edge_update / message / aggregate.
-// Same warp-stream structure as gat_fwd.cu: one warp per edge-balanced work item, phase A (lane = edge) one chunk
-// ahead, rows delivered by the bulk-copy engine into a per-warp ring; packs of short rows; hub rows split into chunks
-// merged in chunk order (deterministic).
+// Same warp-stream structure as gat_fwd.cu: one warp per edge-balanced work item, the staging of a chunk (lane = edge) one
+// chunk ahead, rows delivered by the bulk-copy engine into a per-warp ring; packs of short rows; hub rows split into
+// chunks whose partial sums are added in chunk order (deterministic).
 #include "in_common.cuh"
 #include "gat_stream.cuh"
 

@@ -31,7 +31,7 @@ constexpr int TILE = 128;                // rows (nodes) per image tile
 constexpr int PLANE = TILE * 128;        // 16 KB: one fp16 plane of one k-block (64 features) of one tile
 constexpr int KBLOCK = 2 * PLANE;        // hi plane then lo plane
 
-struct GI { static constexpr int H = in::H, C = in::C; };   // what the shared phase-A code needs
+struct GI { static constexpr int H = in::H, C = in::C; };   // head geometry for the helpers shared with the projected-feature kernels
 
 struct Dims {
     int K, KP, F, NKB;
@@ -96,7 +96,7 @@ inline size_t zimg_bytes(int64_t n_rows, const Dims& d) { return size_t((n_rows 
 namespace gnnfd {
 namespace in {
 
-// ---- lane geometry of the edge kernels ------------------------------------------------------------------------------
+// ---- lane geometry of the logits kernel and of the backward edge kernel -------------------------------------------------
 // lane = (head h = lane >> 2, quarter q = lane & 3).  A staged x row is KP floats = n4 float4s; lane (h, q) owns the
 // float4s 4*i + q (i = 0, 1, ...) of the row for ITS head: 44 accumulators (forward) / 44 Gd values (backward) for
 // K = 166.  Per edge and lane: ceil(n4/4) conflict-free 128-bit shared loads (the four q-lanes read 64 contiguous bytes,
