@@ -199,19 +199,28 @@ struct StoreExcl {
     __device__ void operator()(int64_t i, uint32_t, uint32_t ex) const { p[i] = ex; }
 };
 
+// Scatter pass.  A thread knows the final slot of each of its keys (global base of (digit, block) + rank inside the tile), but
+// writing it directly means 4-byte stores to ~256 open streams per block: every store dirties a 32-byte sector on its own.
+// So the tile is first reordered in shared memory by tile-local rank (the same stable order), then written out in that
+// order: consecutive threads then hold consecutive slots of one digit run, and a run (16 keys on average) leaves as full
+// sectors.  The slots are identical to the direct scatter, bit for bit.
 __global__ void __launch_bounds__(RS_THREADS)
 radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
               uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int64_t n, int shift,
               const uint32_t* __restrict__ offsets, int nblocks)
 {
     __shared__ uint32_t warp_cnt[RS_WARPS][RADIX];
-    __shared__ uint32_t base_off[RADIX];
+    __shared__ uint32_t base_off[RADIX];      // global slot of the tile's first key with digit d
+    __shared__ uint32_t dig_start[RADIX];     // tile-local slot of the tile's first key with digit d
+    __shared__ uint32_t scan_w[RS_WARPS];
+    __shared__ uint32_t sk[RS_TILE], sv[RS_TILE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&warp_cnt[0][0])[i] = 0;
     __syncthreads();
 
     // warp w owns the 512 consecutive keys [w*512, (w+1)*512) of the tile; round r = 32 consecutive keys
-    const int64_t wbase = int64_t(blockIdx.x) * RS_TILE + warp * (RS_ROUNDS * 32);
+    const int64_t tile0 = int64_t(blockIdx.x) * RS_TILE;
+    const int64_t wbase = tile0 + warp * (RS_ROUNDS * 32);
     uint32_t key[RS_ROUNDS], rank[RS_ROUNDS];
     const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
@@ -232,7 +241,8 @@ radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
         __syncwarp();
     }
     __syncthreads();
-    {   // exclusive prefix of each digit over the warps of this block, plus the block's global base
+    {   // exclusive prefix of each digit over the warps of this block, the block's global base, and the exclusive prefix
+        // over the digits of the tile histogram (thread d owns digit d)
         const int d = threadIdx.x;
         uint32_t run = 0;
 #pragma unroll
@@ -242,6 +252,18 @@ radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
             run += c;
         }
         base_off[d] = offsets[int64_t(d) * nblocks + blockIdx.x];
+        uint32_t inc = run;                              // inclusive scan of the 256 digit counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) scan_w[warp] = inc;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) before += (w < warp) ? scan_w[w] : 0u;
+        dig_start[d] = before + inc - run;
     }
     __syncthreads();
 #pragma unroll
@@ -249,10 +271,19 @@ radix_scatter(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__
         const int64_t i = wbase + r * 32 + lane;
         if (i < n) {
             const uint32_t d = (key[r] >> shift) & (RADIX - 1);
-            const uint32_t pos = base_off[d] + warp_cnt[warp][d] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = vals_in ? vals_in[i] : (uint32_t)i;
+            const uint32_t lp = dig_start[d] + warp_cnt[warp][d] + rank[r];
+            sk[lp] = key[r];
+            sv[lp] = vals_in ? vals_in[i] : (uint32_t)i;
         }
+    }
+    __syncthreads();
+    const int tile_n = int(n - tile0 < RS_TILE ? n - tile0 : RS_TILE);
+    for (int i = threadIdx.x; i < tile_n; i += RS_THREADS) {
+        const uint32_t k = sk[i];
+        const uint32_t d = (k >> shift) & (RADIX - 1);
+        const uint32_t pos = base_off[d] + (uint32_t(i) - dig_start[d]);
+        keys_out[pos] = k;
+        vals_out[pos] = sv[i];
     }
 }
 
