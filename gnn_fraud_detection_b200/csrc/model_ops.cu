@@ -334,83 +334,111 @@ gru_head_bwd_kernel(const float* __restrict__ x, const float* __restrict__ h_pre
     }
 }
 
-// C[N, Kd] = A[N, G3] @ Wm[G3, Kd]   (dx = d_gi @ W_ih ; dh = d_gh @ W_hh): block = 32 nodes, thread = (node, 8 columns)
+// C[N, Kd] = A[N, G3] @ Wm[G3, Kd]   (dx = d_gi @ W_ih ; dh = d_gh @ W_hh): block = 64 nodes, thread = (2 nodes, 8 columns):
+// per gate 2 + 2 shared loads feed 16 FMAs
+constexpr int GTW_NODES = 64;
 __global__ void __launch_bounds__(256)
 gates_times_w_kernel(const float* __restrict__ A, const float* __restrict__ Wm /*[192][64]*/, int64_t N, const float* __restrict__ add,
                      float scale_add, float* __restrict__ Cout)
 {
     extern __shared__ __align__(16) float gsm[];
     float* ws = gsm;                       // [192][64]
-    float* as = gsm + G3 * HD;             // [32][192]
+    float* as = gsm + G3 * HD;             // [64][192 + 4]  (padded: the two nodes of a thread and the 8 node pairs of a warp
+                                           //                 quarter fall into different banks)
+    constexpr int LDA = G3 + 4;
     for (int i = threadIdx.x; i < G3 * HD; i += blockDim.x) ws[i] = Wm[i];
-    const int nl = threadIdx.x >> 3, c0 = (threadIdx.x & 7) * 8;
-    for (int64_t t0 = int64_t(blockIdx.x) * GRU_NODES; t0 < N; t0 += int64_t(gridDim.x) * GRU_NODES) {
+    const int nl = (threadIdx.x >> 3) * 2, c0 = (threadIdx.x & 7) * 8;
+    for (int64_t t0 = int64_t(blockIdx.x) * GTW_NODES; t0 < N; t0 += int64_t(gridDim.x) * GTW_NODES) {
         __syncthreads();
-        for (int i = threadIdx.x; i < GRU_NODES * G3 / 4; i += blockDim.x) {
-            const int64_t n = t0 + (i * 4) / G3;
-            reinterpret_cast<float4*>(as)[i] = n < N ? reinterpret_cast<const float4*>(A + t0 * G3)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = threadIdx.x; i < GTW_NODES * G3 / 4; i += blockDim.x) {
+            const int r = (i * 4) / G3, c = (i * 4) % G3;
+            const int64_t n = t0 + r;
+            *reinterpret_cast<float4*>(as + r * LDA + c) =
+                n < N ? *reinterpret_cast<const float4*>(A + n * G3 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
-        const int64_t n = t0 + nl;
-        float acc[8];
+        float acc[2][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+#pragma unroll 4
         for (int o = 0; o < G3; ++o) {
-            const float a = as[nl * G3 + o];
+            const float a0 = as[nl * LDA + o], a1 = as[(nl + 1) * LDA + o];
             const float4 w0 = *reinterpret_cast<const float4*>(ws + o * HD + c0), w1 = *reinterpret_cast<const float4*>(ws + o * HD + c0 + 4);
-            acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
-            acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]); acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+            acc[0][0] = fmaf(a0, w0.x, acc[0][0]); acc[0][1] = fmaf(a0, w0.y, acc[0][1]); acc[0][2] = fmaf(a0, w0.z, acc[0][2]); acc[0][3] = fmaf(a0, w0.w, acc[0][3]);
+            acc[0][4] = fmaf(a0, w1.x, acc[0][4]); acc[0][5] = fmaf(a0, w1.y, acc[0][5]); acc[0][6] = fmaf(a0, w1.z, acc[0][6]); acc[0][7] = fmaf(a0, w1.w, acc[0][7]);
+            acc[1][0] = fmaf(a1, w0.x, acc[1][0]); acc[1][1] = fmaf(a1, w0.y, acc[1][1]); acc[1][2] = fmaf(a1, w0.z, acc[1][2]); acc[1][3] = fmaf(a1, w0.w, acc[1][3]);
+            acc[1][4] = fmaf(a1, w1.x, acc[1][4]); acc[1][5] = fmaf(a1, w1.y, acc[1][5]); acc[1][6] = fmaf(a1, w1.z, acc[1][6]); acc[1][7] = fmaf(a1, w1.w, acc[1][7]);
         }
-        if (n < N) {
-            if (add) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = fmaf(scale_add, add[n * HD + c0 + j], acc[j]);
+        for (int u = 0; u < 2; ++u) {
+            const int64_t n = t0 + nl + u;
+            if (n < N) {
+                if (add) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[u][j] = fmaf(scale_add, add[n * HD + c0 + j], acc[u][j]);
+                }
+                *reinterpret_cast<float4*>(Cout + n * HD + c0) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+                *reinterpret_cast<float4*>(Cout + n * HD + c0 + 4) = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
             }
-            *reinterpret_cast<float4*>(Cout + n * HD + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            *reinterpret_cast<float4*>(Cout + n * HD + c0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
         }
     }
 }
-// P[block][o][k] partial of  dW[o,k] = sum_n G[n,o] * X[n,k]  and  db[o] = sum_n G[n,o]   (o < 192, k < 64)
-// block = 256 threads: thread t owns gate column o = t (t < 192) for all 64 k; x rows broadcast from shared memory
-__global__ void __launch_bounds__(256)
+// P[block][o][k] partial of  dW[o,k] = sum_n G[n,o] * X[n,k]  and  db[o] = sum_n G[n,o]   (o < 192, k < 64).
+// block = 192 threads: thread (og = t % 48, kq = t / 48) owns the 4 gate columns 4 og .. and the 16 inputs 16 kq ..:
+// 64 accumulators fed per node by ONE 128-bit load of G and four broadcast 128-bit shared loads of x.
+// X == NULL (the reference's zero state: dW_hh = 0): only the column sums are computed.
+constexpr int GO_THREADS = 192;
+__global__ void __launch_bounds__(GO_THREADS)
 gates_outer_kernel(const float* __restrict__ G, const float* __restrict__ X, int64_t N, double* __restrict__ P /*[blocks][192][65]*/)
 {
     __shared__ __align__(16) float xs[GRU_NODES][HD];
-    const int o = threadIdx.x;
+    const int og = threadIdx.x % 48, kq = threadIdx.x / 48;
     const int64_t rows_per_block = ((N + gridDim.x - 1) / gridDim.x + GRU_NODES - 1) / GRU_NODES * GRU_NODES;
     const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
     const int64_t r1 = r0 + rows_per_block < N ? r0 + rows_per_block : N;
-    float acc[HD];
-    float accb = 0.f;
+    float acc[4][16];
+    float accb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < HD; ++k) acc[k] = 0.f;
-    for (int64_t t0 = r0; t0 < r1; t0 += GRU_NODES) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < GRU_NODES * HD / 4; i += blockDim.x) {
-            const int64_t n = t0 + (i * 4) / HD;
-            reinterpret_cast<float4*>(&xs[0][0])[i] = (n < r1 && X) ? reinterpret_cast<const float4*>(X + t0 * HD)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncthreads();
-        if (o < G3) {
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[u][k] = 0.f;
+    if (X == nullptr) {
+        if (kq == 0)
+            for (int64_t r = r0; r < r1; ++r) {
+                const float4 g = *reinterpret_cast<const float4*>(G + r * G3 + 4 * og);
+                accb[0] += g.x; accb[1] += g.y; accb[2] += g.z; accb[3] += g.w;
+            }
+    } else {
+        for (int64_t t0 = r0; t0 < r1; t0 += GRU_NODES) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < GRU_NODES * HD / 4; i += blockDim.x) {
+                const int64_t n = t0 + (i * 4) / HD;
+                reinterpret_cast<float4*>(&xs[0][0])[i] = n < r1 ? reinterpret_cast<const float4*>(X + t0 * HD)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncthreads();
             const int cnt = int(r1 - t0 < GRU_NODES ? r1 - t0 : GRU_NODES);
             for (int r = 0; r < cnt; ++r) {
-                const float g = G[(t0 + r) * G3 + o];
-                accb += g;
+                const float4 g4 = *reinterpret_cast<const float4*>(G + (t0 + r) * G3 + 4 * og);
+                const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+                if (kq == 0) { accb[0] += g[0]; accb[1] += g[1]; accb[2] += g[2]; accb[3] += g[3]; }
 #pragma unroll
-                for (int k = 0; k < HD; k += 4) {
-                    const float4 xv = *reinterpret_cast<const float4*>(&xs[r][k]);
-                    acc[k] = fmaf(g, xv.x, acc[k]); acc[k + 1] = fmaf(g, xv.y, acc[k + 1]);
-                    acc[k + 2] = fmaf(g, xv.z, acc[k + 2]); acc[k + 3] = fmaf(g, xv.w, acc[k + 3]);
+                for (int k = 0; k < 16; k += 4) {
+                    const float4 xv = *reinterpret_cast<const float4*>(&xs[r][16 * kq + k]);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc[u][k] = fmaf(g[u], xv.x, acc[u][k]); acc[u][k + 1] = fmaf(g[u], xv.y, acc[u][k + 1]);
+                        acc[u][k + 2] = fmaf(g[u], xv.z, acc[u][k + 2]); acc[u][k + 3] = fmaf(g[u], xv.w, acc[u][k + 3]);
+                    }
                 }
             }
         }
     }
-    if (o < G3) {
-        double* p = P + (int64_t(blockIdx.x) * G3 + o) * (HD + 1);
 #pragma unroll
-        for (int k = 0; k < HD; ++k) p[k] = double(acc[k]);
-        p[HD] = double(accb);
+    for (int u = 0; u < 4; ++u) {
+        double* p = P + (int64_t(blockIdx.x) * G3 + 4 * og + u) * (HD + 1);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) p[16 * kq + k] = double(acc[u][k]);
+        if (kq == 0) p[HD] = double(accb[u]);
     }
 }
 // dW[o,k] / db[o] from the block partials (fixed order)
@@ -667,20 +695,22 @@ int gnnfd_gru_head_bwd(const float* x, const float* h_prev, const float* d_out, 
         gru_head_bwd_kernel<false><<<(unsigned)blocks, 256, smem, st>>>(x, nullptr, d_out, d_hnew, N, W, d_gi, d_gh, nullptr, Pout);
     }
     head_out_reduce_kernel<<<1, 128, 0, st>>>(Pout, (int)blocks, dw_out, db_out);
-    const int smem_w = (G3 * HD + GRU_NODES * G3) * 4;
+    const int smem_w = (G3 * HD + GTW_NODES * (G3 + 4)) * 4;
+    int64_t wblocks = (N + GTW_NODES - 1) / GTW_NODES;
+    if (wblocks > int64_t(sm_count()) * 2) wblocks = int64_t(sm_count()) * 2;
     GNNFD_CUDA(cudaFuncSetAttribute(gates_times_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_w));
-    gates_times_w_kernel<<<(unsigned)blocks, 256, smem_w, st>>>(d_gi, w_ih, N, nullptr, 0.f, dx);
-    int ob = int((N + 1023) / 1024);
+    gates_times_w_kernel<<<(unsigned)wblocks, 256, smem_w, st>>>(d_gi, w_ih, N, nullptr, 0.f, dx);
+    int ob = int((N + 511) / 512);
     if (ob > 296) ob = 296;
     if (ob < 1) ob = 1;
-    gates_outer_kernel<<<ob, 256, 0, st>>>(d_gi, x, N, Pg);
+    gates_outer_kernel<<<ob, GO_THREADS, 0, st>>>(d_gi, x, N, Pg);
     gates_outer_reduce_kernel<<<(G3 * (HD + 1) + 255) / 256, 256, 0, st>>>(Pg, ob, dw_ih, db_ih);
     // state side: dW_hh = d_gh^T h_prev (zero without a state), d b_hh = column sums of d_gh, dh_prev = dh*z + d_gh W_hh
-    gates_outer_kernel<<<ob, 256, 0, st>>>(d_gh, h_prev, N, Pg);
+    gates_outer_kernel<<<ob, GO_THREADS, 0, st>>>(d_gh, h_prev, N, Pg);
     gates_outer_reduce_kernel<<<(G3 * (HD + 1) + 255) / 256, 256, 0, st>>>(Pg, ob, dw_hh, db_hh);
     g_launches += 7;
     if (h_prev) {
-        gates_times_w_kernel<<<(unsigned)blocks, 256, smem_w, st>>>(d_gh, w_hh, N, dh_prev, 1.f, dh_prev);
+        gates_times_w_kernel<<<(unsigned)wblocks, 256, smem_w, st>>>(d_gh, w_hh, N, dh_prev, 1.f, dh_prev);
         g_launches += 1;
     }
     GNNFD_LAUNCH_CHECK();
