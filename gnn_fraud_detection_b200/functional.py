@@ -313,10 +313,10 @@ def in_prepare(W, K, xmax, prep):
 class InAttention:
     """What the input-space forward saves for the backward: ``alpha [E',H]`` (CSR order, normalised, before dropout; sign bit =
     LeakyReLU negative region), ``jflag [E']`` (source id | row-end flag), ``rowmax`` / ``rowsum [n_dst,H]``."""
-    __slots__ = ("alpha", "jflag", "rowmax", "rowsum", "a_src", "a_dst")
+    __slots__ = ("alpha", "jflag", "rowmax", "rowsum")
 
-    def __init__(self, alpha, jflag, rowmax, rowsum, a_src, a_dst):
-        self.alpha, self.jflag, self.rowmax, self.rowsum, self.a_src, self.a_dst = alpha, jflag, rowmax, rowsum, a_src, a_dst
+    def __init__(self, alpha, jflag, rowmax, rowsum):
+        self.alpha, self.jflag, self.rowmax, self.rowsum = alpha, jflag, rowmax, rowsum
 
 
 def in_fwd(g: GraphCSR, x, a_src, a_dst, negative_slope, prep, keep_mask=None, p_drop=0.0, seed=0):
@@ -336,7 +336,7 @@ def in_fwd(g: GraphCSR, x, a_src, a_dst, negative_slope, prep, keep_mask=None, p
                               float(negative_slope), _abi.ptr(keep_mask), float(p_drop), int(seed), prep.data_ptr(),
                               zimg.data_ptr(), rowmax.data_ptr(), rowsum.data_ptr(), alpha.data_ptr(), jflag.data_ptr(),
                               ws.data_ptr(), ws.numel(), _stream()))
-    return zimg, InAttention(alpha, jflag, rowmax, rowsum, a_src, a_dst)
+    return zimg, InAttention(alpha, jflag, rowmax, rowsum)
 
 
 def in_out(zimg, n, K, prep, bias, act=_abi.ACT_NONE, post_scale=None, post_shift=None, residual=None):
@@ -448,7 +448,8 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
             zimg, att = in_fwd(g, x, a_src, a_dst, negative_slope, prep, keep_mask, p_drop, seed)
             out = in_out(zimg, g.n_dst, K, prep, bias)
         rowmax, rowsum = att.rowmax, att.rowsum
-        ctx.save_for_backward(x, W, a_s, a_d, a_src, a_dst, rowmax, rowsum, att.alpha, att.jflag, keep_mask, zimg, prep)
+        # the backward needs neither logits nor row statistics: alpha / jflag carry everything (see gnnfd_in_fwd)
+        ctx.save_for_backward(x, W, a_s, a_d, rowmax, rowsum, att.alpha, att.jflag, keep_mask, zimg, prep)
         ctx.g, ctx.slope, ctx.p, ctx.seed = g, negative_slope, p_drop, seed
         ctx.has_bias = bias is not None
         ctx.att_shape = att_src.shape
@@ -459,7 +460,7 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, *unused):
-        x, W, a_s, a_d, a_src, a_dst, rowmax, rowsum, alpha, jflag, keep_mask, zimg, prep = ctx.saved_tensors
+        x, W, a_s, a_d, rowmax, rowsum, alpha, jflag, keep_mask, zimg, prep = ctx.saved_tensors
         g = ctx.g
         if not g.has_csc:
             raise RuntimeError("backward needs the CSC twin; build the graph with build_csc=True")
@@ -467,7 +468,7 @@ class GATConvInputSpaceFunction(torch.autograd.Function):
             raise RuntimeError("the input-space formulation computes no gradient w.r.t. x (first layer only)")
         d_out = d_out.contiguous().float()
         with torch.cuda.device(x.device):
-            att = InAttention(alpha, jflag, rowmax, rowsum, a_src, a_dst)
+            att = InAttention(alpha, jflag, rowmax, rowsum)
             dz, da_dst = in_bwd_edges(g, x, att, d_out, prep, ctx.slope, keep_mask, ctx.p, seed=ctx.seed)
             da_src = in_dasrc(g, dz)
             dW, datt_src, datt_dst, dbias = in_bwd_params(zimg, d_out, x, W, a_s, a_d, da_src, da_dst, prep)
